@@ -1,0 +1,137 @@
+"""The oracle (oracle/mxint8_oracle.py) against outputs of the unmodified reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py) and against the reference's
+own known-answer vectors.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mxint8_oracle as O
+
+CASES = ["deit_small", "dit_small", "dit_bf16", "pixart_flush", "deit_edges", "deit_tiny_c1"]
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    d = {k: torch.from_numpy(z[k].astype(np.int64) if z[k].dtype == np.int16 else z[k]) for k in z.files}
+    B, H, N, hd, top_k, bfloat, flush = (int(x) for x in z["meta"])
+    return d, dict(B=B, H=H, N=N, hd=hd, top_k=top_k, bfloat=bfloat, flush=bool(flush))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_quantizer_bit_exact(golden_dir, name):
+    d, m = load(golden_dir, name)
+    qc, qe = O.quantize_mxint8(d["q"], 32, m["bfloat"], m["flush"])
+    assert torch.equal(O.dequantize_mxint8(qc, qe), d["MX_Q"])
+    assert torch.equal(O.predictor_exponents(qc, qe).to(torch.float32), d["shared_exp_Q"])
+    assert int(qc.to(torch.int32).abs().max()) <= 127
+    if "MX_K" in d:
+        kc, ke = O.quantize_mxint8(d["k"], 32, m["bfloat"], m["flush"])
+        assert torch.equal(O.dequantize_mxint8(kc, ke), d["MX_K"])
+        assert torch.equal(O.predictor_exponents(kc, ke).to(torch.float32), d["shared_exp_K"])
+
+
+@pytest.mark.parametrize("name", CASES[:-1])
+def test_predictor_bit_exact(golden_dir, name):
+    d, m = load(golden_dir, name)
+    qc, qe = O.quantize_mxint8(d["q"], 32, m["bfloat"], m["flush"])
+    kc, ke = O.quantize_mxint8(d["k"], 32, m["bfloat"], m["flush"])
+    assert torch.equal(O.exponent_based_sign(qc, qe), d["approx_Q"])
+    assert torch.equal(O.exponent_based_sign(kc, ke), d["approx_K"])
+    s_int = O.pred_scores_integer(qc, qe, kc, ke)
+    s_mm = O.pred_scores_matmul(qc, qe, kc, ke)
+    assert torch.equal(s_mm, d["pred_scores"])
+    # block-exact integer formula (what the CUDA kernel computes): bit-equal to the reference
+    # wherever the reference's own fp32 sum is order-independent; elsewhere parity is unpinned
+    ok = O.pred_window_ok(O.predictor_exponents(qc, qe), O.predictor_exponents(kc, ke),
+                          O.block_widths(m["hd"]))
+    assert torch.equal(s_int[ok], d["pred_scores"][ok])
+    if name not in ("pixart_flush", "deit_edges"):      # no all-zero blocks there
+        assert bool(ok.all())
+    assert float(ok.float().mean()) > 0.95
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_topk_and_output(golden_dir, name):
+    d, m = load(golden_dir, name)
+    r = O.pruned_attention(d["q"], d["k"], d["v"], m["top_k"], bfloat=m["bfloat"], flush=m["flush"])
+    assert torch.equal(r["idx"], d["idx"])                       # canonical sets AND order
+    words = O.idx_to_mask_words(r["idx"], m["N"])
+    dense = O.mask_words_to_dense(words, m["N"])
+    assert int(dense.sum()) == m["B"] * m["H"] * m["N"] * m["top_k"]
+    # raw torch.topk (tie order unspecified): same k-th value, same strictly-greater set
+    pred = r["pred_scores"]
+    kth = pred.gather(-1, d["idx"][..., -1:])
+    kth_t = pred.gather(-1, d["topk_idx_torch"][..., -1:])
+    assert torch.equal(kth, kth_t)
+    gt = pred > kth
+    assert bool((dense | ~gt).all())
+    t_dense = torch.zeros_like(dense)
+    t_dense.scatter_(-1, d["topk_idx_torch"], True)
+    assert bool((t_dense | ~gt).all())
+    # fp32 stages: stated tolerance 1e-3 of the reference's max-abs (north star)
+    ref_vals, ref_out = d["true_vals"], d["out"]
+    assert float((r["true_vals"] - ref_vals).abs().max()) <= 1e-5 * float(ref_vals.abs().max())
+    assert float((r["out"] - ref_out).abs().max()) <= 1e-3 * float(ref_out.abs().max())
+
+
+def test_log2_boundary_exponents(golden_dir):
+    z = np.load(os.path.join(golden_dir, "quantizer_log2_boundary.npz"))
+    x, ref = torch.from_numpy(z["x"]), torch.from_numpy(z["MX"])
+    c, e = O.quantize_mxint8(x)
+    assert torch.equal(O.dequantize_mxint8(c, e), ref)
+    # the table itself, re-derived from this machine's torch.log2 (what mx_ops.py:93-97 calls)
+    for n in range(-125, 128):
+        js = np.arange(1, 64, dtype=np.int64)
+        bits = (((n - 1 + 127) << 23) | (2 ** 23 - js)).astype(np.uint32)
+        xs = torch.from_numpy(bits.view(np.float32).copy())
+        ref_e = torch.floor(torch.log2(xs)).to(torch.int32)
+        assert torch.equal(O.shared_exponent_from_absmax(xs), ref_e), n
+
+
+def test_bf16_half_away_kat():
+    # microxscaling/mx/tests/test_corners_elemwise.py:137-144 pins "nearest" == half away
+    x = torch.tensor([1.0 + 2 ** -8, 1.0 + 2 ** -7 + 2 ** -8, -(1.0 + 2 ** -8), 1.0 + 2 ** -9], dtype=torch.float32)
+    y = O.bf16_round_half_away(x)
+    exp = torch.tensor([1.0 + 2 ** -7, 1.0 + 2 ** -6, -(1.0 + 2 ** -7), 1.0], dtype=torch.float32)
+    assert torch.equal(y, exp)
+
+
+def test_mxint8_hw_kat():
+    """Known-answer vectors of microxscaling/mx/tests/test_corners_mx.py:83-124
+    (test_mx_hw_test: int8, block 10, round nearest)."""
+    x = np.array([
+        [1.0] * 10,
+        [1.0] * 5 + [2.0] * 5,
+        [-1.0] * 5 + [-2.0] * 5,
+        [1.0] * 5 + [-2.0] * 5,
+        [1.015625, 1.0234375, 1.03125, 1.0390625, 1.25, 1.2578125, 1.9375, 1.9453125, 1.984375, 1.9921875],
+        [-1.984375, -1.9765625, -1.96875, -1.9609375, -1.9375, -1.9296875, -1.75, -1.7421875, -1.0, -1.9921875],
+        [1.99609375, 1.98828125, 0.0, 0.00390625, 0.0078125, 0.01171875, -0.015625, -0.01171875, -0.0078125,
+         -0.00390625]], dtype=np.float32)
+    y = np.array([
+        [1.0] * 10,
+        [1.0] * 5 + [2.0] * 5,
+        [-1.0] * 5 + [-2.0] * 5,
+        [1.0] * 5 + [-2.0] * 5,
+        [1.015625, 1.03125, 1.03125, 1.046875, 1.25, 1.265625, 1.9375, 1.953125, 1.984375, 1.984375],
+        [-1.984375, -1.984375, -1.96875, -1.96875, -1.9375, -1.9375, -1.75, -1.75, -1.0, -1.984375],
+        [1.984375, 1.984375, 0.0, 0.0, 0.015625, 0.015625, -0.015625, -0.015625, -0.015625, 0.0]], dtype=np.float32)
+    c, e = O.quantize_mxint8(torch.from_numpy(x), block=10)
+    assert torch.equal(O.dequantize_mxint8(c, e, block=10), torch.from_numpy(y))
+
+
+def test_scatter_script_kat():
+    """funcs/test_scatter.py (np seed 0, 200x128, block 32) prints
+    'S_meta range: [-184.000, 180.000]', 'S_meta zeros: 1707/40000',
+    'S_meta negatives: 19064/40000' for sum_b 2^(eq+ek) * <sign_q, sign_k>_b  (:156-174)."""
+    np.random.seed(0)
+    Q = torch.from_numpy(np.random.randn(200, 128)).float()
+    K = torch.from_numpy(np.random.randn(200, 128)).float()
+    qc, qe = O.quantize_mxint8(Q)
+    kc, ke = O.quantize_mxint8(K)
+    S = O.pred_scores_integer(qc, qe, kc, ke)
+    assert float(S.min()) == -184.0 and float(S.max()) == 180.0
+    assert int((S == 0).sum()) == 1707
+    assert int((S < 0).sum()) == 19064
