@@ -1,0 +1,154 @@
+/*
+ * mxprune.h - C ABI of libmxprune.so: the MXINT8 exponent-sign pruned-attention hot path
+ * of d9bjo0522/mx_quantization, rebuilt as sm_100a CUDA.
+ *
+ * Every entry point is `extern "C"`, takes raw DEVICE pointers, explicit element strides and a
+ * CUDA stream (passed as void*, i.e. a cudaStream_t), allocates nothing, never synchronises the
+ * host and keeps no device state.  Work is enqueued asynchronously on `stream`, like the
+ * PyTorch ops it replaces.  Return value: 0 on success, <0 on error (MXP_E_*); the message of the
+ * last error on the calling thread is available from mxp_last_error().
+ *
+ * Tensors named q/k/v/x/out are fp32 "(B,H,N,hd)" views: element (b,h,n,d) lives at
+ * ptr[b*sB + h*sH + n*sN + d] (strides in ELEMENTS, innermost stride 1).  This covers the three
+ * layouts the reference's attention modules produce:
+ *   - fused qkv buffer, permuted view   workloads/deit/scripts/main.py:87-88, DiT models.py:156-157
+ *   - separate (B,N,H*hd) projections   workloads/PixArt/models/MX_transformer_block.py:637-639
+ *   - plain contiguous (B,H,N,hd)       benchmarks / tests
+ * Requirements: hd % 4 == 0, 4 <= hd <= 128, base pointers and row strides 16-byte aligned.
+ *
+ * Compact MXINT8 format shared by all entry points:
+ *   code  int8  in [-127,127]   (sign-magnitude semantics; -128 never produced)
+ *   exp   int8  in [-127,127]   one per 32 elements of head_dim; -126 marks an all-zero block
+ *   value = code * 2^(exp-6);   predictor value = (code<0 ? -1 : +1) * 2^exp
+ *
+ * mx_specs (microxscaling/mx/specs.py:61-181) reaches this ABI as two integers:
+ *   bfloat_bits  16 or 32   mx_specs["bfloat"]  (bf16 pre-rounding, half away from zero)
+ *   flush        0 or 1     mx_specs["mx_flush_fp32_subnorms"]
+ * every other key is validated host-side to the only combination on the path
+ * (int8 / block 32 / round nearest / shared_exp max / scale_bits 8).
+ */
+#ifndef MXPRUNE_H_
+#define MXPRUNE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXP_ABI_VERSION 1
+
+#define MXP_OK             0
+#define MXP_E_BADARG      -1   /* null pointer, bad shape/stride/alignment, k out of range */
+#define MXP_E_UNSUPPORTED -2   /* shape outside what the kernels cover (see mxp_limits)     */
+#define MXP_E_CUDA        -3   /* launch / runtime error reported by CUDA                   */
+
+int mxp_abi_version(void);
+const char* mxp_last_error(void);           /* thread-local, never NULL */
+
+/* Largest key count and head_dim the kernels accept. */
+void mxp_limits(int* max_keys, int* max_head_dim);
+
+/*
+ * MX block quantizer.  Replaces
+ *   quantize_mx_op(quantize_elemwise_op(x, mx_specs, round), mx_specs, elem_format="int8",
+ *                  axes=[-1], round="nearest")
+ *   microxscaling/mx/mx_ops.py:309-341 (+ :180-306), elemwise_ops.py:243-277
+ * but emits the integer codes/exponents instead of fake-quantised fp32.
+ *   codes  int8  [B,H,N,hd]  contiguous           (required)
+ *   exps   int8  [B,H,N,nb]  nb = ceil(hd/32)     (required)
+ *   signs  u32   [B,H,N,nb]  bit d of word b = (code[b*32+d] < 0); may be NULL
+ */
+int mxp_quantize_mxint8(const float* x, int64_t sB, int64_t sH, int64_t sN,
+                        int B, int H, int N, int hd, int bfloat_bits, int flush,
+                        int8_t* codes, int8_t* exps, uint32_t* signs, void* stream);
+
+/*
+ * Dense exponent-sign approximation, (code<0 ? -1 : +1) * 2^exp per element, fp32 contiguous
+ * [B,H,N,hd].  Replaces funcs.exponent_approximation(Q,K,mx_specs).exponent_based_sign()
+ *   funcs/exponent_based_prediction.py:12-38,44-94 (call once per tensor).
+ * Parity / debugging aid: the fused kernels never materialise this.
+ */
+int mxp_exp_sign_approx(const float* x, int64_t sB, int64_t sH, int64_t sN,
+                        int B, int H, int N, int hd, int bfloat_bits, int flush,
+                        float* approx, void* stream);
+
+/*
+ * Dense predicted scores, fp32 contiguous [B,H,Nq,Nk]:
+ *   score[i,j] = sum_b 2^(eq[i,b]+ek[j,b]) * (n_b - 2*popc(sq[i,b]^sk[j,b]))
+ * Replaces `pred_scores = ex_quant_q @ ex_quant_k.transpose(-2,-1)`
+ *   workloads/deit/scripts/main.py:118, DiT models.py:186, MX_transformer_block.py:673.
+ * Parity aid (O(N^2) output); the product path is mxp_predict_topk.
+ */
+int mxp_predict_scores(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                       const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                       int B, int H, int Nq, int Nk, int hd, int bfloat_bits, int flush,
+                       float* scores, void* stream);
+
+/*
+ * Fused quantize + exponent-sign predictor + per-row top-k.  Q and K are read once; the
+ * Nq x Nk score matrix is never written.  Replaces lines 107-123 of
+ * workloads/deit/scripts/main.py (exponent_approximation ctor, exponent_based_sign, `@`,
+ * torch.topk) and the same sequence in DiT models.py:178-194 /
+ * PixArt MX_transformer_block.py:659-678.
+ * Tie rule: descending score, ascending key index (first top_k of a stable descending sort).
+ *   mask     u32 [B,H,Nq,ceil(Nk/32)]  bit (j%32) of word j/32 set iff key j is kept (required)
+ *   idx      i32 [B,H,Nq,top_k]        kept keys in ascending key order; may be NULL
+ *   q_codes  int8 [B,H,Nq,hd], q_exps int8 [B,H,Nq,nb]   may be NULL (both or neither)
+ *   k_codes  int8 [B,H,Nk,hd], k_exps int8 [B,H,Nk,nb]   may be NULL (both or neither)
+ * workspace: mxp_predict_topk_workspace_bytes() bytes of device memory (may be NULL if 0).
+ */
+size_t mxp_predict_topk_workspace_bytes(int B, int H, int Nq, int Nk, int hd);
+int mxp_predict_topk(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                     const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                     int B, int H, int Nq, int Nk, int hd, int top_k,
+                     int bfloat_bits, int flush,
+                     uint32_t* mask, int32_t* idx,
+                     int8_t* q_codes, int8_t* q_exps, int8_t* k_codes, int8_t* k_exps,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Exact MXINT8 attention over the kept keys.  Replaces
+ *   true_scores = mx.matmul(q, k^T) * scale ; vals = gather(idx) ; softmax ; scatter_ ;
+ *   x = mx.matmul(attn, v)            workloads/deit/scripts/main.py:101-102,124,147-152
+ * given Q/K already in compact form and the row bitmask of kept keys.  V (fp32) is quantised
+ * along TOKENS in blocks of 32 (microxscaling/mx/matmul.py:76-83, axes=[-2]); P is quantised
+ * along keys in 32-aligned windows of original key positions.
+ *   out  fp32 (B,H,Nq,hd) view with element strides o_sB,o_sH,o_sN (innermost 1)
+ */
+size_t mxp_sparse_attention_workspace_bytes(int B, int H, int Nq, int Nk, int hd);
+int mxp_sparse_attention(const int8_t* q_codes, const int8_t* q_exps,
+                         const int8_t* k_codes, const int8_t* k_exps,
+                         const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                         const uint32_t* mask,
+                         int B, int H, int Nq, int Nk, int hd,
+                         float scale, int bfloat_bits, int flush,
+                         float* out, int64_t o_sB, int64_t o_sH, int64_t o_sN,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The whole path in one call: q,k,v -> out.  Replaces lines 101-152 of
+ * workloads/deit/scripts/main.py (and DiT models.py:168-225, PixArt
+ * MX_transformer_block.py:647-710) for mx_quant && top_k && approx_flag && pred_mode=="ex_pred".
+ *   mask_out  optional u32 [B,H,Nq,ceil(Nk/32)] copy of the kept-key bitmask (may be NULL)
+ * workspace: mxp_pruned_attention_workspace_bytes() bytes, 256-byte aligned.
+ */
+size_t mxp_pruned_attention_workspace_bytes(int B, int H, int Nq, int Nk, int hd);
+int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                         const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                         const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                         int B, int H, int Nq, int Nk, int hd, int top_k,
+                         float scale, int bfloat_bits, int flush,
+                         float* out, int64_t o_sB, int64_t o_sH, int64_t o_sN,
+                         uint32_t* mask_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernel launches the last successful call on this thread enqueued (bench.py's
+ * gpu_launches claim is counted from this). */
+int mxp_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MXPRUNE_H_ */

@@ -1,0 +1,17 @@
+"""mx_quantization_b200 - the MXINT8 exponent-sign pruned-attention hot path of
+d9bjo0522/mx_quantization as hand-written sm_100a CUDA behind a C ABI (include/mxprune.h).
+
+Public API (mirrors the reference's operator interface for this path):
+    exponent_approximation(Q, K, mx_specs).exponent_based_sign()
+    pruned_attention(q, k, v, mx_specs, top_k, scale=None, return_mask=False)
+    predict_topk / sparse_attention / quantize_mxint8 / predict_scores / exp_sign_approx
+    modules.QuantizedAttentionCore / DeiT, DiT, PixArt attention shims
+"""
+from .ops import (exp_sign_approx, last_launch_count, limits, predict_scores, predict_topk,  # noqa: F401
+                  pruned_attention, quantize_mxint8, sparse_attention)
+from .predictor import exponent_approximation  # noqa: F401
+from .specs import PathSpecs, resolve_specs  # noqa: F401
+
+__all__ = ["exponent_approximation", "pruned_attention", "predict_topk", "sparse_attention",
+           "quantize_mxint8", "predict_scores", "exp_sign_approx", "resolve_specs", "PathSpecs",
+           "limits", "last_launch_count"]

@@ -1,0 +1,799 @@
+// libmxprune: MXINT8 exponent-sign pruned attention for sm_100a behind the C ABI of
+// include/mxprune.h.  See DESIGN.md for the data layout and the roofline of each kernel.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "mxprune.h"
+#include "mxprune_device.cuh"
+
+using namespace mxp;
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// host-side error plumbing
+// ------------------------------------------------------------------------------------
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MXP_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    ++g_launches;
+    return MXP_OK;
+}
+
+constexpr int MAX_HD = 128;
+constexpr int MAX_KEYS_FUSED = 256;   // keys held in registers, 8 per lane
+
+struct View {   // fp32 (B,H,N,hd) view, element strides
+    const float* p;
+    int64_t sB, sH, sN;
+};
+
+int check_view(const char* name, const float* p, int64_t sB, int64_t sH, int64_t sN, int hd) {
+    if (!p) return fail(MXP_E_BADARG, "%s: null pointer", name);
+    if (((uintptr_t)p & 15) || (sB & 3) || (sH & 3) || (sN & 3))
+        return fail(MXP_E_BADARG, "%s: base pointer and strides must be 16-byte aligned", name);
+    if (sN < hd) return fail(MXP_E_BADARG, "%s: row stride %lld < head_dim %d", name, (long long)sN, hd);
+    return MXP_OK;
+}
+
+int check_shape(int B, int H, int Nq, int Nk, int hd, int bfloat_bits) {
+    if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return fail(MXP_E_BADARG, "empty shape B=%d H=%d Nq=%d Nk=%d", B, H, Nq, Nk);
+    if (hd < 4 || hd > MAX_HD || (hd & 3)) return fail(MXP_E_UNSUPPORTED, "head_dim %d: need a multiple of 4 in [4,%d]", hd, MAX_HD);
+    if (bfloat_bits != 16 && bfloat_bits != 32) return fail(MXP_E_UNSUPPORTED, "bfloat=%d: only 16 or 32 are on the path", bfloat_bits);
+    if ((int64_t)B * H > 0x7fffffffLL) return fail(MXP_E_UNSUPPORTED, "B*H too large");
+    return MXP_OK;
+}
+
+inline int row_splits(int heads, int Nq) {
+    // enough CTAs for ~4 per SM when B*H is small; 1 when the grid is already large
+    const int want = 148 * 4;
+    int s = (want + heads - 1) / heads;
+    const int max_s = (Nq + WARPS * 4 - 1) / (WARPS * 4);   // >= 4 rows per warp: staging is per CTA
+    if (s > max_s) s = max_s;
+    return s < 1 ? 1 : s;
+}
+
+// ------------------------------------------------------------------------------------
+// K0a: standalone quantizer (codes / exps / sign words), one warp per row
+// ------------------------------------------------------------------------------------
+template <bool APPROX>
+__global__ void __launch_bounds__(THREADS)
+k_quantize(View x, int rows_per_bh, int H, int64_t total_rows, int hd, int bf16, int flush,
+           int8_t* __restrict__ codes, int8_t* __restrict__ exps, uint32_t* __restrict__ signs,
+           float* __restrict__ approx) {
+    const int lane = threadIdx.x & 31;
+    const int nb = (hd + 31) >> 5;
+    for (int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); row < total_rows;
+         row += (int64_t)gridDim.x * WARPS) {
+        const int64_t bh = row / rows_per_bh;
+        const int n = (int)(row - bh * rows_per_bh);
+        const float* xr = x.p + (bh / H) * x.sB + (bh % H) * x.sH + (int64_t)n * x.sN;
+        for (int b = 0; b < nb; ++b) {
+            const int d = b * 32 + lane;
+            const float v = d < hd ? __ldg(xr + d) : 0.f;
+            int e, ep;
+            const int c = quantize_block_warp(v, bf16, flush, e, ep);
+            const uint32_t sw = __ballot_sync(FULL, c < 0);
+            if (APPROX) {
+                if (d < hd) approx[row * hd + d] = c < 0 ? -exp2i(ep) : exp2i(ep);
+            } else {
+                if (d < hd) codes[row * hd + d] = (int8_t)c;
+                if (lane == 0) {
+                    exps[row * nb + b] = (int8_t)e;
+                    if (signs) signs[row * nb + b] = sw;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Predictor parameters
+// ------------------------------------------------------------------------------------
+struct PredParams {
+    View q, k;
+    int B, H, Nq, Nk, hd, top_k, bf16, flush;
+    uint32_t* mask;
+    int32_t* idx;
+    int8_t *q_codes, *q_exps, *k_codes, *k_exps;
+    float* scores;   // dense debug output (k_predict_scores only)
+};
+
+// Quantize the Nk key rows of one head into shared memory: sign words + 2^e weights.
+// All warps of the CTA cooperate, one row per warp per step.
+template <int NB>
+__device__ __forceinline__ void stage_keys(const PredParams& p, int head, int nkp,
+                                           uint32_t* s_ksign, float* s_kw, bool write_k) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bb = head / p.H, hh = head % p.H;
+    const float* kb = p.k.p + bb * p.k.sB + hh * p.k.sH;
+    for (int j = warp; j < nkp; j += WARPS) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int d = b * 32 + lane;
+            const float x = (j < p.Nk && d < p.hd) ? __ldg(kb + (int64_t)j * p.k.sN + d) : 0.f;
+            int e, ep;
+            const int c = quantize_block_warp(x, p.bf16, p.flush, e, ep);
+            const uint32_t sw = __ballot_sync(FULL, c < 0);
+            if (lane == 0) {
+                s_ksign[b * nkp + j] = sw;
+                s_kw[b * nkp + j] = j < p.Nk ? exp2i(ep) : 0.f;
+            }
+            if (write_k && j < p.Nk) {
+                const int64_t row = (int64_t)head * p.Nk + j;
+                if (d < p.hd) p.k_codes[row * p.hd + d] = (int8_t)c;
+                if (lane == 0) p.k_exps[row * NB + b] = (int8_t)e;
+            }
+        }
+    }
+}
+
+// Quantize one query row held by a warp: warp-uniform sign words and 2^e weights.
+template <int NB>
+__device__ __forceinline__ void quantize_query_row(const PredParams& p, const float* qrow,
+                                                   int64_t row, bool write_q,
+                                                   uint32_t (&sq)[NB], float (&wq)[NB]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int d = b * 32 + lane;
+        const float x = d < p.hd ? __ldg(qrow + d) : 0.f;
+        int e, ep;
+        const int c = quantize_block_warp(x, p.bf16, p.flush, e, ep);
+        sq[b] = __ballot_sync(FULL, c < 0);
+        wq[b] = exp2i(ep);
+        if (write_q) {
+            if (d < p.hd) p.q_codes[row * p.hd + d] = (int8_t)c;
+            if (lane == 0) p.q_exps[row * NB + b] = (int8_t)e;
+        }
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ float block_width_const(int b, int hd) {
+    // 2^24 + n_b  (n_b = real dims in block b), exactly representable since n_b is even
+    const int nb_w = (b < NB - 1) ? 32 : hd - 32 * (NB - 1);
+    return 16777216.0f + (float)nb_w;
+}
+
+// score = sum_b 2^(eq_b + ek_b) * (n_b - 2 popc(sq_b ^ sk_b)), accumulated over b ascending in
+// fp32 (every product is exact; the sum is exact inside a 24-bit window - SURVEY 8a note ii).
+template <int NB>
+__device__ __forceinline__ float pred_score(const uint32_t (&sk)[NB], const float (&wk)[NB],
+                                            const uint32_t (&sq)[NB], const float (&wq)[NB],
+                                            const float (&c24)[NB]) {
+    float s = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const float cnt = signed_count(__popc(sk[b] ^ sq[b]), c24[b]);
+        const float t = wk[b] * cnt;
+        s = (b == 0) ? t * wq[0] : fmaf(t, wq[b], s);
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------
+// K1 (fused, Nk <= 256): quantize K -> smem -> registers; per query row: quantize, score all
+// keys (XOR + POPC), exact radix select of the top_k-th key in registers, emit the row bitmask.
+// One CTA per (head, row split); one warp per query row; lane l owns keys l, l+32, ...
+// ------------------------------------------------------------------------------------
+template <int NB, int KPL>
+__global__ void __launch_bounds__(THREADS)
+k_predict_topk_fused(const PredParams p) {
+    constexpr int NKP = KPL * 32;
+    __shared__ uint32_t s_ksign[NB * NKP];
+    __shared__ float s_kw[NB * NKP];
+    const int head = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Nk = p.Nk, Nq = p.Nq;
+
+    stage_keys<NB>(p, head, NKP, s_ksign, s_kw, p.k_codes != nullptr && blockIdx.y == 0);
+    __syncthreads();
+
+    uint32_t ks[KPL][NB];
+    float kw[KPL][NB];
+#pragma unroll
+    for (int r = 0; r < KPL; ++r)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            ks[r][b] = s_ksign[b * NKP + r * 32 + lane];
+            kw[r][b] = s_kw[b * NKP + r * 32 + lane];
+        }
+    float c24[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) c24[b] = block_width_const<NB>(b, p.hd);
+
+    const int bb = head / p.H, hh = head % p.H;
+    const float* qb = p.q.p + bb * p.q.sB + hh * p.q.sH;
+    const int NW = (Nk + 31) >> 5;
+    const int kk = p.top_k;
+
+    for (int i = blockIdx.y * WARPS + warp; i < Nq; i += WARPS * gridDim.y) {
+        const int64_t row = (int64_t)head * Nq + i;
+        uint32_t sq[NB];
+        float wq[NB];
+        quantize_query_row<NB>(p, qb + (int64_t)i * p.q.sN, row, p.q_codes != nullptr, sq, wq);
+
+        // ---- scores as order-preserving u32 keys, 0 for lanes past Nk
+        uint32_t u[KPL];
+        uint32_t aor = 0u, aand = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+            const float s = pred_score<NB>(ks[r], kw[r], sq, wq, c24);
+            const bool valid = r * 32 + lane < Nk;
+            u[r] = valid ? ordered_key(s) : 0u;
+            aor |= u[r];
+            aand &= valid ? u[r] : 0xffffffffu;
+        }
+        aor = __reduce_or_sync(FULL, aor);
+        aand = __reduce_and_sync(FULL, aand);
+
+        // ---- exact radix select: T = top_k-th largest key.  Only bit positions that differ
+        // between keys need a counting pass (bits set in every key stay set, bits clear in
+        // every key stay clear).
+        uint32_t T = aand, vary = aor & ~aand;
+        while (vary) {
+            const uint32_t m1 = 1u << (31 - __clz(vary));
+            vary ^= m1;
+            const uint32_t cand = T | m1;
+            int c = 0;
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) c += (u[r] >= cand) ? 1 : 0;
+            c = __reduce_add_sync(FULL, c);
+            if (c >= kk) T = cand;
+        }
+
+        // ---- row bitmask: every key > T, plus the lowest-index keys == T up to top_k
+        uint32_t ge[KPL], gt[KPL];
+        int ngt = 0;
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+            ge[r] = __ballot_sync(FULL, u[r] >= T);
+            gt[r] = __ballot_sync(FULL, u[r] > T);
+            ngt += __popc(gt[r]);
+        }
+        int rem = kk - ngt;
+        uint32_t myword = 0u;
+        int mybase = 0, base = 0;
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+            const uint32_t eq = ge[r] & ~gt[r];
+            const int c = __popc(eq);
+            uint32_t take;
+            if (c <= rem) { take = eq; rem -= c; }
+            else { take = keep_lowest_bits(eq, rem); rem = 0; }
+            const uint32_t w = gt[r] | take;
+            if (lane == r) myword = w;
+            if (p.idx) {
+                if ((w >> lane) & 1u)
+                    p.idx[row * kk + base + __popc(w & ((1u << lane) - 1u))] = r * 32 + lane;
+                base += __popc(w);
+            }
+        }
+        (void)mybase;
+        if (lane < NW) p.mask[row * NW + lane] = myword;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K1-debug: dense predicted scores (parity aid).  Same staging and scoring code.
+// ------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(THREADS)
+k_predict_scores(const PredParams p, int nkp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_ksign = reinterpret_cast<uint32_t*>(smem_raw);
+    float* s_kw = reinterpret_cast<float*>(s_ksign + NB * nkp);
+    const int head = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    stage_keys<NB>(p, head, nkp, s_ksign, s_kw, false);
+    __syncthreads();
+    float c24[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) c24[b] = block_width_const<NB>(b, p.hd);
+    const int bb = head / p.H, hh = head % p.H;
+    const float* qb = p.q.p + bb * p.q.sB + hh * p.q.sH;
+    for (int i = blockIdx.y * WARPS + warp; i < p.Nq; i += WARPS * gridDim.y) {
+        const int64_t row = (int64_t)head * p.Nq + i;
+        uint32_t sq[NB];
+        float wq[NB];
+        quantize_query_row<NB>(p, qb + (int64_t)i * p.q.sN, row, false, sq, wq);
+        for (int j = lane; j < p.Nk; j += 32) {
+            uint32_t sk[NB];
+            float wk[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) { sk[b] = s_ksign[b * nkp + j]; wk[b] = s_kw[b * nkp + j]; }
+            p.scores[row * p.Nk + j] = pred_score<NB>(sk, wk, sq, wq, c24) + 0.0f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K2 (Nk <= 256): exact MXINT8 attention over the kept keys of each row.
+// One CTA per (head, row split).  Staged once per CTA in shared memory:
+//   s_kt   [hd/4][NKP+1] u32   K codes, word c of key j (4 consecutive dims)
+//   s_kwf  [NB][NKP]     f32   2^(ek-6)
+//   s_v    [KPL][2][hd]  16 B  V codes quantised along TOKENS: window r, half, column d ->
+//                              16 consecutive tokens of column d (dp4a runs along tokens)
+//   s_vef  [KPL][hd]     f32   2^(eV-6) per (token window, column)
+//   s_p    [WARPS][NKP]  u8    P codes of the row a warp is working on, dense key positions
+// One warp per query row; lane l owns key positions l, l+32, ... = one P window per step.
+// ------------------------------------------------------------------------------------
+struct AttnParams {
+    const int8_t *q_codes, *q_exps, *k_codes, *k_exps;
+    View v;
+    const uint32_t* mask;
+    int B, H, Nq, Nk, hd;
+    float scale;
+    int bf16, flush;
+    float* out;
+    int64_t o_sB, o_sH, o_sN;
+};
+
+struct AttnSmem {
+    int kt_stride;      // NKP + 1
+    size_t off_kwf, off_vef, off_v, off_p, total;
+};
+
+__host__ __device__ inline AttnSmem attn_smem_layout(int nb, int kpl, int hd) {
+    AttnSmem L;
+    const int nkp = kpl * 32, hw = hd >> 2;
+    L.kt_stride = nkp + 1;
+    size_t o = (size_t)hw * L.kt_stride * 4;
+    L.off_kwf = o; o += (size_t)nb * nkp * 4;
+    L.off_vef = o; o += (size_t)kpl * hd * 4;
+    o = (o + 15) & ~(size_t)15;
+    L.off_v = o;   o += (size_t)kpl * 2 * hd * 16;
+    L.off_p = o;   o += (size_t)WARPS * nkp;
+    L.total = o;
+    return L;
+}
+
+template <int NB, int KPL>
+__global__ void __launch_bounds__(THREADS)
+k_sparse_attention(const AttnParams p) {
+    constexpr int NKP = KPL * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int hd = p.hd, HW = hd >> 2, Nk = p.Nk, Nq = p.Nq;
+    const AttnSmem L = attn_smem_layout(NB, KPL, hd);
+    uint32_t* s_kt = reinterpret_cast<uint32_t*>(smem_raw);
+    float* s_kwf = reinterpret_cast<float*>(smem_raw + L.off_kwf);
+    float* s_vef = reinterpret_cast<float*>(smem_raw + L.off_vef);
+    uint4* s_v = reinterpret_cast<uint4*>(smem_raw + L.off_v);
+    unsigned char* s_p = smem_raw + L.off_p;
+    const int KS = L.kt_stride;
+
+    const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool bf16 = p.bf16, flush = p.flush;
+
+    // ---- stage K codes (transposed to [word][key]) and 2^(ek-6)
+    {
+        const uint32_t* kc = reinterpret_cast<const uint32_t*>(p.k_codes + (int64_t)head * Nk * hd);
+        for (int t = threadIdx.x; t < NKP * HW; t += THREADS) {
+            const int j = t / HW, c = t - j * HW;
+            s_kt[c * KS + j] = j < Nk ? __ldg(kc + t) : 0u;
+        }
+        const int8_t* ke = p.k_exps + (int64_t)head * Nk * NB;
+        for (int t = threadIdx.x; t < NKP * NB; t += THREADS) {
+            const int j = t / NB, b = t - j * NB;
+            s_kwf[b * NKP + j] = j < Nk ? exp2i((int)ke[t] - 6) : 0.f;
+        }
+    }
+    // ---- stage V: quantise along tokens, 32-token windows per column (matmul.py:76-83)
+    {
+        const float* vb = p.v.p + bb * p.v.sB + hh * p.v.sH;
+        for (int r = warp; r < KPL; r += WARPS) {
+            for (int dd = 0; dd < NB; ++dd) {
+                const int d = dd * 32 + lane;
+                uint32_t xb[32];
+                uint32_t mx = 0u;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const int j = r * 32 + t;
+                    const float x = (d < hd && j < Nk) ? __ldg(vb + (int64_t)j * p.v.sN + d) : 0.f;
+                    uint32_t b = __float_as_uint(x);
+                    if (bf16) b = bf16_half_away(b);
+                    xb[t] = b;
+                    mx = max(mx, b & 0x7fffffffu);
+                }
+                const int e = mx_shared_exp(mx);
+                const bool dead = flush && e <= -127;
+                uint32_t w[8];
+#pragma unroll
+                for (int qd = 0; qd < 8; ++qd) {
+                    uint32_t word = 0u;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        word |= ((uint32_t)mx_code(xb[qd * 4 + t], e, dead) & 0xffu) << (8 * t);
+                    w[qd] = word;
+                }
+                if (d < hd) {
+                    s_v[(r * 2 + 0) * hd + d] = make_uint4(w[0], w[1], w[2], w[3]);
+                    s_v[(r * 2 + 1) * hd + d] = make_uint4(w[4], w[5], w[6], w[7]);
+                    s_vef[r * hd + d] = exp2i(e - 6);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int NW = (Nk + 31) >> 5;
+    unsigned char* my_p = s_p + warp * NKP;
+    for (int i = blockIdx.y * WARPS + warp; i < Nq; i += WARPS * gridDim.y) {
+        const int64_t row = (int64_t)head * Nq + i;
+        const uint32_t mymask = lane < NW ? __ldg(p.mask + row * NW + lane) : 0u;
+        const uint32_t myq = lane < HW
+            ? __ldg(reinterpret_cast<const uint32_t*>(p.q_codes + row * hd) + lane) : 0u;
+        int qw[NB * 8];
+#pragma unroll
+        for (int c = 0; c < NB * 8; ++c) qw[c] = (int)__shfl_sync(FULL, myq, c);
+        float wqf[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) wqf[b] = exp2i((int)__ldg(p.q_exps + row * NB + b) - 6);
+
+        // ---- A7: true scores at the kept positions (block-exact int8 dots, fp32 combine)
+        float val[KPL];
+        float m = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+            const int j = r * 32 + lane;
+            float s = 0.f;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                int acc = 0;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const int c = b * 8 + c8;
+                    if (c < HW) acc = __dp4a(qw[c], (int)s_kt[c * KS + j], acc);
+                }
+                const float t = (float)acc * (wqf[b] * s_kwf[b * NKP + j]);
+                s = (b == 0) ? t : s + t;
+            }
+            if (bf16) s = bf16_half_away(s);
+            const float tv = s * p.scale;
+            const bool kept = (__shfl_sync(FULL, mymask, r) >> lane) & 1u;
+            val[r] = kept ? tv : -INFINITY;
+            m = fmaxf(m, val[r]);
+        }
+        // ---- softmax over the kept keys (fp32)
+        m = warp_max(m);
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+            val[r] = expf(val[r] - m);      // expf(-inf) == 0 for pruned positions
+            sum += val[r];
+        }
+        sum = warp_sum(sum);
+        // ---- A8: P -> MXINT8 per 32-key window of original positions
+        float pscale[KPL];
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+            uint32_t pb = __float_as_uint(val[r] / sum);
+            if (bf16) pb = bf16_half_away(pb);
+            const uint32_t mx = __reduce_max_sync(FULL, pb);
+            int c = 0;
+            pscale[r] = 0.f;
+            if (mx != 0u) {
+                const int e = mx_shared_exp(mx);
+                const bool dead = flush && e <= -127;
+                c = mx_code(pb, e, dead);
+                pscale[r] = exp2i(e - 6);
+            }
+            my_p[r * 32 + lane] = (unsigned char)c;
+        }
+        __syncwarp();
+        // ---- P.V: int8 dot along the 32 tokens of each window, exponent rescale in fp32
+        float o[NB];
+#pragma unroll
+        for (int dd = 0; dd < NB; ++dd) o[dd] = 0.f;
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+            if (pscale[r] != 0.f) {
+                const uint4 pa = *reinterpret_cast<const uint4*>(my_p + r * 32);
+                const uint4 pc = *reinterpret_cast<const uint4*>(my_p + r * 32 + 16);
+#pragma unroll
+                for (int dd = 0; dd < NB; ++dd) {
+                    const int d = dd * 32 + lane;
+                    if (d < hd) {
+                        const uint4 va = s_v[(r * 2 + 0) * hd + d];
+                        const uint4 vc = s_v[(r * 2 + 1) * hd + d];
+                        int acc = __dp4a((int)pa.x, (int)va.x, 0);
+                        acc = __dp4a((int)pa.y, (int)va.y, acc);
+                        acc = __dp4a((int)pa.z, (int)va.z, acc);
+                        acc = __dp4a((int)pa.w, (int)va.w, acc);
+                        acc = __dp4a((int)pc.x, (int)vc.x, acc);
+                        acc = __dp4a((int)pc.y, (int)vc.y, acc);
+                        acc = __dp4a((int)pc.z, (int)vc.z, acc);
+                        acc = __dp4a((int)pc.w, (int)vc.w, acc);
+                        o[dd] = fmaf((float)acc, pscale[r] * s_vef[r * hd + d], o[dd]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        float* orow = p.out + bb * p.o_sB + hh * p.o_sH + (int64_t)i * p.o_sN;
+#pragma unroll
+        for (int dd = 0; dd < NB; ++dd) {
+            const int d = dd * 32 + lane;
+            if (d < hd) orow[d] = bf16 ? bf16_half_away(o[dd]) : o[dd];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// dispatch helpers
+// ------------------------------------------------------------------------------------
+inline int pick_kpl(int Nk) {
+    const int nw = (Nk + 31) / 32;
+    if (nw <= 1) return 1;
+    if (nw <= 2) return 2;
+    if (nw <= 4) return 4;
+    if (nw <= 7) return 7;
+    return 8;
+}
+
+template <int NB>
+int launch_predict_topk_nb(const PredParams& p, dim3 grid, cudaStream_t st) {
+    switch (pick_kpl(p.Nk)) {
+        case 1: k_predict_topk_fused<NB, 1><<<grid, THREADS, 0, st>>>(p); break;
+        case 2: k_predict_topk_fused<NB, 2><<<grid, THREADS, 0, st>>>(p); break;
+        case 4: k_predict_topk_fused<NB, 4><<<grid, THREADS, 0, st>>>(p); break;
+        case 7: k_predict_topk_fused<NB, 7><<<grid, THREADS, 0, st>>>(p); break;
+        default: k_predict_topk_fused<NB, 8><<<grid, THREADS, 0, st>>>(p); break;
+    }
+    return check_launch("k_predict_topk_fused");
+}
+
+template <int NB, int KPL>
+int launch_attn_one(const AttnParams& p, dim3 grid, cudaStream_t st) {
+    const AttnSmem L = attn_smem_layout(NB, KPL, p.hd);
+    cudaError_t e = cudaFuncSetAttribute(k_sparse_attention<NB, KPL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    k_sparse_attention<NB, KPL><<<grid, THREADS, L.total, st>>>(p);
+    return check_launch("k_sparse_attention");
+}
+
+template <int NB>
+int launch_attn_nb(const AttnParams& p, dim3 grid, cudaStream_t st) {
+    switch (pick_kpl(p.Nk)) {
+        case 1: return launch_attn_one<NB, 1>(p, grid, st);
+        case 2: return launch_attn_one<NB, 2>(p, grid, st);
+        case 4: return launch_attn_one<NB, 4>(p, grid, st);
+        case 7: return launch_attn_one<NB, 7>(p, grid, st);
+        default: return launch_attn_one<NB, 8>(p, grid, st);
+    }
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+int mxp_abi_version(void) { return MXP_ABI_VERSION; }
+const char* mxp_last_error(void) { return g_err; }
+int mxp_last_launch_count(void) { return g_launches; }
+void mxp_limits(int* max_keys, int* max_head_dim) {
+    if (max_keys) *max_keys = MAX_KEYS_FUSED;
+    if (max_head_dim) *max_head_dim = MAX_HD;
+}
+
+static int quantize_common(const float* x, int64_t sB, int64_t sH, int64_t sN, int B, int H, int N,
+                           int hd, int bfloat_bits, int flush, int8_t* codes, int8_t* exps,
+                           uint32_t* signs, float* approx, void* stream) {
+    g_launches = 0;
+    int rc = check_shape(B, H, N, N, hd, bfloat_bits);
+    if (rc) return rc;
+    rc = check_view("x", x, sB, sH, sN, hd);
+    if (rc) return rc;
+    const int64_t rows = (int64_t)B * H * N;
+    int64_t blocks = (rows + WARPS - 1) / WARPS;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    View v{x, sB, sH, sN};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (approx)
+        k_quantize<true><<<(unsigned)blocks, THREADS, 0, st>>>(v, N, H, rows, hd, bfloat_bits == 16, flush != 0, nullptr, nullptr, nullptr, approx);
+    else
+        k_quantize<false><<<(unsigned)blocks, THREADS, 0, st>>>(v, N, H, rows, hd, bfloat_bits == 16, flush != 0, codes, exps, signs, nullptr);
+    return check_launch("k_quantize");
+}
+
+int mxp_quantize_mxint8(const float* x, int64_t sB, int64_t sH, int64_t sN, int B, int H, int N,
+                        int hd, int bfloat_bits, int flush, int8_t* codes, int8_t* exps,
+                        uint32_t* signs, void* stream) {
+    if (!codes || !exps) return fail(MXP_E_BADARG, "codes/exps: null pointer");
+    return quantize_common(x, sB, sH, sN, B, H, N, hd, bfloat_bits, flush, codes, exps, signs, nullptr, stream);
+}
+
+int mxp_exp_sign_approx(const float* x, int64_t sB, int64_t sH, int64_t sN, int B, int H, int N,
+                        int hd, int bfloat_bits, int flush, float* approx, void* stream) {
+    if (!approx) return fail(MXP_E_BADARG, "approx: null pointer");
+    return quantize_common(x, sB, sH, sN, B, H, N, hd, bfloat_bits, flush, nullptr, nullptr, nullptr, approx, stream);
+}
+
+int mxp_predict_scores(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                       const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                       int B, int H, int Nq, int Nk, int hd, int bfloat_bits, int flush,
+                       float* scores, void* stream) {
+    g_launches = 0;
+    int rc = check_shape(B, H, Nq, Nk, hd, bfloat_bits);
+    if (rc) return rc;
+    if ((rc = check_view("q", q, q_sB, q_sH, q_sN, hd))) return rc;
+    if ((rc = check_view("k", k, k_sB, k_sH, k_sN, hd))) return rc;
+    if (!scores) return fail(MXP_E_BADARG, "scores: null pointer");
+    const int nb = (hd + 31) / 32;
+    const int nkp = ((Nk + 31) / 32) * 32;
+    const size_t smem = (size_t)nb * nkp * 8;
+    if (smem > 200 * 1024) return fail(MXP_E_UNSUPPORTED, "Nk=%d too large for the dense score aid", Nk);
+    PredParams p{};
+    p.q = View{q, q_sB, q_sH, q_sN};
+    p.k = View{k, k_sB, k_sH, k_sN};
+    p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk; p.hd = hd; p.top_k = 0;
+    p.bf16 = bfloat_bits == 16; p.flush = flush != 0;
+    p.scores = scores;
+    dim3 grid((unsigned)(B * H), (unsigned)row_splits(B * H, Nq));
+    cudaStream_t st = (cudaStream_t)stream;
+#define MXP_SCORES(NB_)                                                                        \
+    do {                                                                                       \
+        cudaError_t e_ = cudaFuncSetAttribute(k_predict_scores<NB_>,                           \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+        if (e_ != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e_)); \
+        k_predict_scores<NB_><<<grid, THREADS, smem, st>>>(p, nkp);                            \
+    } while (0)
+    switch (nb) {
+        case 1: MXP_SCORES(1); break;
+        case 2: MXP_SCORES(2); break;
+        case 3: MXP_SCORES(3); break;
+        default: MXP_SCORES(4); break;
+    }
+#undef MXP_SCORES
+    return check_launch("k_predict_scores");
+}
+
+size_t mxp_predict_topk_workspace_bytes(int, int, int, int, int) { return 0; }
+
+static int predict_topk_impl(const PredParams& p, cudaStream_t st) {
+    if (p.Nk > MAX_KEYS_FUSED)
+        return fail(MXP_E_UNSUPPORTED, "Nk=%d: fused predictor covers Nk <= %d", p.Nk, MAX_KEYS_FUSED);
+    dim3 grid((unsigned)(p.B * p.H), (unsigned)row_splits(p.B * p.H, p.Nq));
+    switch ((p.hd + 31) / 32) {
+        case 1: return launch_predict_topk_nb<1>(p, grid, st);
+        case 2: return launch_predict_topk_nb<2>(p, grid, st);
+        case 3: return launch_predict_topk_nb<3>(p, grid, st);
+        default: return launch_predict_topk_nb<4>(p, grid, st);
+    }
+}
+
+int mxp_predict_topk(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                     const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                     int B, int H, int Nq, int Nk, int hd, int top_k, int bfloat_bits, int flush,
+                     uint32_t* mask, int32_t* idx, int8_t* q_codes, int8_t* q_exps,
+                     int8_t* k_codes, int8_t* k_exps, void*, size_t, void* stream) {
+    g_launches = 0;
+    int rc = check_shape(B, H, Nq, Nk, hd, bfloat_bits);
+    if (rc) return rc;
+    if ((rc = check_view("q", q, q_sB, q_sH, q_sN, hd))) return rc;
+    if ((rc = check_view("k", k, k_sB, k_sH, k_sN, hd))) return rc;
+    if (!mask) return fail(MXP_E_BADARG, "mask: null pointer");
+    if (top_k < 1 || top_k > Nk) return fail(MXP_E_BADARG, "top_k=%d outside [1, Nk=%d]", top_k, Nk);
+    if ((q_codes == nullptr) != (q_exps == nullptr) || (k_codes == nullptr) != (k_exps == nullptr))
+        return fail(MXP_E_BADARG, "codes and exps outputs must be given together");
+    PredParams p{};
+    p.q = View{q, q_sB, q_sH, q_sN};
+    p.k = View{k, k_sB, k_sH, k_sN};
+    p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk; p.hd = hd; p.top_k = top_k;
+    p.bf16 = bfloat_bits == 16; p.flush = flush != 0;
+    p.mask = mask; p.idx = idx;
+    p.q_codes = q_codes; p.q_exps = q_exps; p.k_codes = k_codes; p.k_exps = k_exps;
+    return predict_topk_impl(p, (cudaStream_t)stream);
+}
+
+size_t mxp_sparse_attention_workspace_bytes(int, int, int, int, int) { return 0; }
+
+static int sparse_attention_impl(const AttnParams& p, cudaStream_t st) {
+    if (p.Nk > MAX_KEYS_FUSED)
+        return fail(MXP_E_UNSUPPORTED, "Nk=%d: sparse attention covers Nk <= %d", p.Nk, MAX_KEYS_FUSED);
+    dim3 grid((unsigned)(p.B * p.H), (unsigned)row_splits(p.B * p.H, p.Nq));
+    switch ((p.hd + 31) / 32) {
+        case 1: return launch_attn_nb<1>(p, grid, st);
+        case 2: return launch_attn_nb<2>(p, grid, st);
+        case 3: return launch_attn_nb<3>(p, grid, st);
+        default: return launch_attn_nb<4>(p, grid, st);
+    }
+}
+
+int mxp_sparse_attention(const int8_t* q_codes, const int8_t* q_exps, const int8_t* k_codes,
+                         const int8_t* k_exps, const float* v, int64_t v_sB, int64_t v_sH,
+                         int64_t v_sN, const uint32_t* mask, int B, int H, int Nq, int Nk, int hd,
+                         float scale, int bfloat_bits, int flush, float* out, int64_t o_sB,
+                         int64_t o_sH, int64_t o_sN, void*, size_t, void* stream) {
+    g_launches = 0;
+    int rc = check_shape(B, H, Nq, Nk, hd, bfloat_bits);
+    if (rc) return rc;
+    if ((rc = check_view("v", v, v_sB, v_sH, v_sN, hd))) return rc;
+    if ((rc = check_view("out", out, o_sB, o_sH, o_sN, hd))) return rc;
+    if (!q_codes || !q_exps || !k_codes || !k_exps || !mask)
+        return fail(MXP_E_BADARG, "codes/exps/mask: null pointer");
+    if (((uintptr_t)q_codes & 3) || ((uintptr_t)k_codes & 3) || ((uintptr_t)mask & 3))
+        return fail(MXP_E_BADARG, "codes/mask must be 4-byte aligned");
+    AttnParams p{};
+    p.q_codes = q_codes; p.q_exps = q_exps; p.k_codes = k_codes; p.k_exps = k_exps;
+    p.v = View{v, v_sB, v_sH, v_sN};
+    p.mask = mask;
+    p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk; p.hd = hd;
+    p.scale = scale; p.bf16 = bfloat_bits == 16; p.flush = flush != 0;
+    p.out = out; p.o_sB = o_sB; p.o_sH = o_sH; p.o_sN = o_sN;
+    return sparse_attention_impl(p, (cudaStream_t)stream);
+}
+
+size_t mxp_pruned_attention_workspace_bytes(int B, int H, int Nq, int Nk, int hd) {
+    const size_t bh = (size_t)B * H, nb = (size_t)(hd + 31) / 32, nw = (size_t)(Nk + 31) / 32;
+    return align256(bh * Nq * hd) + align256(bh * Nq * nb) + align256(bh * Nk * hd) +
+           align256(bh * Nk * nb) + align256(bh * Nq * nw * 4);
+}
+
+int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                         const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                         const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                         int B, int H, int Nq, int Nk, int hd, int top_k, float scale,
+                         int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
+                         int64_t o_sN, uint32_t* mask_out, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+    g_launches = 0;
+    int rc = check_shape(B, H, Nq, Nk, hd, bfloat_bits);
+    if (rc) return rc;
+    if ((rc = check_view("q", q, q_sB, q_sH, q_sN, hd))) return rc;
+    if ((rc = check_view("k", k, k_sB, k_sH, k_sN, hd))) return rc;
+    if ((rc = check_view("v", v, v_sB, v_sH, v_sN, hd))) return rc;
+    if ((rc = check_view("out", out, o_sB, o_sH, o_sN, hd))) return rc;
+    if (top_k < 1 || top_k > Nk) return fail(MXP_E_BADARG, "top_k=%d outside [1, Nk=%d]", top_k, Nk);
+    const size_t need = mxp_pruned_attention_workspace_bytes(B, H, Nq, Nk, hd);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
+        return fail(MXP_E_BADARG, "workspace: need %zu bytes, 256-byte aligned", need);
+    const size_t bh = (size_t)B * H, nb = (size_t)(hd + 31) / 32;
+    unsigned char* w = (unsigned char*)workspace;
+    int8_t* qc = (int8_t*)w; w += align256(bh * Nq * hd);
+    int8_t* qe = (int8_t*)w; w += align256(bh * Nq * nb);
+    int8_t* kc = (int8_t*)w; w += align256(bh * Nk * hd);
+    int8_t* ke = (int8_t*)w; w += align256(bh * Nk * nb);
+    uint32_t* mask = mask_out ? mask_out : (uint32_t*)w;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    PredParams pp{};
+    pp.q = View{q, q_sB, q_sH, q_sN};
+    pp.k = View{k, k_sB, k_sH, k_sN};
+    pp.B = B; pp.H = H; pp.Nq = Nq; pp.Nk = Nk; pp.hd = hd; pp.top_k = top_k;
+    pp.bf16 = bfloat_bits == 16; pp.flush = flush != 0;
+    pp.mask = mask; pp.idx = nullptr;
+    pp.q_codes = qc; pp.q_exps = qe; pp.k_codes = kc; pp.k_exps = ke;
+    if ((rc = predict_topk_impl(pp, st))) return rc;
+
+    AttnParams ap{};
+    ap.q_codes = qc; ap.q_exps = qe; ap.k_codes = kc; ap.k_exps = ke;
+    ap.v = View{v, v_sB, v_sH, v_sN};
+    ap.mask = mask;
+    ap.B = B; ap.H = H; ap.Nq = Nq; ap.Nk = Nk; ap.hd = hd;
+    ap.scale = scale; ap.bf16 = bfloat_bits == 16; ap.flush = flush != 0;
+    ap.out = out; ap.o_sB = o_sB; ap.o_sH = o_sH; ap.o_sN = o_sN;
+    return sparse_attention_impl(ap, st);
+}
+
+}  // extern "C"

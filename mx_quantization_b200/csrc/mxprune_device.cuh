@@ -1,0 +1,112 @@
+// Device-side building blocks shared by every kernel of libmxprune.
+//
+// Arithmetic contract (reference citations relative to the
+// d9bjo0522/mx_quantization checkout):
+//   A1 bf16 pre-rounding, half away from zero   microxscaling/mx/elemwise_ops.py:201-216, :64-65
+//   A2 MXINT8 block quantizer                   microxscaling/mx/mx_ops.py:49-99, 180-306
+//                                               microxscaling/mx/elemwise_ops.py:92-180
+// All of it is integer / exactly-rounded fp32 work, so results are bit-identical to the
+// reference's CPU fp32 path by construction, not by tolerance.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mxp {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr int ZERO_BLOCK_EXP = -126;   // floor(log2(2^-126)), mx_ops.py:83-87
+
+// 2^e as fp32 for e in [-149, 127] (subnormal below -126).
+__device__ __forceinline__ float exp2i(int e) {
+    return __uint_as_float(e >= -126 ? (uint32_t)(e + 127) << 23 : 1u << (e + 149));
+}
+
+// A1: round-half-away to bf16 on the fp32 bit pattern (sign preserved).
+__device__ __forceinline__ uint32_t bf16_half_away(uint32_t b) {
+    return (((b & 0x7fffffffu) + 0x8000u) & 0xffff0000u) | (b & 0x80000000u);
+}
+__device__ __forceinline__ float bf16_half_away(float x) {
+    return __uint_as_float(bf16_half_away(__float_as_uint(x)));
+}
+
+// Shared exponent of a block from the bit pattern of its max magnitude.
+// The reference evaluates floor(log2(max)) in fp32 (mx_ops.py:93-97): when max is within
+// jmax(n) ulps below 2^n the fp32 logarithm rounds up to n.  jmax depends only on the binade
+// of n: floor(ln2 * 2^floor(log2 a)), a = n-1 (n>0) or -n (n<0)  ->  {0,1,2,5,11,22,44,88}.
+// zero block -> -126; subnormal max -> -127 (the scale_bits=8 floor, mx_ops.py:289-291).
+__device__ __forceinline__ int mx_shared_exp(uint32_t maxbits) {
+    const int E = (int)(maxbits >> 23);
+    const uint32_t m = maxbits & 0x7fffffu;
+    if (E == 0) return m == 0 ? ZERO_BLOCK_EXP : -127;
+    int e = E - 127;
+    const int n = e + 1;
+    const int a = n > 0 ? n - 1 : -n;
+    int jm = 0;
+    if (a > 0) jm = (int)((0x582C160B05020100ull >> (8 * (31 - __clz(a)))) & 0xffull);
+    if ((int)(0x800000u - m) <= jm) e += 1;
+    return min(e, 127);
+}
+
+// Element code given the (possibly bf16-rounded) bit pattern and the block exponent:
+// sign * min(127, floor(|x| / 2^e * 64 + 0.5)), the +0.5 being an fp32 add exactly as in
+// elemwise_ops.py:64-65 (so that 0.5 - 2^-25 rounds the way the reference rounds it).
+__device__ __forceinline__ int mx_code(uint32_t bits, int e, bool dead) {
+    const float t = __uint_as_float(bits & 0x7fffffffu) * exp2i(-e) * 64.0f;
+    const float r = floorf(t + 0.5f);
+    int c = (int)fminf(r, 127.0f);
+    if (dead) c = 0;
+    return (bits >> 31) ? -c : c;
+}
+
+// One warp quantizes one 32-wide block held one element per lane (padding lanes pass 0).
+// Returns the lane's code; e_out = block exponent (A2), ep_out = predictor exponent (A3:
+// floor(log2(max|MX|)) == e for every non-zero in-contract block, -126 for a zero block).
+__device__ __forceinline__ int quantize_block_warp(float x, bool bf16, bool flush,
+                                                   int& e_out, int& ep_out) {
+    uint32_t b = __float_as_uint(x);
+    if (bf16) b = bf16_half_away(b);
+    const uint32_t mx = __reduce_max_sync(FULL, b & 0x7fffffffu);
+    const int e = mx_shared_exp(mx);
+    const bool dead = flush && e <= -127;           // mx_ops.py:282-283
+    e_out = e;
+    ep_out = dead ? ZERO_BLOCK_EXP : e;
+    return mx_code(b, e, dead);
+}
+
+// float -> u32 key whose unsigned order equals the float order (-0 canonicalised to +0 first).
+__device__ __forceinline__ uint32_t ordered_key(float s) {
+    const uint32_t b = __float_as_uint(s + 0.0f);
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+
+// n_b - 2*p as an exact float without an int->float conversion:
+// (2^23 + p) * -2 + (2^24 + n_b), one FFMA, exact because n_b is even.
+__device__ __forceinline__ float signed_count(int popc, float two24_plus_nb) {
+    return fmaf(__uint_as_float(0x4B000000u | (uint32_t)popc), -2.0f, two24_plus_nb);
+}
+
+// Keep only the m lowest set bits of x.
+__device__ __forceinline__ uint32_t keep_lowest_bits(uint32_t x, int m) {
+    uint32_t y = 0;
+    for (int t = 0; t < m; ++t) {
+        const uint32_t low = x & (0u - x);
+        y |= low;
+        x ^= low;
+    }
+    return y;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+}  // namespace mxp

@@ -1,0 +1,205 @@
+"""Tensor-level entry points over the C ABI (include/mxprune.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every computation
+happens in libmxprune's sm_100a kernels.  CPU tensors are rejected - there is no CPU path.
+"""
+from ctypes import c_void_p
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .specs import resolve_specs
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def _view4(t: torch.Tensor, name: str) -> torch.Tensor:
+    """Accept the strided (B,H,N,hd) views the attention modules produce; copy only when the
+    layout is outside what the kernels address (innermost stride 1, 16-byte aligned rows)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if t.device.type != "cuda":
+        raise ValueError(f"{name}: expected a CUDA tensor (device={t.device}); there is no CPU fallback")
+    if t.dim() != 4:
+        raise ValueError(f"{name}: expected a 4-D (B,H,N,head_dim) tensor, got shape {tuple(t.shape)}")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name}: expected float32 (the reference's fake-quant dtype), got {t.dtype}")
+    ok = t.stride(-1) == 1 and t.data_ptr() % 16 == 0 and all(s % 4 == 0 for s in t.stride()[:3])
+    return t if ok else t.contiguous()
+
+
+def _strides(t: torch.Tensor) -> Tuple[int, int, int]:
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def _same_device(*ts):
+    dev = ts[0].device
+    for t in ts[1:]:
+        if t is not None and t.device != dev:
+            raise ValueError("all tensors must live on the same CUDA device")
+    return dev
+
+
+def limits() -> Tuple[int, int]:
+    import ctypes
+    a, b = ctypes.c_int(), ctypes.c_int()
+    _lib.load().mxp_limits(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
+def last_launch_count() -> int:
+    return _lib.load().mxp_last_launch_count()
+
+
+def quantize_mxint8(x: torch.Tensor, mx_specs, with_signs: bool = False):
+    """MXINT8 codes/exponents of ``x`` along head_dim (replaces quantize_mx_op on this path).
+
+    Returns (codes int8 (B,H,N,hd), exps int8 (B,H,N,nb)[, signs int32 (B,H,N,nb)])."""
+    sp = resolve_specs(mx_specs)
+    lib = _lib.load()
+    x = _view4(x, "x")
+    B, H, N, hd = x.shape
+    nb = (hd + 31) // 32
+    with torch.cuda.device(x.device):
+        codes = torch.empty((B, H, N, hd), dtype=torch.int8, device=x.device)
+        exps = torch.empty((B, H, N, nb), dtype=torch.int8, device=x.device)
+        signs = torch.empty((B, H, N, nb), dtype=torch.int32, device=x.device) if with_signs else None
+        rc = lib.mxp_quantize_mxint8(_ptr(x), *_strides(x), B, H, N, hd, sp.bfloat_bits, int(sp.flush),
+                                     _ptr(codes), _ptr(exps), _ptr(signs), _stream())
+    _lib.check(rc, "mxp_quantize_mxint8")
+    return (codes, exps, signs) if with_signs else (codes, exps)
+
+
+def exp_sign_approx(x: torch.Tensor, mx_specs) -> torch.Tensor:
+    """Dense (code<0 ? -1 : +1) * 2^e tensor, fp32 (B,H,N,hd)."""
+    sp = resolve_specs(mx_specs)
+    lib = _lib.load()
+    x = _view4(x, "x")
+    B, H, N, hd = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, H, N, hd), dtype=torch.float32, device=x.device)
+        rc = lib.mxp_exp_sign_approx(_ptr(x), *_strides(x), B, H, N, hd, sp.bfloat_bits, int(sp.flush),
+                                     _ptr(out), _stream())
+    _lib.check(rc, "mxp_exp_sign_approx")
+    return out
+
+
+def _qk_shapes(q, k):
+    B, H, Nq, hd = q.shape
+    if k.shape[0] != B or k.shape[1] != H or k.shape[3] != hd:
+        raise ValueError(f"q {tuple(q.shape)} and k {tuple(k.shape)} disagree on (B,H,head_dim)")
+    return B, H, Nq, k.shape[2], hd
+
+
+def predict_scores(q: torch.Tensor, k: torch.Tensor, mx_specs) -> torch.Tensor:
+    """Dense predicted scores (B,H,Nq,Nk) - parity aid, O(N^2) output."""
+    sp = resolve_specs(mx_specs)
+    lib = _lib.load()
+    q, k = _view4(q, "q"), _view4(k, "k")
+    _same_device(q, k)
+    B, H, Nq, Nk, hd = _qk_shapes(q, k)
+    with torch.cuda.device(q.device):
+        out = torch.empty((B, H, Nq, Nk), dtype=torch.float32, device=q.device)
+        rc = lib.mxp_predict_scores(_ptr(q), *_strides(q), _ptr(k), *_strides(k), B, H, Nq, Nk, hd,
+                                    sp.bfloat_bits, int(sp.flush), _ptr(out), _stream())
+    _lib.check(rc, "mxp_predict_scores")
+    return out
+
+
+def predict_topk(q: torch.Tensor, k: torch.Tensor, mx_specs, top_k: int, return_idx: bool = False,
+                 return_codes: bool = False):
+    """Fused quantize + exp-sign predictor + per-row top-k.
+
+    Returns a dict: mask int32 (B,H,Nq,ceil(Nk/32)) [bit j%32 of word j//32 = key j kept],
+    optionally idx int32 (B,H,Nq,top_k) ascending key order, and q/k codes+exps."""
+    sp = resolve_specs(mx_specs)
+    lib = _lib.load()
+    q, k = _view4(q, "q"), _view4(k, "k")
+    dev = _same_device(q, k)
+    B, H, Nq, Nk, hd = _qk_shapes(q, k)
+    nb, nw = (hd + 31) // 32, (Nk + 31) // 32
+    res = {}
+    with torch.cuda.device(dev):
+        res["mask"] = torch.empty((B, H, Nq, nw), dtype=torch.int32, device=dev)
+        if return_idx:
+            res["idx"] = torch.empty((B, H, Nq, int(top_k)), dtype=torch.int32, device=dev)
+        if return_codes:
+            res["q_codes"] = torch.empty((B, H, Nq, hd), dtype=torch.int8, device=dev)
+            res["q_exps"] = torch.empty((B, H, Nq, nb), dtype=torch.int8, device=dev)
+            res["k_codes"] = torch.empty((B, H, Nk, hd), dtype=torch.int8, device=dev)
+            res["k_exps"] = torch.empty((B, H, Nk, nb), dtype=torch.int8, device=dev)
+        ws_bytes = lib.mxp_predict_topk_workspace_bytes(B, H, Nq, Nk, hd)
+        ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev) if ws_bytes else None
+        rc = lib.mxp_predict_topk(_ptr(q), *_strides(q), _ptr(k), *_strides(k), B, H, Nq, Nk, hd, int(top_k),
+                                  sp.bfloat_bits, int(sp.flush), _ptr(res["mask"]), _ptr(res.get("idx")),
+                                  _ptr(res.get("q_codes")), _ptr(res.get("q_exps")),
+                                  _ptr(res.get("k_codes")), _ptr(res.get("k_exps")),
+                                  _ptr(ws), ws_bytes, _stream())
+    _lib.check(rc, "mxp_predict_topk")
+    return res
+
+
+def sparse_attention(q_codes, q_exps, k_codes, k_exps, v: torch.Tensor, mask: torch.Tensor, mx_specs,
+                     scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Exact MXINT8 softmax(QK^T*scale)V over the keys selected by ``mask``."""
+    sp = resolve_specs(mx_specs)
+    lib = _lib.load()
+    v = _view4(v, "v")
+    B, H, Nk, hd = v.shape
+    Nq = q_codes.shape[2]
+    dev = _same_device(v, q_codes, q_exps, k_codes, k_exps, mask)
+    for name, t, dt in (("q_codes", q_codes, torch.int8), ("q_exps", q_exps, torch.int8),
+                        ("k_codes", k_codes, torch.int8), ("k_exps", k_exps, torch.int8),
+                        ("mask", mask, torch.int32)):
+        if t.dtype != dt or not t.is_contiguous():
+            raise ValueError(f"{name}: expected a contiguous {dt} tensor")
+    scale = float(hd) ** -0.5 if scale is None else float(scale)
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((B, H, Nq, hd), dtype=torch.float32, device=dev)
+        rc = lib.mxp_sparse_attention(_ptr(q_codes), _ptr(q_exps), _ptr(k_codes), _ptr(k_exps),
+                                      _ptr(v), *_strides(v), _ptr(mask), B, H, Nq, Nk, hd,
+                                      scale, sp.bfloat_bits, int(sp.flush),
+                                      _ptr(out), *_strides(out), c_void_p(0), 0, _stream())
+    _lib.check(rc, "mxp_sparse_attention")
+    return out
+
+
+def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs, top_k: int,
+                     scale: Optional[float] = None, return_mask: bool = False,
+                     out: Optional[torch.Tensor] = None):
+    """MXINT8 exponent-sign predicted top-k attention: q,k,v (B,H,N,hd) fp32 -> out (B,H,Nq,hd).
+
+    Drop-in for lines 101-152 of workloads/deit/scripts/main.py (DiT models.py:168-225, PixArt
+    MX_transformer_block.py:647-710) when mx_quant, top_k, approx_flag and pred_mode=="ex_pred".
+    ``out`` may be any fp32 (B,H,Nq,hd) *view* with innermost stride 1, e.g. a permuted
+    (B,Nq,H,hd) buffer so that the module's transpose(1,2).reshape(B,N,C) is free.
+    """
+    sp = resolve_specs(mx_specs)
+    lib = _lib.load()
+    q, k, v = _view4(q, "q"), _view4(k, "k"), _view4(v, "v")
+    dev = _same_device(q, k, v, out)
+    B, H, Nq, Nk, hd = _qk_shapes(q, k)
+    if tuple(v.shape) != (B, H, Nk, hd):
+        raise ValueError(f"v {tuple(v.shape)} must be (B,H,Nk,head_dim) = {(B, H, Nk, hd)}")
+    scale = float(hd) ** -0.5 if scale is None else float(scale)
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((B, H, Nq, hd), dtype=torch.float32, device=dev)
+        elif tuple(out.shape) != (B, H, Nq, hd) or out.dtype != torch.float32 or out.stride(-1) != 1:
+            raise ValueError("out must be an fp32 (B,H,Nq,head_dim) view with innermost stride 1")
+        mask = torch.empty((B, H, Nq, (Nk + 31) // 32), dtype=torch.int32, device=dev) if return_mask else None
+        ws_bytes = lib.mxp_pruned_attention_workspace_bytes(B, H, Nq, Nk, hd)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        rc = lib.mxp_pruned_attention(_ptr(q), *_strides(q), _ptr(k), *_strides(k), _ptr(v), *_strides(v),
+                                      B, H, Nq, Nk, hd, int(top_k), scale, sp.bfloat_bits, int(sp.flush),
+                                      _ptr(out), *_strides(out), _ptr(mask), _ptr(ws), ws_bytes, _stream())
+    _lib.check(rc, "mxp_pruned_attention")
+    return (out, mask) if return_mask else out

@@ -1,0 +1,68 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import mxint8_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def mx_specs(bfloat=32, flush=False):
+    """The dict the reference's scripts build (workloads/deit/scripts/main.py:719-735)."""
+    return {
+        'w_elem_format': 'int8', 'a_elem_format': 'int8', 'scale_bits': 8,
+        'shared_exp_method': 'max', 'block_size': 32, 'bfloat': bfloat, 'fp': 0,
+        'bfloat_subnorms': True, 'round': 'nearest', 'round_mx_output': 'nearest',
+        'round_output': 'nearest', 'round_weight': 'nearest',
+        'mx_flush_fp32_subnorms': flush, 'custom_cuda': False, 'quantize_backprop': False,
+    }
+
+
+def make_qkv(B, H, N, hd, seed=0, kind="randn", Nk=None):
+    """Synthetic activations: randn, per-token log-normal scale spread, edge rows."""
+    Nk = N if Nk is None else Nk
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, H, N, hd, generator=g)
+    k = torch.randn(B, H, Nk, hd, generator=g)
+    v = torch.randn(B, H, Nk, hd, generator=g)
+    if kind == "lognormal":
+        q = q * torch.exp(1.5 * torch.randn(B, H, N, 1, generator=g))
+        k = k * torch.exp(1.5 * torch.randn(B, H, Nk, 1, generator=g))
+        v = v * torch.exp(0.5 * torch.randn(B, H, Nk, 1, generator=g))
+    if kind == "edges":
+        q[0, 0, 3 % N] = 0.0
+        k[0, 0, 5 % Nk] = 0.0
+        if hd > 32:
+            q[0, 0, 7 % N, 32:min(64, hd)] = 0.0
+        k[0, -1, 2 % Nk, :32] = 0.0
+        q[0, -1, 4 % N, :8] = -1e-6
+        k[0, -1, 9 % Nk, hd // 2:hd // 2 + 8] = -1e-7
+        k[0, 0, 11 % Nk] = k[0, 0, 10 % Nk]
+        k[0, 0, 12 % Nk] = k[0, 0, 10 % Nk]
+        v[0, 0, 6 % Nk] = 0.0
+        # block maxima just below a power of two (fp32 log2 rounds up in the reference)
+        q[0, 0, 1 % N, 0] = float(np.nextafter(np.float32(8.0), np.float32(0)))
+        k[0, 0, 1 % Nk, 1] = -float(np.nextafter(np.float32(16.0), np.float32(0)))
+    return q, k, v
+
+
+def fused_qkv_views(q, k, v):
+    """Re-create the reference's layout: one (B,N,3,H,hd) buffer, q/k/v = permuted views
+    (workloads/deit/scripts/main.py:87-88).  Requires Nq == Nk."""
+    B, H, N, hd = q.shape
+    buf = torch.stack([q, k, v], dim=0).permute(1, 3, 0, 2, 4).contiguous()   # (B,N,3,H,hd)
+    qkv = buf.permute(2, 0, 3, 1, 4)
+    return qkv[0], qkv[1], qkv[2]
+
+
+def unpack_mask(mask_i32, n_keys):
+    return O.mask_words_to_dense(mask_i32.cpu().to(torch.int64) & 0xFFFFFFFF, n_keys)
+
+
+def load_golden(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    d = {k: torch.from_numpy(z[k].astype(np.int64) if z[k].dtype == np.int16 else z[k]) for k in z.files}
+    B, H, N, hd, top_k, bfloat, flush = (int(x) for x in z["meta"])
+    return d, dict(B=B, H=H, N=N, hd=hd, top_k=top_k, bfloat=bfloat, flush=bool(flush))
