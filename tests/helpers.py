@@ -66,3 +66,54 @@ def load_golden(name):
     d = {k: torch.from_numpy(z[k].astype(np.int64) if z[k].dtype == np.int16 else z[k]) for k in z.files}
     B, H, N, hd, top_k, bfloat, flush = (int(x) for x in z["meta"])
     return d, dict(B=B, H=H, N=N, hd=hd, top_k=top_k, bfloat=bfloat, flush=bool(flush))
+
+
+def out_error_budget(ref, v, n_keys, bfloat=32, out_tol=1e-3, rel_window=1e-6):
+    """Per-row absolute error budget for the fp32 attention output.
+
+    Base: out_tol * max|ref out| (the stated tolerance).  The reference's P quantizer
+    (mx.matmul on the softmax matrix, workloads/deit/scripts/main.py:152) is DISCONTINUOUS in p:
+    where p*64/2^e sits within a few ulps of a rounding tie, or a window's max p within a few
+    ulps of a power of two (e.g. one-hot rows with p = 1 - 2^-24 vs 1.0), a 1-ulp difference in
+    exp()/sum order moves the dequantised P by one code step 2^(e-6).  Any two implementations
+    (including the reference's own CPU and CUDA runs) disagree there, so such entries add one
+    code step * max|V row| to the row's budget.  Everything else must meet the base tolerance.
+    """
+    vals, idx, out_ref = ref["true_vals"], ref["idx"], ref["out"]
+    p64 = torch.softmax(vals.double(), dim=-1)
+    attn = torch.zeros(*vals.shape[:-1], n_keys, dtype=torch.float64)
+    attn.scatter_(-1, idx, p64)
+    nw = (n_keys + 31) // 32
+    pad = nw * 32 - n_keys
+    a = torch.nn.functional.pad(attn, (0, pad)).reshape(*attn.shape[:-1], nw, 32)
+    amax = a.amax(-1, keepdim=True)
+    mant, ex = torch.frexp(amax)                     # amax = mant * 2^ex, mant in [0.5, 1)
+    e = (ex - 1).clamp(min=-127)                     # floor(log2(amax))
+    step = torch.ldexp(torch.ones_like(amax), e - 6)
+    t = a / step                                     # code-domain value
+    frac = t - torch.floor(t)
+    tie = ((frac - 0.5).abs() <= rel_window * t.clamp(min=1.0)) & (a > 0)
+    exp_edge = ((mant > 1 - rel_window) | (mant < 0.5 + rel_window)) & (amax > 0)
+    risky = tie | (exp_edge & (a > 0))
+    if bfloat == 16:      # A1 rounds P to bf16 first: ties of that rounding are risk points too
+        m8, _ = torch.frexp(a)
+        f8 = m8 * 256.0 - torch.floor(m8 * 256.0)
+        risky = risky | (((f8 - 0.5).abs() <= rel_window * 256.0) & (a > 0))
+    vrow = v.abs().amax(-1)                          # (B,H,Nk)
+    vrow = torch.nn.functional.pad(vrow, (0, pad)).reshape(*vrow.shape[:-1], nw, 32).unsqueeze(-3)
+    extra = (risky.double() * (2 * step) * vrow.double()).sum(dim=(-1, -2))     # (B,H,Nq)
+    base = out_tol * float(out_ref.abs().max())
+    return base + extra.float()
+
+
+def assert_out_close(out, ref, v, n_keys, bfloat=32, out_tol=1e-3, max_relaxed_frac=None):
+    budget = out_error_budget(ref, v, n_keys, bfloat, out_tol)
+    err = (out - ref["out"]).abs().amax(-1)
+    bad = err > budget
+    base = out_tol * float(ref["out"].abs().max())
+    frac_relaxed = float((budget > base * 1.0001).float().mean())
+    assert not bool(bad.any()), (
+        f"{int(bad.sum())} rows exceed their budget; worst err {float(err.max()):.3e}, base tol {base:.3e}")
+    if max_relaxed_frac is not None:     # well-conditioned inputs: almost no row may need the allowance
+        assert frac_relaxed <= max_relaxed_frac, f"{frac_relaxed:.1%} of rows needed the code-step allowance"
+    return float(err.max()), frac_relaxed
