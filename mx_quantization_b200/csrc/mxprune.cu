@@ -7,6 +7,7 @@
 
 #include "mxprune.h"
 #include "mxprune_device.cuh"
+#include "mxprune_predict.cuh"
 
 using namespace mxp;
 
@@ -35,11 +36,6 @@ int check_launch(const char* what) {
 
 constexpr int MAX_HD = 128;
 constexpr int MAX_KEYS_FUSED = 256;   // keys held in registers, 8 per lane
-
-struct View {   // fp32 (B,H,N,hd) view, element strides
-    const float* p;
-    int64_t sB, sH, sN;
-};
 
 int check_view(const char* name, const float* p, int64_t sB, int64_t sH, int64_t sN, int hd) {
     if (!p) return fail(MXP_E_BADARG, "%s: null pointer", name);
@@ -103,15 +99,6 @@ k_quantize(View x, int rows_per_bh, int H, int64_t total_rows, int hd, int bf16,
 // ------------------------------------------------------------------------------------
 // Predictor parameters
 // ------------------------------------------------------------------------------------
-struct PredParams {
-    View q, k;
-    int B, H, Nq, Nk, hd, top_k, bf16, flush;
-    uint32_t* mask;
-    int32_t* idx;
-    int8_t *q_codes, *q_exps, *k_codes, *k_exps;
-    float* scores;   // dense debug output (k_predict_scores only)
-};
-
 // Quantize the Nk key rows of one head into shared memory: sign words + 2^e weights.
 // All warps of the CTA cooperate, one row per warp per step.
 template <int NB>
@@ -183,109 +170,6 @@ __device__ __forceinline__ float pred_score(const uint32_t (&sk)[NB], const floa
         s = (b == 0) ? t * wq[0] : fmaf(t, wq[b], s);
     }
     return s;
-}
-
-// ------------------------------------------------------------------------------------
-// K1 (fused, Nk <= 256): quantize K -> smem -> registers; per query row: quantize, score all
-// keys (XOR + POPC), exact radix select of the top_k-th key in registers, emit the row bitmask.
-// One CTA per (head, row split); one warp per query row; lane l owns keys l, l+32, ...
-// ------------------------------------------------------------------------------------
-template <int NB, int KPL>
-__global__ void __launch_bounds__(THREADS)
-k_predict_topk_fused(const PredParams p) {
-    constexpr int NKP = KPL * 32;
-    __shared__ uint32_t s_ksign[NB * NKP];
-    __shared__ float s_kw[NB * NKP];
-    const int head = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int Nk = p.Nk, Nq = p.Nq;
-
-    stage_keys<NB>(p, head, NKP, s_ksign, s_kw, p.k_codes != nullptr && blockIdx.y == 0);
-    __syncthreads();
-
-    uint32_t ks[KPL][NB];
-    float kw[KPL][NB];
-#pragma unroll
-    for (int r = 0; r < KPL; ++r)
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            ks[r][b] = s_ksign[b * NKP + r * 32 + lane];
-            kw[r][b] = s_kw[b * NKP + r * 32 + lane];
-        }
-    float c24[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) c24[b] = block_width_const<NB>(b, p.hd);
-
-    const int bb = head / p.H, hh = head % p.H;
-    const float* qb = p.q.p + bb * p.q.sB + hh * p.q.sH;
-    const int NW = (Nk + 31) >> 5;
-    const int kk = p.top_k;
-
-    for (int i = blockIdx.y * WARPS + warp; i < Nq; i += WARPS * gridDim.y) {
-        const int64_t row = (int64_t)head * Nq + i;
-        uint32_t sq[NB];
-        float wq[NB];
-        quantize_query_row<NB>(p, qb + (int64_t)i * p.q.sN, row, p.q_codes != nullptr, sq, wq);
-
-        // ---- scores as order-preserving u32 keys, 0 for lanes past Nk
-        uint32_t u[KPL];
-        uint32_t aor = 0u, aand = 0xffffffffu;
-#pragma unroll
-        for (int r = 0; r < KPL; ++r) {
-            const float s = pred_score<NB>(ks[r], kw[r], sq, wq, c24);
-            const bool valid = r * 32 + lane < Nk;
-            u[r] = valid ? ordered_key(s) : 0u;
-            aor |= u[r];
-            aand &= valid ? u[r] : 0xffffffffu;
-        }
-        aor = __reduce_or_sync(FULL, aor);
-        aand = __reduce_and_sync(FULL, aand);
-
-        // ---- exact radix select: T = top_k-th largest key.  Only bit positions that differ
-        // between keys need a counting pass (bits set in every key stay set, bits clear in
-        // every key stay clear).
-        uint32_t T = aand, vary = aor & ~aand;
-        while (vary) {
-            const uint32_t m1 = 1u << (31 - __clz(vary));
-            vary ^= m1;
-            const uint32_t cand = T | m1;
-            int c = 0;
-#pragma unroll
-            for (int r = 0; r < KPL; ++r) c += (u[r] >= cand) ? 1 : 0;
-            c = __reduce_add_sync(FULL, c);
-            if (c >= kk) T = cand;
-        }
-
-        // ---- row bitmask: every key > T, plus the lowest-index keys == T up to top_k
-        uint32_t ge[KPL], gt[KPL];
-        int ngt = 0;
-#pragma unroll
-        for (int r = 0; r < KPL; ++r) {
-            ge[r] = __ballot_sync(FULL, u[r] >= T);
-            gt[r] = __ballot_sync(FULL, u[r] > T);
-            ngt += __popc(gt[r]);
-        }
-        int rem = kk - ngt;
-        uint32_t myword = 0u;
-        int mybase = 0, base = 0;
-#pragma unroll
-        for (int r = 0; r < KPL; ++r) {
-            const uint32_t eq = ge[r] & ~gt[r];
-            const int c = __popc(eq);
-            uint32_t take;
-            if (c <= rem) { take = eq; rem -= c; }
-            else { take = keep_lowest_bits(eq, rem); rem = 0; }
-            const uint32_t w = gt[r] | take;
-            if (lane == r) myword = w;
-            if (p.idx) {
-                if ((w >> lane) & 1u)
-                    p.idx[row * kk + base + __popc(w & ((1u << lane) - 1u))] = r * 32 + lane;
-                base += __popc(w);
-            }
-        }
-        (void)mybase;
-        if (lane < NW) p.mask[row * NW + lane] = myword;
-    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -547,15 +431,19 @@ inline int pick_kpl(int Nk) {
 }
 
 template <int NB>
-int launch_predict_topk_nb(const PredParams& p, dim3 grid, cudaStream_t st) {
-    switch (pick_kpl(p.Nk)) {
-        case 1: k_predict_topk_fused<NB, 1><<<grid, THREADS, 0, st>>>(p); break;
-        case 2: k_predict_topk_fused<NB, 2><<<grid, THREADS, 0, st>>>(p); break;
-        case 4: k_predict_topk_fused<NB, 4><<<grid, THREADS, 0, st>>>(p); break;
-        case 7: k_predict_topk_fused<NB, 7><<<grid, THREADS, 0, st>>>(p); break;
-        default: k_predict_topk_fused<NB, 8><<<grid, THREADS, 0, st>>>(p); break;
-    }
-    return check_launch("k_predict_topk_fused");
+int launch_predict_topk_nb(const PredParams& p, cudaStream_t st) {
+    const K1Smem L = k1_smem_layout(NB, p.Nk);
+    cudaError_t e = cudaFuncSetAttribute(k_predict_topk_rows<NB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int heads = p.B * p.H;
+    const int tiles = (p.Nq + K1T - 1) / K1T;
+    int splits = (148 * 3 + heads - 1) / heads;         // 3 CTAs per SM resident
+    if (splits > tiles) splits = tiles;
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)heads, (unsigned)splits);
+    k_predict_topk_rows<NB><<<grid, K1T, L.total, st>>>(p);
+    return check_launch("k_predict_topk_rows");
 }
 
 template <int NB, int KPL>
@@ -673,12 +561,11 @@ size_t mxp_predict_topk_workspace_bytes(int, int, int, int, int) { return 0; }
 static int predict_topk_impl(const PredParams& p, cudaStream_t st) {
     if (p.Nk > MAX_KEYS_FUSED)
         return fail(MXP_E_UNSUPPORTED, "Nk=%d: fused predictor covers Nk <= %d", p.Nk, MAX_KEYS_FUSED);
-    dim3 grid((unsigned)(p.B * p.H), (unsigned)row_splits(p.B * p.H, p.Nq));
     switch ((p.hd + 31) / 32) {
-        case 1: return launch_predict_topk_nb<1>(p, grid, st);
-        case 2: return launch_predict_topk_nb<2>(p, grid, st);
-        case 3: return launch_predict_topk_nb<3>(p, grid, st);
-        default: return launch_predict_topk_nb<4>(p, grid, st);
+        case 1: return launch_predict_topk_nb<1>(p, st);
+        case 2: return launch_predict_topk_nb<2>(p, st);
+        case 3: return launch_predict_topk_nb<3>(p, st);
+        default: return launch_predict_topk_nb<4>(p, st);
     }
 }
 

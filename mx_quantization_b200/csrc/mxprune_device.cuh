@@ -18,6 +18,20 @@ constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
 constexpr int ZERO_BLOCK_EXP = -126;   // floor(log2(2^-126)), mx_ops.py:83-87
 
+struct View {   // fp32 (B,H,N,hd) view, element strides, innermost stride 1
+    const float* p;
+    int64_t sB, sH, sN;
+};
+
+struct PredParams {
+    View q, k;
+    int B, H, Nq, Nk, hd, top_k, bf16, flush;
+    uint32_t* mask;
+    int32_t* idx;
+    int8_t *q_codes, *q_exps, *k_codes, *k_exps;
+    float* scores;   // dense debug output (k_predict_scores only)
+};
+
 // 2^e as fp32 for e in [-149, 127] (subnormal below -126).
 __device__ __forceinline__ float exp2i(int e) {
     return __uint_as_float(e >= -126 ? (uint32_t)(e + 127) << 23 : 1u << (e + 149));
@@ -76,9 +90,12 @@ __device__ __forceinline__ int quantize_block_warp(float x, bool bf16, bool flus
 }
 
 // float -> u32 key whose unsigned order equals the float order (-0 canonicalised to +0 first).
+// Negative values map to 0x80000000 - magnitude (not to ~bits): a subtraction keeps the trailing
+// zero bits that these scores have (small integers times a power of two), so the radix select
+// only has to resolve the few bit positions that really differ between keys.
 __device__ __forceinline__ uint32_t ordered_key(float s) {
     const uint32_t b = __float_as_uint(s + 0.0f);
-    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+    return (b & 0x80000000u) ? 0x80000000u - (b & 0x7fffffffu) : b | 0x80000000u;
 }
 
 // n_b - 2*p as an exact float without an int->float conversion:
