@@ -1,0 +1,144 @@
+"""Attention-module integration hooks.
+
+The three attention modules the reference patches all run the same sequence between their qkv
+projection and their output projection:
+    workloads/deit/scripts/main.py:85-157                       QuantizedAttention.forward
+    workloads/DiT/models.py:154-230                             Attention.forward
+    workloads/PixArt/models/MX_transformer_block.py:624-717     MXSelfAttention.forward
+``PrunedAttentionCore`` is that sequence (lines 101-152 of the DeiT file) as one call into
+libmxprune; the three shims keep the reference constructors' / ``set_config`` argument names so a
+maintainer can swap the body of ``forward`` (INTEGRATION.md shows the patch).  The qkv / output
+projections stay whatever the host model uses (``mx.Linear`` in the reference - outside the hot
+path); here they are plain ``nn.Linear`` unless the caller passes its own.
+
+Only mx_quant && top_k && approx/ex_pred && pred_mode == "ex_pred" is implemented; every other
+combination raises (no silent fallback, per the north star).
+"""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .specs import resolve_specs
+
+
+class PrunedAttentionCore(nn.Module):
+    """q, k, v (B,H,N,hd) fp32 views -> x (B,N,H*hd), ready for the output projection."""
+
+    def __init__(self, mx_specs, k: int, scale: Optional[float] = None):
+        super().__init__()
+        resolve_specs(mx_specs)
+        self.mx_specs = mx_specs
+        self.k = int(k)
+        self.scale = scale
+
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+        B, H, N, hd = q.shape
+        buf = torch.empty((B, N, H, hd), dtype=torch.float32, device=q.device)
+        # write straight into (B,N,H,hd): the reference's x.transpose(1,2).reshape(B,N,C) is free
+        ops.pruned_attention(q, k, v, self.mx_specs, self.k, scale=self.scale, out=buf.permute(0, 2, 1, 3))
+        return buf.reshape(B, N, H * hd)
+
+
+def _require_hot_path(mx_quant, top_k, approx, pred_mode, where):
+    if not (mx_quant and top_k and approx and pred_mode == "ex_pred"):
+        raise NotImplementedError(
+            f"{where}: only mx_quant=True, top_k=True, approx/ex_pred=True, pred_mode='ex_pred' is on the "
+            f"B200 hot path (got mx_quant={mx_quant}, top_k={top_k}, approx={approx}, pred_mode={pred_mode!r}); "
+            "dense / related-work predictor modes are out of scope (SURVEY.md 8f3) and there is no fallback")
+
+
+class QuantizedAttention(nn.Module):
+    """DeiT shim - constructor mirrors workloads/deit/scripts/main.py:42."""
+
+    def __init__(self, orig_attn, mx_quant=False, mx_specs=None, top_k=True, k=20, approx_flag=True,
+                 pred_mode="ex_pred", anal=False, file_name_dict=None, block_idx=None, orthogonal_matrix=None):
+        super().__init__()
+        _require_hot_path(mx_quant, top_k, approx_flag, pred_mode, "QuantizedAttention")
+        if anal:
+            raise NotImplementedError("--anal analysis dumps are out of scope (SURVEY.md 8f4)")
+        self.num_heads = orig_attn.num_heads
+        self.scale = orig_attn.scale
+        self.qkv, self.proj = orig_attn.qkv, orig_attn.proj
+        self.proj_drop = getattr(orig_attn, "proj_drop", nn.Identity())
+        self.block_idx = block_idx
+        self.current_timestep = 0
+        self.core = PrunedAttentionCore(mx_specs, k, scale=self.scale)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        x = self.core(qkv[0], qkv[1], qkv[2])         # strided views of the fused buffer, no copies
+        x = self.proj_drop(self.proj(x))
+        self.current_timestep += 1
+        return x
+
+
+class Attention(nn.Module):
+    """DiT shim - constructor mirrors workloads/DiT/models.py:105-126."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_norm=False, proj_bias=True, attn_drop=0.,
+                 proj_drop=0., norm_layer=nn.LayerNorm, mx_quant=False, mx_specs=None, top_k=False, k=20,
+                 ex_pred=False, pred_mode="ex_pred", anal=False, file_name_dict=None, block_idx=None,
+                 exclude_timesteps=None, orthogonal_matrix=None):
+        super().__init__()
+        assert dim % num_heads == 0, 'dim should be divisible by num_heads'
+        _require_hot_path(mx_quant, top_k, ex_pred, pred_mode, "Attention")
+        if anal or exclude_timesteps:
+            raise NotImplementedError("anal / exclude_timesteps (dense steps) are out of scope")
+        self.num_heads, self.head_dim = num_heads, dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.q_norm = norm_layer(self.head_dim) if qk_norm else nn.Identity()
+        self.k_norm = norm_layer(self.head_dim) if qk_norm else nn.Identity()
+        self.proj = nn.Linear(dim, dim, bias=proj_bias)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.block_idx = block_idx
+        self.current_timestep = 0
+        self.core = PrunedAttentionCore(mx_specs, k, scale=self.scale)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv.unbind(0)
+        q, k = self.q_norm(q), self.k_norm(k)
+        x = self.core(q, k, v)
+        x = self.proj_drop(self.proj(x))
+        self.current_timestep += 1
+        return x
+
+
+class MXSelfAttention(nn.Module):
+    """PixArt-alpha shim - mirrors workloads/PixArt/models/MX_transformer_block.py:567-717."""
+
+    def __init__(self, dim, num_heads: int, has_bias: bool = True):
+        super().__init__()
+        self.dim, self.num_heads, self.head_dim, self.has_bias = dim, num_heads, dim // num_heads, has_bias
+        self.to_q = nn.Linear(dim, dim, bias=has_bias)
+        self.to_k = nn.Linear(dim, dim, bias=has_bias)
+        self.to_v = nn.Linear(dim, dim, bias=has_bias)
+        self.to_out = nn.Sequential(nn.Linear(dim, dim, bias=has_bias), nn.Dropout(p=0.0))
+        self.core = None
+        self.current_timestep = 0
+
+    def set_config(self, mx_quant=False, mx_specs=None, top_k=False, k=20, ex_pred=False, exclude_timesteps=None,
+                   pred_mode="ex_pred", block_idx=None, anal=False, file_name_dict=None, orthogonal_matrix=None):
+        _require_hot_path(mx_quant, top_k, ex_pred, pred_mode, "MXSelfAttention.set_config")
+        if anal or exclude_timesteps:
+            raise NotImplementedError("anal / exclude_timesteps (dense steps) are out of scope")
+        self.block_idx = block_idx
+        # reference: scale_factor = 1 / math.sqrt(q.size(-1)) applied as an fp32 scalar (:647-653)
+        self.core = PrunedAttentionCore(mx_specs, k, scale=1.0 / (self.head_dim ** 0.5))
+        return self
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs):
+        if self.core is None:
+            raise RuntimeError("MXSelfAttention.set_config(...) must be called first")
+        B, N, C = hidden_states.shape
+        q = self.to_q(hidden_states).view(B, N, self.num_heads, self.head_dim).transpose(1, 2)
+        k = self.to_k(hidden_states).view(B, N, self.num_heads, self.head_dim).transpose(1, 2)
+        v = self.to_v(hidden_states).view(B, N, self.num_heads, self.head_dim).transpose(1, 2)
+        x = self.to_out(self.core(q, k, v))
+        self.current_timestep += 1
+        return x
