@@ -144,6 +144,14 @@ int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_s
                          uint32_t* mask_out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Which implementation mxp_sparse_attention / mxp_pruned_attention use for the exact stage:
+ *   0 (default)  tcgen05 tensor cores: bf16 operands (exact for MXINT8 values), fp32 TMEM accumulators
+ *   1            CUDA-core dp4a gather path (kept for A/B measurement; needs head_dim % 4 == 0 only)
+ * Process-wide; returns MXP_E_BADARG for any other value.
+ */
+int mxp_set_attention_path(int path);
+
 /* Number of kernel launches the last successful call on this thread enqueued (bench.py's
  * gpu_launches claim is counted from this). */
 int mxp_last_launch_count(void);

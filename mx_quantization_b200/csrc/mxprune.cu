@@ -8,6 +8,7 @@
 #include "mxprune.h"
 #include "mxprune_device.cuh"
 #include "mxprune_predict.cuh"
+#include "mxprune_attend.cuh"
 
 using namespace mxp;
 
@@ -216,17 +217,6 @@ k_predict_scores(const PredParams p, int nkp) {
 //   s_p    [WARPS][NKP]  u8    P codes of the row a warp is working on, dense key positions
 // One warp per query row; lane l owns key positions l, l+32, ... = one P window per step.
 // ------------------------------------------------------------------------------------
-struct AttnParams {
-    const int8_t *q_codes, *q_exps, *k_codes, *k_exps;
-    View v;
-    const uint32_t* mask;
-    int B, H, Nq, Nk, hd;
-    float scale;
-    int bf16, flush;
-    float* out;
-    int64_t o_sB, o_sH, o_sN;
-};
-
 struct AttnSmem {
     int kt_stride;      // NKP + 1
     size_t off_kwf, off_vef, off_v, off_p, total;
@@ -467,6 +457,26 @@ int launch_attn_nb(const AttnParams& p, dim3 grid, cudaStream_t st) {
     }
 }
 
+int g_attn_path = 0;     // 0 = tcgen05 tensor-core path (default), 1 = CUDA-core dp4a path
+
+int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
+    const K2Smem L = k2_smem_layout(p.Nk, p.hd);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_attend_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024);
+        if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int heads = p.B * p.H;
+    const int tiles = (p.Nq + K2T - 1) / K2T;
+    int splits = (148 * 2 + heads - 1) / heads;
+    if (splits > tiles) splits = tiles;
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)heads, (unsigned)splits);
+    k_attend_umma<<<grid, K2T, L.total, st>>>(p);
+    return check_launch("k_attend_umma");
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -477,6 +487,11 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 extern "C" {
 
 int mxp_abi_version(void) { return MXP_ABI_VERSION; }
+int mxp_set_attention_path(int path) {
+    if (path != 0 && path != 1) return fail(MXP_E_BADARG, "attention path %d: 0 = tcgen05, 1 = CUDA-core dp4a", path);
+    g_attn_path = path;
+    return MXP_OK;
+}
 const char* mxp_last_error(void) { return g_err; }
 int mxp_last_launch_count(void) { return g_launches; }
 void mxp_limits(int* max_keys, int* max_head_dim) {
@@ -598,6 +613,10 @@ size_t mxp_sparse_attention_workspace_bytes(int, int, int, int, int) { return 0;
 static int sparse_attention_impl(const AttnParams& p, cudaStream_t st) {
     if (p.Nk > MAX_KEYS_FUSED)
         return fail(MXP_E_UNSUPPORTED, "Nk=%d: sparse attention covers Nk <= %d", p.Nk, MAX_KEYS_FUSED);
+    if (g_attn_path == 0) {
+        if (p.hd & 7) return fail(MXP_E_UNSUPPORTED, "head_dim %d: the tensor-core attention path needs a multiple of 8", p.hd);
+        return launch_attend_umma(p, st);
+    }
     dim3 grid((unsigned)(p.B * p.H), (unsigned)row_splits(p.B * p.H, p.Nq));
     switch ((p.hd + 31) / 32) {
         case 1: return launch_attn_nb<1>(p, grid, st);

@@ -54,6 +54,14 @@ def limits() -> Tuple[int, int]:
     return a.value, b.value
 
 
+def set_attention_path(path: str) -> None:
+    """'tcgen05' (default: both GEMMs of the exact stage on the tensor cores) or 'cuda_core' (dp4a)."""
+    codes = {"tcgen05": 0, "cuda_core": 1}
+    if path not in codes:
+        raise ValueError(f"attention path must be one of {sorted(codes)}")
+    _lib.check(_lib.load().mxp_set_attention_path(codes[path]), "mxp_set_attention_path")
+
+
 def last_launch_count() -> int:
     return _lib.load().mxp_last_launch_count()
 

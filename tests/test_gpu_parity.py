@@ -86,8 +86,10 @@ def test_topk_mask_bit_exact(mxq, B, H, N, hd, kind, bfloat, flush, kfrac):
     assert torch.equal(r["k_codes"].cpu(), kc) and torch.equal(r["k_exps"].cpu(), ke)
 
 
+@pytest.mark.parametrize("path", ["tcgen05", "cuda_core"])
 @pytest.mark.parametrize("B,H,N,hd,kind,bfloat,flush", SHAPES)
-def test_sparse_attention_same_index_set(mxq, B, H, N, hd, kind, bfloat, flush):
+def test_sparse_attention_same_index_set(mxq, B, H, N, hd, kind, bfloat, flush, path):
+    mxq.set_attention_path(path)
     top_k = max(1, int(0.3 * N))
     q, k, v = make_qkv(B, H, N, hd, seed=4, kind=kind)
     specs = mx_specs(bfloat, flush)
@@ -97,6 +99,7 @@ def test_sparse_attention_same_index_set(mxq, B, H, N, hd, kind, bfloat, flush):
     out = mxq.sparse_attention(ref["q_codes"].cuda(), ref["q_exps"].cuda(), ref["k_codes"].cuda(),
                                ref["k_exps"].cuda(), v.cuda(), mask_i32.cuda(), specs,
                                scale=O.default_scale(hd)).cpu()
+    mxq.set_attention_path("tcgen05")
     assert_out_close(out, ref, v, N, bfloat, OUT_TOL, 0.02 if (kind == "randn" and bfloat == 32) else None)
 
 
