@@ -74,6 +74,14 @@ __device__ __forceinline__ uint4 dequant8_bf16(uint32_t lo, uint32_t hi, float w
                       pack_bf16_trunc(f[6], f[7]));
 }
 
+// r[w] for a runtime w without dynamic register indexing (a 3-level select tree)
+__device__ __forceinline__ uint32_t pick8(const uint32_t (&r)[8], int w) {
+    const uint32_t a = (w & 1) ? r[1] : r[0], b = (w & 1) ? r[3] : r[2];
+    const uint32_t c = (w & 1) ? r[5] : r[4], d = (w & 1) ? r[7] : r[6];
+    const uint32_t ab = (w & 2) ? b : a, cd = (w & 2) ? d : c;
+    return (w & 4) ? cd : ab;
+}
+
 __global__ void __launch_bounds__(K2T)
 k_attend_umma(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -95,6 +103,7 @@ k_attend_umma(const AttnParams p) {
     // ---------------- stage K: codes * 2^(e-6) -> bf16 chunks [kc][key]
     {
         const int kchunks = hdp >> 3;
+#pragma unroll 4
         for (int t = tid; t < nkp * kchunks; t += K2T) {
             const int kc = t / nkp, j = t - kc * nkp;        // consecutive threads -> consecutive keys
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -114,11 +123,13 @@ k_attend_umma(const AttnParams p) {
             const int w = t / hdp, d = t - w * hdp;          // consecutive threads -> consecutive columns
             uint32_t xb[32];
             uint32_t mx = 0u;
+            const float* vp = vb + (int64_t)(w * 32) * p.v.sN + d;
+            const int nvalid = (d < hd) ? min(32, Nk - w * 32) : 0;
 #pragma unroll
             for (int tt = 0; tt < 32; ++tt) {
-                const int j = w * 32 + tt;
                 uint32_t b = 0u;
-                if (d < hd && j < Nk) b = __float_as_uint(__ldg(vb + (int64_t)j * p.v.sN + d));
+                if (tt < nvalid) b = __float_as_uint(__ldg(vp));
+                vp += p.v.sN;
                 if (bf16) b = bf16_half_away(b);
                 xb[tt] = b;
                 mx = max(mx, b & 0x7fffffffu);
@@ -151,6 +162,10 @@ k_attend_umma(const AttnParams p) {
         const bool valid = i < Nq;
         const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
 
+        // ---- this row's kept-key bitmask (<= 8 words): requested at once, held in registers
+        uint32_t mreg[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) mreg[w] = (valid && w < NW) ? __ldg(p.mask + row * NW + w) : 0u;
         // ---- Q tile -> bf16 A operand (aliases the P buffer)
         for (int kc = 0; kc < (hdp >> 3); ++kc) {
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -180,7 +195,7 @@ k_attend_umma(const AttnParams p) {
         // ---- pass A: row max over the kept keys (A7: bf16 rounding of the matmul output, * scale)
         float m = -INFINITY;
         for (int w = 0; w < NW; ++w) {
-            const uint32_t mw = valid ? __ldg(p.mask + row * NW + w) : 0u;
+            const uint32_t mw = pick8(mreg, w);
             uint32_t r[32];
             tmem_ld_32x32b_x32(my_tmem + w * 32, r);
             tmem_ld_wait();
@@ -196,7 +211,7 @@ k_attend_umma(const AttnParams p) {
         // ---- pass B: E = exp(t - m) on kept keys, 0 elsewhere; written back over S; row sum
         float sum = 0.f;
         for (int w = 0; w < NW; ++w) {
-            const uint32_t mw = valid ? __ldg(p.mask + row * NW + w) : 0u;
+            const uint32_t mw = pick8(mreg, w);
             uint32_t r[32];
             tmem_ld_32x32b_x32(my_tmem + w * 32, r);
             tmem_ld_wait();
@@ -204,7 +219,7 @@ k_attend_umma(const AttnParams p) {
             for (int c = 0; c < 32; ++c) {
                 float s = __uint_as_float(r[c]);
                 if (bf16) s = bf16_half_away(s);
-                const float ev = ((mw >> c) & 1u) ? expf(__fsub_rn(__fmul_rn(s, p.scale), m)) : 0.f;
+                const float ev = ((mw >> c) & 1u) ? exp_nonpos(__fsub_rn(__fmul_rn(s, p.scale), m)) : 0.f;
                 sum += ev;
                 r[c] = __float_as_uint(ev);
             }

@@ -115,6 +115,22 @@ __device__ __forceinline__ uint32_t keep_lowest_bits(uint32_t x, int m) {
     return y;
 }
 
+// exp(x) for x <= 0, branch-free (the softmax epilogue evaluates it for every key position of a
+// row under a per-thread predicate, so divergence would serialise it).  x*log2(e) is split into
+// n = rint(.) and a remainder f in [-0.5, 0.5] carried in two FMAs (hi/lo parts of log2 e), so the
+// argument error does not grow with |x|; 2^f comes from MUFU.EX2 (<= 2 ulp), 2^n is added into the
+// exponent field.  x is clamped at -87 (exp(-87) ~ 1.6e-38, the last normal binade).
+__device__ __forceinline__ float exp_nonpos(float x) {
+    x = fmaxf(x, -87.0f);
+    const float t = fmaf(x, 1.4426950216293335f, 12582912.0f);         // 1.5 * 2^23 + rint(x * log2e)
+    const float n = t - 12582912.0f;
+    float f = fmaf(x, 1.4426950216293335f, -n);
+    f = fmaf(x, 1.9259629911266175e-8f, f);
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f));
+    return __uint_as_float(__float_as_uint(r) + (__float_as_uint(t) << 23));
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));

@@ -311,6 +311,7 @@ k_predict_topk_rows(const PredParams p) {
         const int moff = ((int)M + 1) & ~1;
 
         // ---- pass 1: integer scores -> packed 15-bit keys in shared memory
+        // (groups of 8 keys; only the last group can contain padding keys, which get key 0)
         for (int jg = 0; jg < ng; ++jg) {
             uint32_t us[8];
 #pragma unroll
@@ -324,9 +325,12 @@ k_predict_topk_rows(const PredParams p) {
                     const int c = nbw - 2 * __popc(rq.sign[b] ^ rec.x);
                     S += (c * (int)rec.y) * mq[b];
                 }
-                uint32_t u = ((uint32_t)S >> 1) + 1u;
-                if (j >= Nk) u = 0u;
-                us[t] = u | 0x8000u;
+                us[t] = (((uint32_t)S >> 1) + 1u) | 0x8000u;
+            }
+            if (jg == ng - 1) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (jg * 8 + t >= Nk) us[t] = 0x8000u;
             }
             *reinterpret_cast<uint4*>(my_sc + jg * 4) =
                 make_uint4(us[0] | (us[4] << 16), us[1] | (us[5] << 16), us[2] | (us[6] << 16),

@@ -46,7 +46,9 @@ def main():
                 i = hdr.index(w)
                 lines.append(f"  {w:72s} {r[i]} {units[i]}")
     for kn in dict.fromkeys(names):
-        short = kn.split('<')[0].split('::')[-1]
+        import re
+        mm = re.search(r'([A-Za-z_][A-Za-z_0-9]*)\s*(<|\()', kn)
+        short = mm.group(1) if mm else kn
         src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--kernel-name",
                                                 "regex:" + short]))))
         if len(src) < 3:
