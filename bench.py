@@ -48,10 +48,12 @@ def mx_specs(bfloat, flush):
 def bytes_per_head(N, hd):
     """ALGORITHMIC bytes per (batch, head) unit (DESIGN.md 'Measurement')."""
     nb, nw = (hd + 31) // 32, (N + 31) // 32
+    hdp = (hd + 15) // 16 * 16
     pred = 2 * N * hd * 4 + N * nw * 4                       # Q,K fp32 in ; bitmask out
-    attn = 2 * N * hd * 4 + 2 * N * (hd + nb) + N * nw * 4   # V in, O out ; compact Q,K ; mask in
+    prep = N * hd * 4 + N * hdp * 2                          # V fp32 in ; bf16 V^T operand out
+    attn = 3 * N * hdp * 2 + N * nw * 4 + N * hd * 4         # bf16 Q,K,V operands + mask in ; O fp32 out
     full = 16 * N * hd                                       # Q,K,V in ; O out
-    return {"predict_topk": pred, "sparse_attention": attn, "full": full}
+    return {"predict_topk": pred, "prep_v": prep, "exact_attention": attn, "full": full}
 
 
 def hbm_peak():
@@ -246,23 +248,19 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    # ---- per-kernel timing (same stream, CUDA events around each launch) for the roofline
-    kt = {"predict_topk": 0.0, "sparse_attention": 0.0}
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    # ---- per-kernel timing for the roofline: CUDA events around each kernel of the same call,
+    # recorded inside the library on the launching stream (mxp_pruned_attention_profile)
+    kt = {"predict_topk": 0.0, "prep_v": 0.0, "exact_attention": 0.0}
     reps = 0
-    for it in range(1 + max(1, min(args.steps, 3))):        # first pass untimed (allocator warm-up)
+    for it in range(1 + max(1, min(args.steps, 3))):        # first pass untimed
         for (q, k, v) in layers:
-            e[0].record()
-            r = mxq.predict_topk(q, k, specs, top_k, return_codes=True)
-            e[1].record()
-            mxq.sparse_attention(r["q_codes"], r["q_exps"], r["k_codes"], r["k_exps"], v, r["mask"], specs,
-                                 out=out_view)
-            e[2].record()
-            e[2].synchronize()
+            ms3 = []
+            mxq.pruned_attention(q, k, v, specs, top_k, out=out_view, _kernel_ms=ms3)
             if it == 0:
                 continue
-            kt["predict_topk"] += e[0].elapsed_time(e[1])
-            kt["sparse_attention"] += e[1].elapsed_time(e[2])
+            kt["predict_topk"] += ms3[0]
+            kt["prep_v"] += ms3[1]
+            kt["exact_attention"] += ms3[2]
             reps += 1
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:

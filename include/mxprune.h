@@ -145,6 +145,20 @@ int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_s
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Measurement aid: same as mxp_pruned_attention (tcgen05 path), but brackets the three kernels
+ * (predict+top-k, V operand prep, exact attention) with CUDA events on `stream`, SYNCHRONISES, and
+ * returns their durations in milliseconds in kernel_ms[0..2].  bench.py's roofline uses this.
+ */
+int mxp_pruned_attention_profile(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                                 const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                                 const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                                 int B, int H, int Nq, int Nk, int hd, int top_k,
+                                 float scale, int bfloat_bits, int flush,
+                                 float* out, int64_t o_sB, int64_t o_sH, int64_t o_sN,
+                                 uint32_t* mask_out,
+                                 void* workspace, size_t workspace_bytes, void* stream, float* kernel_ms);
+
+/*
  * Which implementation mxp_sparse_attention / mxp_pruned_attention use for the exact stage:
  *   0 (default)  tcgen05 tensor cores: bf16 operands (exact for MXINT8 values), fp32 TMEM accumulators
  *   1            CUDA-core dp4a gather path (kept for A/B measurement; needs head_dim % 4 == 0 only)

@@ -217,6 +217,17 @@ k_predict_scores(const PredParams p, int nkp) {
 //   s_p    [WARPS][NKP]  u8    P codes of the row a warp is working on, dense key positions
 // One warp per query row; lane l owns key positions l, l+32, ... = one P window per step.
 // ------------------------------------------------------------------------------------
+struct AttnCoreParams {          // CUDA-core (dp4a) attention path: consumes compact codes
+    const int8_t *q_codes, *q_exps, *k_codes, *k_exps;
+    View v;
+    const uint32_t* mask;
+    int B, H, Nq, Nk, hd;
+    float scale;
+    int bf16, flush;
+    float* out;
+    int64_t o_sB, o_sH, o_sN;
+};
+
 struct AttnSmem {
     int kt_stride;      // NKP + 1
     size_t off_kwf, off_vef, off_v, off_p, total;
@@ -238,7 +249,7 @@ __host__ __device__ inline AttnSmem attn_smem_layout(int nb, int kpl, int hd) {
 
 template <int NB, int KPL>
 __global__ void __launch_bounds__(THREADS)
-k_sparse_attention(const AttnParams p) {
+k_sparse_attention(const AttnCoreParams p) {
     constexpr int NKP = KPL * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int hd = p.hd, HW = hd >> 2, Nk = p.Nk, Nq = p.Nq;
@@ -437,7 +448,7 @@ int launch_predict_topk_nb(const PredParams& p, cudaStream_t st) {
 }
 
 template <int NB, int KPL>
-int launch_attn_one(const AttnParams& p, dim3 grid, cudaStream_t st) {
+int launch_attn_one(const AttnCoreParams& p, dim3 grid, cudaStream_t st) {
     const AttnSmem L = attn_smem_layout(NB, KPL, p.hd);
     cudaError_t e = cudaFuncSetAttribute(k_sparse_attention<NB, KPL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
@@ -447,7 +458,7 @@ int launch_attn_one(const AttnParams& p, dim3 grid, cudaStream_t st) {
 }
 
 template <int NB>
-int launch_attn_nb(const AttnParams& p, dim3 grid, cudaStream_t st) {
+int launch_attn_nb(const AttnCoreParams& p, dim3 grid, cudaStream_t st) {
     switch (pick_kpl(p.Nk)) {
         case 1: return launch_attn_one<NB, 1>(p, grid, st);
         case 2: return launch_attn_one<NB, 2>(p, grid, st);
@@ -458,23 +469,57 @@ int launch_attn_nb(const AttnParams& p, dim3 grid, cudaStream_t st) {
 }
 
 int g_attn_path = 0;     // 0 = tcgen05 tensor-core path (default), 1 = CUDA-core dp4a path
+thread_local cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+thread_local bool g_profile = false;
+inline void prof_mark(int i, cudaStream_t st) {
+    if (!g_profile) return;
+    if (!g_ev[i]) cudaEventCreate(&g_ev[i]);
+    cudaEventRecord(g_ev[i], st);
+}
 
 int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
-    const K2Smem L = k2_smem_layout(p.Nk, p.hd);
+    const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
+    const K2Smem L = k2_smem_layout(O);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attend_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_attend_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
+    if (L.total > 160 * 1024) return fail(MXP_E_UNSUPPORTED, "attention operands need %zu bytes of shared memory", L.total);
     const int heads = p.B * p.H;
-    const int tiles = (p.Nq + K2T - 1) / K2T;
     int splits = (148 * 2 + heads - 1) / heads;
-    if (splits > tiles) splits = tiles;
+    if (splits > O.q_tiles) splits = O.q_tiles;
     if (splits < 1) splits = 1;
     dim3 grid((unsigned)heads, (unsigned)splits);
     k_attend_umma<<<grid, K2T, L.total, st>>>(p);
     return check_launch("k_attend_umma");
+}
+
+int launch_prep_v(const View& v, int B, int H, int Nq, int Nk, int hd, int bf16, int flush, unsigned char* v_op,
+                  cudaStream_t st) {
+    const OpsLayout O = ops_layout(Nq, Nk, hd);
+    VPrepParams vp{v, H, Nq, Nk, hd, bf16, flush, v_op};
+    dim3 grid((unsigned)(B * H), (unsigned)((O.nblk * O.wpb + 3) / 4));
+    k_prep_v<<<grid, K2T, 0, st>>>(vp);
+    return check_launch("k_prep_v");
+}
+
+int launch_codes_to_ops(const int8_t* codes, const int8_t* exps, unsigned char* ops, int heads, int Nq, int Nk,
+                        int hd, int which, cudaStream_t st) {
+    const OpsLayout O = ops_layout(Nq, Nk, hd);
+    const int64_t total = (int64_t)heads * (which == 0 ? O.q_tiles * K2T : O.nblk * O.kb_rows) * (O.hdp >> 3);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_codes_to_ops<<<(unsigned)blocks, 256, 0, st>>>(codes, exps, ops, heads, Nq, Nk, hd, which);
+    return check_launch("k_codes_to_ops");
+}
+
+struct OpsBytes { size_t q, k, v; };
+inline OpsBytes ops_bytes(int B, int H, int Nq, int Nk, int hd) {
+    const OpsLayout O = ops_layout(Nq, Nk, hd);
+    const size_t bh = (size_t)B * H;
+    return OpsBytes{bh * O.q_head_bytes, bh * O.k_head_bytes, bh * O.v_head_bytes};
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -608,15 +653,14 @@ int mxp_predict_topk(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
     return predict_topk_impl(p, (cudaStream_t)stream);
 }
 
-size_t mxp_sparse_attention_workspace_bytes(int, int, int, int, int) { return 0; }
+size_t mxp_sparse_attention_workspace_bytes(int B, int H, int Nq, int Nk, int hd) {
+    const OpsBytes ob = ops_bytes(B, H, Nq, Nk, hd);
+    return align256(ob.q) + align256(ob.k) + align256(ob.v);
+}
 
-static int sparse_attention_impl(const AttnParams& p, cudaStream_t st) {
+static int attend_core_impl(const AttnCoreParams& p, cudaStream_t st) {
     if (p.Nk > MAX_KEYS_FUSED)
-        return fail(MXP_E_UNSUPPORTED, "Nk=%d: sparse attention covers Nk <= %d", p.Nk, MAX_KEYS_FUSED);
-    if (g_attn_path == 0) {
-        if (p.hd & 7) return fail(MXP_E_UNSUPPORTED, "head_dim %d: the tensor-core attention path needs a multiple of 8", p.hd);
-        return launch_attend_umma(p, st);
-    }
+        return fail(MXP_E_UNSUPPORTED, "Nk=%d: the CUDA-core attention path covers Nk <= %d", p.Nk, MAX_KEYS_FUSED);
     dim3 grid((unsigned)(p.B * p.H), (unsigned)row_splits(p.B * p.H, p.Nq));
     switch ((p.hd + 31) / 32) {
         case 1: return launch_attn_nb<1>(p, grid, st);
@@ -630,7 +674,7 @@ int mxp_sparse_attention(const int8_t* q_codes, const int8_t* q_exps, const int8
                          const int8_t* k_exps, const float* v, int64_t v_sB, int64_t v_sH,
                          int64_t v_sN, const uint32_t* mask, int B, int H, int Nq, int Nk, int hd,
                          float scale, int bfloat_bits, int flush, float* out, int64_t o_sB,
-                         int64_t o_sH, int64_t o_sN, void*, size_t, void* stream) {
+                         int64_t o_sH, int64_t o_sN, void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
     int rc = check_shape(B, H, Nq, Nk, hd, bfloat_bits);
     if (rc) return rc;
@@ -638,22 +682,45 @@ int mxp_sparse_attention(const int8_t* q_codes, const int8_t* q_exps, const int8
     if ((rc = check_view("out", out, o_sB, o_sH, o_sN, hd))) return rc;
     if (!q_codes || !q_exps || !k_codes || !k_exps || !mask)
         return fail(MXP_E_BADARG, "codes/exps/mask: null pointer");
-    if (((uintptr_t)q_codes & 3) || ((uintptr_t)k_codes & 3) || ((uintptr_t)mask & 3))
-        return fail(MXP_E_BADARG, "codes/mask must be 4-byte aligned");
+    if (((uintptr_t)q_codes & 7) || ((uintptr_t)k_codes & 7) || ((uintptr_t)mask & 3))
+        return fail(MXP_E_BADARG, "codes must be 8-byte aligned, mask 4-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g_attn_path == 1) {
+        AttnCoreParams p{};
+        p.q_codes = q_codes; p.q_exps = q_exps; p.k_codes = k_codes; p.k_exps = k_exps;
+        p.v = View{v, v_sB, v_sH, v_sN};
+        p.mask = mask;
+        p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk; p.hd = hd;
+        p.scale = scale; p.bf16 = bfloat_bits == 16; p.flush = flush != 0;
+        p.out = out; p.o_sB = o_sB; p.o_sH = o_sH; p.o_sN = o_sN;
+        return attend_core_impl(p, st);
+    }
+    if (hd & 7) return fail(MXP_E_UNSUPPORTED, "head_dim %d: the tensor-core attention path needs a multiple of 8", hd);
+    const size_t need = mxp_sparse_attention_workspace_bytes(B, H, Nq, Nk, hd);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
+        return fail(MXP_E_BADARG, "workspace: need %zu bytes, 256-byte aligned", need);
+    const OpsBytes ob = ops_bytes(B, H, Nq, Nk, hd);
+    unsigned char* w = (unsigned char*)workspace;
+    unsigned char* q_op = w; w += align256(ob.q);
+    unsigned char* k_op = w; w += align256(ob.k);
+    unsigned char* v_op = w;
+    if ((rc = launch_codes_to_ops(q_codes, q_exps, q_op, B * H, Nq, Nk, hd, 0, st))) return rc;
+    if ((rc = launch_codes_to_ops(k_codes, k_exps, k_op, B * H, Nq, Nk, hd, 1, st))) return rc;
+    if ((rc = launch_prep_v(View{v, v_sB, v_sH, v_sN}, B, H, Nq, Nk, hd, bfloat_bits == 16, flush != 0, v_op, st))) return rc;
     AttnParams p{};
-    p.q_codes = q_codes; p.q_exps = q_exps; p.k_codes = k_codes; p.k_exps = k_exps;
-    p.v = View{v, v_sB, v_sH, v_sN};
-    p.mask = mask;
+    p.q_op = q_op; p.k_op = k_op; p.v_op = v_op; p.mask = mask;
     p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk; p.hd = hd;
     p.scale = scale; p.bf16 = bfloat_bits == 16; p.flush = flush != 0;
     p.out = out; p.o_sB = o_sB; p.o_sH = o_sH; p.o_sN = o_sN;
-    return sparse_attention_impl(p, (cudaStream_t)stream);
+    return launch_attend_umma(p, st);
 }
 
 size_t mxp_pruned_attention_workspace_bytes(int B, int H, int Nq, int Nk, int hd) {
     const size_t bh = (size_t)B * H, nb = (size_t)(hd + 31) / 32, nw = (size_t)(Nk + 31) / 32;
-    return align256(bh * Nq * hd) + align256(bh * Nq * nb) + align256(bh * Nk * hd) +
-           align256(bh * Nk * nb) + align256(bh * Nq * nw * 4);
+    const OpsBytes ob = ops_bytes(B, H, Nq, Nk, hd);
+    const size_t ops = align256(ob.q) + align256(ob.k) + align256(ob.v);
+    const size_t codes = align256(bh * Nq * hd) + align256(bh * Nq * nb) + align256(bh * Nk * hd) + align256(bh * Nk * nb);
+    return (ops > codes ? ops : codes) + align256(bh * Nq * nw * 4);
 }
 
 int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
@@ -674,13 +741,12 @@ int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_s
     const size_t need = mxp_pruned_attention_workspace_bytes(B, H, Nq, Nk, hd);
     if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
         return fail(MXP_E_BADARG, "workspace: need %zu bytes, 256-byte aligned", need);
-    const size_t bh = (size_t)B * H, nb = (size_t)(hd + 31) / 32;
+    const bool tc = g_attn_path == 0;
+    if (tc && (hd & 7)) return fail(MXP_E_UNSUPPORTED, "head_dim %d: the tensor-core attention path needs a multiple of 8", hd);
+    const size_t bh = (size_t)B * H, nb = (size_t)(hd + 31) / 32, nw = (size_t)(Nk + 31) / 32;
+    const OpsBytes ob = ops_bytes(B, H, Nq, Nk, hd);
     unsigned char* w = (unsigned char*)workspace;
-    int8_t* qc = (int8_t*)w; w += align256(bh * Nq * hd);
-    int8_t* qe = (int8_t*)w; w += align256(bh * Nq * nb);
-    int8_t* kc = (int8_t*)w; w += align256(bh * Nk * hd);
-    int8_t* ke = (int8_t*)w; w += align256(bh * Nk * nb);
-    uint32_t* mask = mask_out ? mask_out : (uint32_t*)w;
+    uint32_t* mask = mask_out ? mask_out : (uint32_t*)(w + need - align256(bh * Nq * nw * 4));
     cudaStream_t st = (cudaStream_t)stream;
 
     PredParams pp{};
@@ -689,17 +755,59 @@ int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_s
     pp.B = B; pp.H = H; pp.Nq = Nq; pp.Nk = Nk; pp.hd = hd; pp.top_k = top_k;
     pp.bf16 = bfloat_bits == 16; pp.flush = flush != 0;
     pp.mask = mask; pp.idx = nullptr;
+    if (tc) {
+        unsigned char* q_op = w; w += align256(ob.q);
+        unsigned char* k_op = w; w += align256(ob.k);
+        unsigned char* v_op = w;
+        pp.q_op = q_op; pp.k_op = k_op;
+        prof_mark(0, st);
+        if ((rc = predict_topk_impl(pp, st))) return rc;
+        prof_mark(1, st);
+        if ((rc = launch_prep_v(View{v, v_sB, v_sH, v_sN}, B, H, Nq, Nk, hd, bfloat_bits == 16, flush != 0, v_op, st))) return rc;
+        prof_mark(2, st);
+        AttnParams ap{};
+        ap.q_op = q_op; ap.k_op = k_op; ap.v_op = v_op; ap.mask = mask;
+        ap.B = B; ap.H = H; ap.Nq = Nq; ap.Nk = Nk; ap.hd = hd;
+        ap.scale = scale; ap.bf16 = bfloat_bits == 16; ap.flush = flush != 0;
+        ap.out = out; ap.o_sB = o_sB; ap.o_sH = o_sH; ap.o_sN = o_sN;
+        rc = launch_attend_umma(ap, st);
+        prof_mark(3, st);
+        return rc;
+    }
+    int8_t* qc = (int8_t*)w; w += align256(bh * Nq * hd);
+    int8_t* qe = (int8_t*)w; w += align256(bh * Nq * nb);
+    int8_t* kc = (int8_t*)w; w += align256(bh * Nk * hd);
+    int8_t* ke = (int8_t*)w;
     pp.q_codes = qc; pp.q_exps = qe; pp.k_codes = kc; pp.k_exps = ke;
     if ((rc = predict_topk_impl(pp, st))) return rc;
-
-    AttnParams ap{};
+    AttnCoreParams ap{};
     ap.q_codes = qc; ap.q_exps = qe; ap.k_codes = kc; ap.k_exps = ke;
     ap.v = View{v, v_sB, v_sH, v_sN};
     ap.mask = mask;
     ap.B = B; ap.H = H; ap.Nq = Nq; ap.Nk = Nk; ap.hd = hd;
     ap.scale = scale; ap.bf16 = bfloat_bits == 16; ap.flush = flush != 0;
     ap.out = out; ap.o_sB = o_sB; ap.o_sH = o_sH; ap.o_sN = o_sN;
-    return sparse_attention_impl(ap, st);
+    return attend_core_impl(ap, st);
+}
+
+int mxp_pruned_attention_profile(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                                 const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                                 const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                                 int B, int H, int Nq, int Nk, int hd, int top_k, float scale,
+                                 int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
+                                 int64_t o_sN, uint32_t* mask_out, void* workspace, size_t workspace_bytes,
+                                 void* stream, float* kernel_ms) {
+    if (!kernel_ms) return fail(MXP_E_BADARG, "kernel_ms: null pointer");
+    if (g_attn_path != 0) return fail(MXP_E_UNSUPPORTED, "per-kernel profile is implemented for the tcgen05 path");
+    g_profile = true;
+    int rc = mxp_pruned_attention(q, q_sB, q_sH, q_sN, k, k_sB, k_sH, k_sN, v, v_sB, v_sH, v_sN, B, H, Nq, Nk, hd,
+                                  top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, mask_out, workspace,
+                                  workspace_bytes, stream);
+    g_profile = false;
+    if (rc) return rc;
+    if (cudaEventSynchronize(g_ev[3]) != cudaSuccess) return fail(MXP_E_CUDA, "cudaEventSynchronize failed");
+    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&kernel_ms[i], g_ev[i], g_ev[i + 1]);
+    return MXP_OK;
 }
 
 }  // extern "C"

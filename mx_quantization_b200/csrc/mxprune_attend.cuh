@@ -1,4 +1,4 @@
-// K2: exact MXINT8 attention over the kept keys on the Blackwell tensor cores (Nk <= 256).
+// K2: exact MXINT8 attention over the kept keys on the Blackwell tensor cores (any Nk).
 //
 // Key fact: every MXINT8 value c * 2^(e-6) (|c| <= 127) is EXACTLY representable in bf16 (8
 // significant bits, fp32 exponent range).  So both contractions of the reference,
@@ -8,18 +8,22 @@
 // tcgen05.mma kind::f16 with bf16 inputs and fp32 accumulators in tensor memory.  No product is
 // altered; only the fp32 summation order differs from MKL's (as between any two BLAS).
 //
-// One CTA (128 threads) per (head, row split).  Thread t owns query row t of the tile == TMEM
-// lane t, so the softmax / P-quantisation epilogue needs no cross-thread communication at all.
-//   stage (per head)  K codes/exps -> bf16 B-operand chunks;  V fp32 -> A1 -> MXINT8 along TOKENS
-//                     (32-token windows per column, matmul.py:76-83) -> bf16 B-operand chunks (V^T)
-//   per 128-row tile  Q codes -> bf16 A operand; S = Q.K^T  (hd/16 MMAs, M=128, N=Nk)  -> TMEM
-//                     pass A: max over kept keys;  pass B: E = exp(s - max) kept / 0 pruned, sum,
-//                     E written back to TMEM;  pass C: P = E/sum -> A1 -> MXINT8 per 32-key window
-//                     of original positions -> bf16 A operand;  O += P_w . V_w (2 MMAs per window)
-//                     O (fp32, TMEM) -> A1 -> global
-// Operand layout in shared memory: K-major, no swizzle; a 16-byte chunk holds 8 consecutive K
-// elements of one row; chunk (row r, k-chunk c) lives at c*(ROWS*16) + r*16, i.e. SBO = 128 B,
-// LBO = ROWS*16 B.  Threads write one chunk each with consecutive r -> conflict-free 128-bit stores.
+// Operands arrive "MMA-ready" in HBM (OpsLayout below): K1 writes the dequantised Q and K as bf16
+// in the exact shared-memory image the MMA wants (K-major, no swizzle, 16-byte chunks of 8
+// consecutive K elements; chunk (row r, k-chunk c) at c*(ROWS*16) + r*16  =>  SBO = 128 B,
+// LBO = ROWS*16 B), k_prep_v does the same for V^T after quantising V along TOKENS
+// (matmul.py:76-83).  K2 therefore stages with TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx) and spends its instructions on the softmax / P-quantisation epilogue only.
+//
+// One CTA (128 threads) per (head, row split); thread t owns query row t of the tile == TMEM
+// lane t, so the epilogue needs no cross-thread communication.
+//   Nk <= 256  one key block: S = Q.K^T (hd/16 MMAs, N = Nk) -> TMEM; pass A max over kept keys;
+//              pass B E = exp(s - max) (0 where pruned) written back over S, row sum; pass C
+//              P = E/sum -> A1 -> MXINT8 per 32-key window -> bf16 A operand, O += P_w.V_w
+//              (O reuses the TMEM columns of windows already consumed).
+//   Nk  > 256  key blocks of 128: pass 1 streams the blocks with an online max/sum, pass 2
+//              streams them again (S recomputed by the tensor core) to form P and accumulate O
+//              in its own TMEM columns.
 #pragma once
 #include "mxprune_device.cuh"
 #include "mxprune_umma.cuh"
@@ -27,12 +31,12 @@
 namespace mxp {
 
 constexpr int K2T = 128;
-constexpr int K2_PW = 4;                       // P windows buffered per MMA group (4 x 32 keys)
-constexpr int K2_P_BYTES = K2_PW * 4 * K2T * 16;   // 32 KiB; also holds the Q tile (<= 16 chunks)
+constexpr int K2_PW = 4;                           // P windows buffered per MMA group (4 x 32 keys)
+constexpr int K2_P_BYTES = K2_PW * 4 * K2T * 16;   // 32 KiB
+constexpr int K2_SINGLE_MAX = 256;                 // largest Nk handled as one key block
 
 struct AttnParams {
-    const int8_t *q_codes, *q_exps, *k_codes, *k_exps;
-    View v;
+    const unsigned char *q_op, *k_op, *v_op;       // MMA-ready bf16 operands (OpsLayout)
     const uint32_t* mask;
     int B, H, Nq, Nk, hd;
     float scale;
@@ -41,37 +45,70 @@ struct AttnParams {
     int64_t o_sB, o_sH, o_sN;
 };
 
-struct K2Smem {
-    int nkp, hdp, nw, tmem_cols;
-    size_t off_v, off_p, total;
+// Layout of the MMA-ready operand buffers of one head (all sizes in bytes).
+struct OpsLayout {
+    int hdp, nw, single, kb_rows, nblk, wpb, q_tiles;
+    size_t q_tile_bytes, k_blk_bytes, v_blk_bytes, q_head_bytes, k_head_bytes, v_head_bytes;
 };
 
-__host__ __device__ inline K2Smem k2_smem_layout(int Nk, int hd) {
-    K2Smem L;
-    L.nkp = (Nk + 15) & ~15;
+__host__ __device__ inline OpsLayout ops_layout(int Nq, int Nk, int hd) {
+    OpsLayout L;
     L.hdp = (hd + 15) & ~15;
     L.nw = (Nk + 31) >> 5;
-    int need = L.nkp > L.hdp ? L.nkp : L.hdp;
+    L.single = Nk <= K2_SINGLE_MAX;
+    L.kb_rows = L.single ? ((Nk + 15) & ~15) : 128;            // key rows per block (MMA N)
+    L.nblk = L.single ? 1 : (Nk + 127) / 128;
+    L.wpb = L.single ? L.nw : 4;                                // 32-key windows per block
+    L.q_tiles = (Nq + K2T - 1) / K2T;
+    L.q_tile_bytes = (size_t)(L.hdp / 8) * K2T * 16;
+    L.k_blk_bytes = (size_t)(L.hdp / 8) * L.kb_rows * 16;
+    L.v_blk_bytes = (size_t)(L.wpb * 4) * L.hdp * 16;
+    L.q_head_bytes = L.q_tile_bytes * L.q_tiles;
+    L.k_head_bytes = L.k_blk_bytes * L.nblk;
+    L.v_head_bytes = L.v_blk_bytes * L.nblk;
+    return L;
+}
+// byte offset (within a head) of the 16-byte chunk holding dims [8kc, 8kc+8) of query row i
+__host__ __device__ inline size_t q_op_offset(const OpsLayout& L, int i, int kc) {
+    return (size_t)(i / K2T) * L.q_tile_bytes + ((size_t)kc * K2T + (i % K2T)) * 16;
+}
+// ... of key row j
+__host__ __device__ inline size_t k_op_offset(const OpsLayout& L, int j, int kc) {
+    const int blk = L.single ? 0 : j / 128, jl = L.single ? j : j % 128;
+    return (size_t)blk * L.k_blk_bytes + ((size_t)kc * L.kb_rows + jl) * 16;
+}
+// ... holding tokens [8tc, 8tc+8) of V column d
+__host__ __device__ inline size_t v_op_offset(const OpsLayout& L, int tc, int d) {
+    const int blk = L.single ? 0 : tc / 16, tl = L.single ? tc : tc % 16;
+    return (size_t)blk * L.v_blk_bytes + ((size_t)tl * L.hdp + d) * 16;
+}
+
+struct K2Smem {
+    int tmem_cols;
+    size_t off_v, off_p, total;
+};
+__host__ __device__ inline K2Smem k2_smem_layout(const OpsLayout& O) {
+    K2Smem L;
+    int need = O.single ? (O.kb_rows > O.hdp ? O.kb_rows : O.hdp) : 256;
     int c = 32;
     while (c < need) c <<= 1;
     L.tmem_cols = c;
-    size_t o = (size_t)(L.hdp / 8) * L.nkp * 16;        // K operand
-    L.off_v = o; o += (size_t)(L.nw * 4) * L.hdp * 16;  // V^T operand
-    L.off_p = o; o += K2_P_BYTES;                       // P window group / Q tile
+    size_t o = O.k_blk_bytes;
+    L.off_v = o; o += O.v_blk_bytes;
+    L.off_p = o; o += K2_P_BYTES;                    // P window group; also the Q tile (<= 32 KiB)
     L.total = o;
     return L;
 }
 
-// 8 int8 codes (two words) of one MX block with exponent weight w = 2^(e-6) -> 8 bf16 in a uint4
-__device__ __forceinline__ uint4 dequant8_bf16(uint32_t lo, uint32_t hi, float w) {
-    float f[8];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        f[t] = (float)(int)(signed char)((lo >> (8 * t)) & 0xff) * w;
-        f[4 + t] = (float)(int)(signed char)((hi >> (8 * t)) & 0xff) * w;
-    }
-    return make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]), pack_bf16_trunc(f[4], f[5]),
-                      pack_bf16_trunc(f[6], f[7]));
+// ---- TMA bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 // r[w] for a runtime w without dynamic register indexing (a 3-level select tree)
@@ -85,200 +122,228 @@ __device__ __forceinline__ uint32_t pick8(const uint32_t (&r)[8], int w) {
 __global__ void __launch_bounds__(K2T)
 k_attend_umma(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar_s, bar_o;
+    __shared__ uint64_t bar_ld, bar_s, bar_o;
     __shared__ uint32_t tmem_base_s;
     const int Nk = p.Nk, Nq = p.Nq, hd = p.hd;
-    const K2Smem L = k2_smem_layout(Nk, hd);
-    const int nkp = L.nkp, hdp = L.hdp, NW = L.nw, NB = (hd + 31) >> 5;
+    const OpsLayout O = ops_layout(Nq, Nk, hd);
+    const K2Smem L = k2_smem_layout(O);
+    const int hdp = O.hdp, NW = O.nw, kbr = O.kb_rows;
+    const bool single = O.single;
     unsigned char* sK = smem;
     unsigned char* sV = smem + L.off_v;
     unsigned char* sP = smem + L.off_p;
     const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool bf16 = p.bf16, flush = p.flush;
+    const unsigned char* q_op = p.q_op + (size_t)head * O.q_head_bytes;
+    const unsigned char* k_op = p.k_op + (size_t)head * O.k_head_bytes;
+    const unsigned char* v_op = p.v_op + (size_t)head * O.v_head_bytes;
 
-    if (tid == 0) { mbar_init(&bar_s, 1); mbar_init(&bar_o, 1); }
+    if (tid == 0) { mbar_init(&bar_ld, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1); }
     if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)L.tmem_cols);
-
-    // ---------------- stage K: codes * 2^(e-6) -> bf16 chunks [kc][key]
-    {
-        const int kchunks = hdp >> 3;
-#pragma unroll 4
-        for (int t = tid; t < nkp * kchunks; t += K2T) {
-            const int kc = t / nkp, j = t - kc * nkp;        // consecutive threads -> consecutive keys
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (j < Nk && kc * 8 < hd) {
-                const int64_t krow = (int64_t)head * Nk + j;
-                const uint2 c = __ldg(reinterpret_cast<const uint2*>(p.k_codes + krow * hd + kc * 8));
-                const float w = exp2i((int)__ldg(p.k_exps + krow * NB + (kc >> 2)) - 6);
-                v = dequant8_bf16(c.x, c.y, w);
-            }
-            *reinterpret_cast<uint4*>(sK + ((size_t)kc * nkp + j) * 16) = v;
-        }
-    }
-    // ---------------- stage V: A1, MXINT8 along tokens (32-token windows per column), -> bf16 [tc][d]
-    {
-        const float* vb = p.v.p + bb * p.v.sB + hh * p.v.sH;
-        for (int t = tid; t < NW * hdp; t += K2T) {
-            const int w = t / hdp, d = t - w * hdp;          // consecutive threads -> consecutive columns
-            uint32_t xb[32];
-            uint32_t mx = 0u;
-            const float* vp = vb + (int64_t)(w * 32) * p.v.sN + d;
-            const int nvalid = (d < hd) ? min(32, Nk - w * 32) : 0;
-#pragma unroll
-            for (int tt = 0; tt < 32; ++tt) {
-                uint32_t b = 0u;
-                if (tt < nvalid) b = __float_as_uint(__ldg(vp));
-                vp += p.v.sN;
-                if (bf16) b = bf16_half_away(b);
-                xb[tt] = b;
-                mx = max(mx, b & 0x7fffffffu);
-            }
-            const int e = mx_shared_exp(mx);
-            const bool dead = flush && e <= -127;
-            const float wgt = exp2i(e - 6);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float f[8];
-#pragma unroll
-                for (int tt = 0; tt < 8; ++tt) f[tt] = (float)mx_code(xb[q * 8 + tt], e, dead) * wgt;
-                *reinterpret_cast<uint4*>(sV + ((size_t)(w * 4 + q) * hdp + d) * 16) =
-                    make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]),
-                               pack_bf16_trunc(f[4], f[5]), pack_bf16_trunc(f[6], f[7]));
-            }
-        }
-    }
     tcgen05_fence_before_sync();
     __syncthreads();
     tcgen05_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 lanes
-    const uint32_t idesc_s = umma_idesc_bf16_f32(128, nkp);
+    const uint32_t o_col = single ? 0u : 128u;
+    const uint32_t idesc_s = umma_idesc_bf16_f32(128, kbr);
     const uint32_t idesc_o = umma_idesc_bf16_f32(128, hdp);
-    uint32_t ph_s = 0, ph_o = 0;
+    uint32_t ph_ld = 0, ph_s = 0, ph_o = 0;
 
-    for (int i0 = blockIdx.y * K2T; i0 < Nq; i0 += K2T * gridDim.y) {
-        const int i = i0 + tid;
+    if (single) {                                  // the head's K and V operands stay resident
+        if (tid == 0) {
+            mbar_expect_tx(&bar_ld, (uint32_t)(O.k_blk_bytes + O.v_blk_bytes));
+            tma_bulk_g2s(sK, k_op, (uint32_t)O.k_blk_bytes, &bar_ld);
+            tma_bulk_g2s(sV, v_op, (uint32_t)O.v_blk_bytes, &bar_ld);
+        }
+        mbar_wait(&bar_ld, ph_ld);
+        ph_ld ^= 1u;
+    }
+
+    for (int tile = blockIdx.y; tile < O.q_tiles; tile += gridDim.y) {
+        const int i = tile * K2T + tid;
         const bool valid = i < Nq;
         const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
+        const uint32_t* mrow = p.mask + row * NW;
 
-        // ---- this row's kept-key bitmask (<= 8 words): requested at once, held in registers
-        uint32_t mreg[8];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) mreg[w] = (valid && w < NW) ? __ldg(p.mask + row * NW + w) : 0u;
-        // ---- Q tile -> bf16 A operand (aliases the P buffer)
-        for (int kc = 0; kc < (hdp >> 3); ++kc) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (valid && kc * 8 < hd) {
-                const uint2 c = __ldg(reinterpret_cast<const uint2*>(p.q_codes + row * hd + kc * 8));
-                const float w = exp2i((int)__ldg(p.q_exps + row * NB + (kc >> 2)) - 6);
-                v = dequant8_bf16(c.x, c.y, w);
-            }
-            *reinterpret_cast<uint4*>(sP + ((size_t)kc * K2T + tid) * 16) = v;
-        }
-        fence_proxy_async_smem();
-        tcgen05_fence_before_sync();
-        __syncthreads();
+        // ---- Q tile (A operand) -> the P buffer region, by TMA
         if (tid == 0) {
+            mbar_expect_tx(&bar_ld, (uint32_t)O.q_tile_bytes);
+            tma_bulk_g2s(sP, q_op + (size_t)tile * O.q_tile_bytes, (uint32_t)O.q_tile_bytes, &bar_ld);
+        }
+        mbar_wait(&bar_ld, ph_ld);
+        ph_ld ^= 1u;
+
+        float m = -INFINITY, l = 0.f;
+        // =============== pass 1: row max and sum of exp over the kept keys
+        for (int blk = 0; blk < O.nblk; ++blk) {
+            const int wbase = blk * O.wpb, nwb = min(O.wpb, NW - wbase);
+            if (!single) {
+                if (tid == 0) {
+                    mbar_expect_tx(&bar_ld, (uint32_t)O.k_blk_bytes);
+                    tma_bulk_g2s(sK, k_op + (size_t)blk * O.k_blk_bytes, (uint32_t)O.k_blk_bytes, &bar_ld);
+                }
+                mbar_wait(&bar_ld, ph_ld);
+                ph_ld ^= 1u;
+            }
+            if (tid == 0) {
+                tcgen05_fence_after_sync();
+                for (int ks = 0; ks < (hdp >> 4); ++ks) {
+                    const uint64_t da = umma_smem_desc(smem_u32(sP + (size_t)(2 * ks) * K2T * 16), K2T * 16, 128);
+                    const uint64_t db = umma_smem_desc(smem_u32(sK + (size_t)(2 * ks) * kbr * 16), kbr * 16, 128);
+                    umma_bf16_ss(tmem, da, db, idesc_s, ks > 0);
+                }
+                umma_commit(&bar_s);
+            }
+            uint32_t mreg[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) mreg[w] = (valid && w < nwb) ? __ldg(mrow + wbase + w) : 0u;
+            mbar_wait(&bar_s, ph_s);
+            ph_s ^= 1u;
             tcgen05_fence_after_sync();
-            for (int ks = 0; ks < (hdp >> 4); ++ks) {
-                const uint64_t da = umma_smem_desc(smem_u32(sP + (size_t)(2 * ks) * K2T * 16), K2T * 16, 128);
-                const uint64_t db = umma_smem_desc(smem_u32(sK + (size_t)(2 * ks) * nkp * 16), nkp * 16, 128);
-                umma_bf16_ss(tmem, da, db, idesc_s, ks > 0);
-            }
-            umma_commit(&bar_s);
-        }
-        mbar_wait(&bar_s, ph_s);
-        ph_s ^= 1u;
-        tcgen05_fence_after_sync();
 
-        // ---- pass A: row max over the kept keys (A7: bf16 rounding of the matmul output, * scale)
-        float m = -INFINITY;
-        for (int w = 0; w < NW; ++w) {
-            const uint32_t mw = pick8(mreg, w);
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(my_tmem + w * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                float s = __uint_as_float(r[c]);
-                if (bf16) s = bf16_half_away(s);
-                const float tv = __fmul_rn(s, p.scale);
-                m = fmaxf(m, ((mw >> c) & 1u) ? tv : -INFINITY);
-            }
-        }
-        if (m == -INFINITY) m = 0.f;           // row without kept keys (padding rows of the tile)
-        // ---- pass B: E = exp(t - m) on kept keys, 0 elsewhere; written back over S; row sum
-        float sum = 0.f;
-        for (int w = 0; w < NW; ++w) {
-            const uint32_t mw = pick8(mreg, w);
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(my_tmem + w * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                float s = __uint_as_float(r[c]);
-                if (bf16) s = bf16_half_away(s);
-                const float ev = ((mw >> c) & 1u) ? exp_nonpos(__fsub_rn(__fmul_rn(s, p.scale), m)) : 0.f;
-                sum += ev;
-                r[c] = __float_as_uint(ev);
-            }
-            tmem_st_32x32b_x32(my_tmem + w * 32, r);
-        }
-        tmem_st_wait();
-        const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-
-        // ---- pass C: P = E/sum -> A1 -> MXINT8 per window -> bf16 A operand; O += P_w . V_w
-        for (int g0 = 0; g0 < NW; g0 += K2_PW) {
-            if (g0 > 0) {                       // previous group's MMAs have finished reading sP
-                mbar_wait(&bar_o, ph_o);
-                ph_o ^= 1u;
-            }
-            const int g1 = min(g0 + K2_PW, NW);
-            for (int w = g0; w < g1; ++w) {
+            // pass A (A7: bf16 rounding of the matmul output, * scale)
+            float mb = -INFINITY;
+            for (int w = 0; w < nwb; ++w) {
+                const uint32_t mw = pick8(mreg, w);
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(my_tmem + w * 32, r);
                 tmem_ld_wait();
-                uint32_t mx = 0u;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    uint32_t pb = __float_as_uint(__uint_as_float(r[c]) * inv);
-                    if (bf16) pb = bf16_half_away(pb);
-                    r[c] = pb;
-                    mx = max(mx, pb);              // p >= 0: bit patterns order like the values
-                }
-                const int e = mx_shared_exp(mx);
-                const bool dead = (flush && e <= -127) || mx == 0u;
-                const float s1 = exp2i(-e), wgt = exp2i(e - 6);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float f[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const float rr = __uint_as_float(r[q * 8 + t]) * s1 * 64.0f + 0.5f;
-                        const int c = dead ? 0 : min(__float2int_rz(rr), 127);
-                        f[t] = (float)c * wgt;
-                    }
-                    *reinterpret_cast<uint4*>(sP + ((size_t)((w - g0) * 4 + q) * K2T + tid) * 16) =
-                        make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]),
-                                   pack_bf16_trunc(f[4], f[5]), pack_bf16_trunc(f[6], f[7]));
+                    float s = __uint_as_float(r[c]);
+                    if (bf16) s = bf16_half_away(s);
+                    const float tv = __fmul_rn(s, p.scale);
+                    mb = fmaxf(mb, ((mw >> c) & 1u) ? tv : -INFINITY);
                 }
             }
-            fence_proxy_async_smem();
-            tcgen05_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tcgen05_fence_after_sync();
-                for (int w = g0; w < g1; ++w)
+            const float m_new = fmaxf(m, mb);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;     // no kept key so far
+            if (m != -INFINITY) l *= exp_nonpos(m - m_use);
+            // pass B: exp(t - m) on kept keys; single block: written back over S for pass 2
+            float sum = 0.f;
+            for (int w = 0; w < nwb; ++w) {
+                const uint32_t mw = pick8(mreg, w);
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(my_tmem + w * 32, r);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint64_t da = umma_smem_desc(
-                            smem_u32(sP + (size_t)((w - g0) * 4 + 2 * h) * K2T * 16), K2T * 16, 128);
-                        const uint64_t db = umma_smem_desc(
-                            smem_u32(sV + (size_t)(w * 4 + 2 * h) * hdp * 16), hdp * 16, 128);
-                        umma_bf16_ss(tmem, da, db, idesc_o, !(w == 0 && h == 0));
+                for (int c = 0; c < 32; ++c) {
+                    float s = __uint_as_float(r[c]);
+                    if (bf16) s = bf16_half_away(s);
+                    const float ev = ((mw >> c) & 1u) ? exp_nonpos(__fsub_rn(__fmul_rn(s, p.scale), m_use)) : 0.f;
+                    sum += ev;
+                    r[c] = __float_as_uint(ev);
+                }
+                if (single) tmem_st_32x32b_x32(my_tmem + w * 32, r);
+            }
+            if (single) tmem_st_wait();
+            l += sum;
+            m = m_new;
+            if (!single) {                          // S columns and sK are reused by the next block
+                tcgen05_fence_before_sync();
+                __syncthreads();
+                tcgen05_fence_after_sync();
+            }
+        }
+        const float m_fin = (m == -INFINITY) ? 0.f : m;
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+
+        // =============== pass 2: P = E/sum -> A1 -> MXINT8 per window -> bf16; O += P_w . V_w
+        bool first_mma = true;
+        for (int blk = 0; blk < O.nblk; ++blk) {
+            const int wbase = blk * O.wpb, nwb = min(O.wpb, NW - wbase);
+            uint32_t mreg[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) mreg[w] = 0u;
+            if (!single) {
+                if (blk > 0) {                      // previous block's P.V MMAs are done with sP / sV
+                    mbar_wait(&bar_o, ph_o);
+                    ph_o ^= 1u;
+                }
+                if (tid == 0) {
+                    const bool need_q = true;       // sP was overwritten by P: re-fetch the Q tile
+                    mbar_expect_tx(&bar_ld, (uint32_t)(O.k_blk_bytes + O.v_blk_bytes + (need_q ? O.q_tile_bytes : 0)));
+                    tma_bulk_g2s(sK, k_op + (size_t)blk * O.k_blk_bytes, (uint32_t)O.k_blk_bytes, &bar_ld);
+                    tma_bulk_g2s(sV, v_op + (size_t)blk * O.v_blk_bytes, (uint32_t)O.v_blk_bytes, &bar_ld);
+                    tma_bulk_g2s(sP, q_op + (size_t)tile * O.q_tile_bytes, (uint32_t)O.q_tile_bytes, &bar_ld);
+                }
+#pragma unroll
+                for (int w = 0; w < 8; ++w) mreg[w] = (valid && w < nwb) ? __ldg(mrow + wbase + w) : 0u;
+                mbar_wait(&bar_ld, ph_ld);
+                ph_ld ^= 1u;
+                if (tid == 0) {
+                    tcgen05_fence_after_sync();
+                    for (int ks = 0; ks < (hdp >> 4); ++ks) {
+                        const uint64_t da = umma_smem_desc(smem_u32(sP + (size_t)(2 * ks) * K2T * 16), K2T * 16, 128);
+                        const uint64_t db = umma_smem_desc(smem_u32(sK + (size_t)(2 * ks) * kbr * 16), kbr * 16, 128);
+                        umma_bf16_ss(tmem, da, db, idesc_s, ks > 0);
                     }
-                umma_commit(&bar_o);
+                    umma_commit(&bar_s);
+                }
+                mbar_wait(&bar_s, ph_s);            // S ready AND the Q tile in sP has been consumed
+                ph_s ^= 1u;
+                tcgen05_fence_after_sync();
+            }
+            for (int g0 = 0; g0 < nwb; g0 += K2_PW) {
+                if (g0 > 0) {                       // previous group's MMAs have finished reading sP
+                    mbar_wait(&bar_o, ph_o);
+                    ph_o ^= 1u;
+                }
+                const int g1 = min(g0 + K2_PW, nwb);
+                for (int w = g0; w < g1; ++w) {
+                    const uint32_t mw = pick8(mreg, w);
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(my_tmem + w * 32, r);
+                    tmem_ld_wait();
+                    uint32_t mx = 0u;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        float ev = __uint_as_float(r[c]);
+                        if (!single) {
+                            if (bf16) ev = bf16_half_away(ev);
+                            ev = ((mw >> c) & 1u) ? exp_nonpos(__fsub_rn(__fmul_rn(ev, p.scale), m_fin)) : 0.f;
+                        }
+                        uint32_t pb = __float_as_uint(ev * inv);
+                        if (bf16) pb = bf16_half_away(pb);
+                        r[c] = pb;
+                        mx = max(mx, pb);          // p >= 0: bit patterns order like the values
+                    }
+                    const int e = mx_shared_exp(mx);
+                    const bool dead = (flush && e <= -127) || mx == 0u;
+                    const float s1 = exp2i(-e), wgt = exp2i(e - 6);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float f[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            const float rr = __uint_as_float(r[q * 8 + t]) * s1 * 64.0f + 0.5f;
+                            const int c = dead ? 0 : min(__float2int_rz(rr), 127);
+                            f[t] = (float)c * wgt;
+                        }
+                        *reinterpret_cast<uint4*>(sP + ((size_t)((w - g0) * 4 + q) * K2T + tid) * 16) =
+                            make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]),
+                                       pack_bf16_trunc(f[4], f[5]), pack_bf16_trunc(f[6], f[7]));
+                    }
+                }
+                fence_proxy_async_smem();
+                tcgen05_fence_before_sync();
+                __syncthreads();
+                if (tid == 0) {
+                    tcgen05_fence_after_sync();
+                    for (int w = g0; w < g1; ++w)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint64_t da = umma_smem_desc(
+                                smem_u32(sP + (size_t)((w - g0) * 4 + 2 * h) * K2T * 16), K2T * 16, 128);
+                            const uint64_t db = umma_smem_desc(
+                                smem_u32(sV + (size_t)(w * 4 + 2 * h) * hdp * 16), hdp * 16, 128);
+                            umma_bf16_ss(tmem + o_col, da, db, idesc_o, !first_mma);
+                            first_mma = false;
+                        }
+                    umma_commit(&bar_o);
+                }
             }
         }
         mbar_wait(&bar_o, ph_o);
@@ -289,7 +354,7 @@ k_attend_umma(const AttnParams p) {
         float* orow = p.out + bb * p.o_sB + hh * p.o_sH + (int64_t)(valid ? i : 0) * p.o_sN;
         for (int c0 = 0; c0 < hdp; c0 += 16) {
             uint32_t r[16];
-            tmem_ld_32x32b_x16(my_tmem + c0, r);
+            tmem_ld_32x32b_x16(my_tmem + o_col + c0, r);
             tmem_ld_wait();
             if (valid) {
 #pragma unroll
@@ -307,10 +372,100 @@ k_attend_umma(const AttnParams p) {
             }
         }
         tcgen05_fence_before_sync();
-        __syncthreads();                        // every lane has read O before the next S MMA overwrites it
+        __syncthreads();                        // every lane has read O before TMEM / sP are reused
         tcgen05_fence_after_sync();
     }
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)L.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// V -> A1 -> MXINT8 along TOKENS (32-token windows per column) -> bf16 MMA-ready V^T operand.
+// grid (heads, groups of 4 windows); thread <-> (window, column) pairs, consecutive threads on
+// consecutive columns (coalesced loads, conflict-free 16-byte stores).
+// ------------------------------------------------------------------------------------------
+struct VPrepParams {
+    View v;
+    int H, Nq, Nk, hd, bf16, flush;
+    unsigned char* v_op;
+};
+
+__global__ void __launch_bounds__(K2T)
+k_prep_v(const VPrepParams p) {
+    const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
+    const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
+    const int hdp = O.hdp, Nk = p.Nk, hd = p.hd;
+    const int nw_pad = O.nblk * O.wpb;                         // windows incl. block padding
+    const float* vb = p.v.p + bb * p.v.sB + hh * p.v.sH;
+    unsigned char* dst = p.v_op + (size_t)head * O.v_head_bytes;
+    const int w0 = blockIdx.y * 4, w1 = min(w0 + 4, nw_pad);
+    for (int t = threadIdx.x; t < (w1 - w0) * hdp; t += K2T) {
+        const int w = w0 + t / hdp, d = t % hdp;
+        uint32_t xb[32];
+        uint32_t mx = 0u;
+        const float* vp = vb + (int64_t)(w * 32) * p.v.sN + d;
+        const int nvalid = (d < hd) ? max(0, min(32, Nk - w * 32)) : 0;
+#pragma unroll
+        for (int tt = 0; tt < 32; ++tt) {
+            uint32_t b = 0u;
+            if (tt < nvalid) b = __float_as_uint(__ldg(vp));
+            vp += p.v.sN;
+            if (p.bf16) b = bf16_half_away(b);
+            xb[tt] = b;
+            mx = max(mx, b & 0x7fffffffu);
+        }
+        const int e = mx_shared_exp(mx);
+        const bool dead = p.flush && e <= -127;
+        const float wgt = exp2i(e - 6);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) f[tt] = (float)mx_code(xb[q * 8 + tt], e, dead) * wgt;
+            *reinterpret_cast<uint4*>(dst + v_op_offset(O, w * 4 + q, d)) =
+                make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]), pack_bf16_trunc(f[4], f[5]),
+                           pack_bf16_trunc(f[6], f[7]));
+        }
+    }
+}
+
+// 8 int8 codes (two words) of one MX block with exponent weight w = 2^(e-6) -> 8 bf16 in a uint4
+__device__ __forceinline__ uint4 dequant8_bf16(uint32_t lo, uint32_t hi, float w) {
+    float f[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        f[t] = (float)(int)(signed char)((lo >> (8 * t)) & 0xff) * w;
+        f[4 + t] = (float)(int)(signed char)((hi >> (8 * t)) & 0xff) * w;
+    }
+    return make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]), pack_bf16_trunc(f[4], f[5]),
+                      pack_bf16_trunc(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------
+// Compact codes/exps -> MMA-ready operands (public mxp_sparse_attention entry, which receives
+// codes).  which = 0: query rows (tiles of 128), 1: key rows (key blocks).  Also zero-fills padding.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_codes_to_ops(const int8_t* __restrict__ codes, const int8_t* __restrict__ exps, unsigned char* __restrict__ ops,
+               int heads, int Nq, int Nk, int hd, int which) {
+    const OpsLayout O = ops_layout(Nq, Nk, hd);
+    const int NB = (hd + 31) >> 5, kch = O.hdp >> 3;
+    const int rows = which == 0 ? Nq : Nk;
+    const int rows_pad = which == 0 ? O.q_tiles * K2T : O.nblk * O.kb_rows;
+    const size_t head_bytes = which == 0 ? O.q_head_bytes : O.k_head_bytes;
+    const int64_t total = (int64_t)heads * rows_pad * kch;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t % rows_pad);
+        const int kc = (int)((t / rows_pad) % kch);
+        const int64_t head = t / ((int64_t)rows_pad * kch);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows && kc * 8 < hd) {
+            const int64_t grow = head * rows + r;
+            const uint2 c = __ldg(reinterpret_cast<const uint2*>(codes + grow * hd + kc * 8));
+            v = dequant8_bf16(c.x, c.y, exp2i((int)__ldg(exps + grow * NB + (kc >> 2)) - 6));
+        }
+        const size_t off = which == 0 ? q_op_offset(O, r, kc) : k_op_offset(O, r, kc);
+        *reinterpret_cast<uint4*>(ops + head * head_bytes + off) = v;
+    }
 }
 
 }  // namespace mxp

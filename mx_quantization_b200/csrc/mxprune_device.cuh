@@ -29,6 +29,7 @@ struct PredParams {
     uint32_t* mask;
     int32_t* idx;
     int8_t *q_codes, *q_exps, *k_codes, *k_exps;
+    unsigned char *q_op, *k_op;   // MMA-ready bf16 operands for the exact-attention kernel (may be null)
     float* scores;   // dense debug output (k_predict_scores only)
 };
 

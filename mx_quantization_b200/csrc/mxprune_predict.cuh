@@ -23,6 +23,7 @@
 // identical sets wherever both apply.
 #pragma once
 #include "mxprune_device.cuh"
+#include "mxprune_attend.cuh"
 
 namespace mxp {
 
@@ -60,9 +61,11 @@ struct RowQ {
 
 // One thread quantizes one row of hd fp32 values (16-byte aligned).  Optionally writes the int8
 // codes (4-byte aligned destination).
+// op_row (optional): address of this row's first 16-byte bf16 operand chunk, chunks op_stride apart.
 template <int NB>
 __device__ __forceinline__ void quantize_row_thread(const float* __restrict__ row, int hd, bool bf16,
-                                                    bool flush, RowQ<NB>& rq, int8_t* codes_out) {
+                                                    bool flush, RowQ<NB>& rq, int8_t* codes_out,
+                                                    unsigned char* op_row = nullptr, int op_stride = 0) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int nd = min(32, hd - 32 * b);
@@ -84,11 +87,14 @@ __device__ __forceinline__ void quantize_row_thread(const float* __restrict__ ro
         const int e = mx_shared_exp(mx);
         const bool dead = flush && e <= -127;
         const float s1 = exp2i(-e);
+        const float wgt = exp2i(e - 6);
         uint32_t sw = 0u;
         uint32_t cw[8];
+        uint32_t ow[16];                                    // dequantised values as bf16 pairs
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
             uint32_t word = 0u;
+            float fq[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const uint32_t xv = xb[4 * v + t];
@@ -97,9 +103,20 @@ __device__ __forceinline__ void quantize_row_thread(const float* __restrict__ ro
                 if (dead) c = 0;
                 const bool neg = (xv >> 31) && c != 0;
                 sw |= (neg ? 1u : 0u) << (4 * v + t);
-                word |= ((uint32_t)(neg ? -c : c) & 0xffu) << (8 * t);
+                const int sc = neg ? -c : c;
+                word |= ((uint32_t)sc & 0xffu) << (8 * t);
+                fq[t] = (float)sc * wgt;                    // c * 2^(e-6): exact in bf16
             }
             cw[v] = word;
+            ow[2 * v] = pack_bf16_trunc(fq[0], fq[1]);
+            ow[2 * v + 1] = pack_bf16_trunc(fq[2], fq[3]);
+        }
+        if (op_row) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+                if (8 * ch < nd)
+                    *reinterpret_cast<uint4*>(op_row + (size_t)(b * 4 + ch) * op_stride) =
+                        make_uint4(ow[4 * ch], ow[4 * ch + 1], ow[4 * ch + 2], ow[4 * ch + 3]);
         }
         rq.sign[b] = sw;
         rq.e[b] = e;
@@ -225,6 +242,10 @@ k_predict_topk_rows(const PredParams p) {
     const int tid = threadIdx.x;
     const bool bf16 = p.bf16, flush = p.flush;
     const bool write_k = p.k_codes != nullptr && blockIdx.y == 0;
+    const bool write_kop = p.k_op != nullptr && blockIdx.y == 0;
+    const OpsLayout OL = ops_layout(Nq, Nk, hd);
+    unsigned char* k_op = p.k_op ? p.k_op + (size_t)head * OL.k_head_bytes : nullptr;
+    unsigned char* q_op = p.q_op ? p.q_op + (size_t)head * OL.q_head_bytes : nullptr;
 
     // ---------------- stage the keys of this head
     if (tid < 4) { s_kmin[tid] = 0x7fffffff; s_kmax[tid] = -0x7fffffff; }
@@ -236,7 +257,8 @@ k_predict_topk_rows(const PredParams p) {
                 RowQ<NB> kq;
                 const int64_t krow = (int64_t)head * Nk + j;
                 quantize_row_thread<NB>(kb + (int64_t)j * p.k.sN, hd, bf16, flush, kq,
-                                        write_k ? p.k_codes + krow * hd : nullptr);
+                                        write_k ? p.k_codes + krow * hd : nullptr,
+                                        write_kop ? k_op + k_op_offset(OL, j, 0) : nullptr, OL.kb_rows * 16);
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     s_krec[(j * NB + b) * 2] = kq.sign[b];
@@ -248,6 +270,14 @@ k_predict_topk_rows(const PredParams p) {
             } else {
 #pragma unroll
                 for (int b = 0; b < NB; ++b) { s_krec[(j * NB + b) * 2] = 0u; s_kexp[b * nkp + j] = 0; }
+            }
+        }
+        if (write_kop) {        // zero the padding of the operand image (key rows / head_dim up to 16)
+            const int kch = OL.hdp >> 3, rows_pad = OL.nblk * OL.kb_rows;
+            for (int t = tid; t < rows_pad * kch; t += K1T) {
+                const int j = t % rows_pad, kc = t / rows_pad;
+                if (j >= Nk || kc * 8 >= hd)
+                    *reinterpret_cast<uint4*>(k_op + k_op_offset(OL, j, kc)) = make_uint4(0u, 0u, 0u, 0u);
             }
         }
     }
@@ -276,9 +306,15 @@ k_predict_topk_rows(const PredParams p) {
         const bool valid = i < Nq;
         const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
         RowQ<NB> rq;
+        if (q_op) {             // padding of the A-operand tile: rows past Nq, head_dim up to 16
+            for (int kc = 0; kc < (OL.hdp >> 3); ++kc)
+                if (!valid || kc * 8 >= hd)
+                    *reinterpret_cast<uint4*>(q_op + q_op_offset(OL, i, kc)) = make_uint4(0u, 0u, 0u, 0u);
+        }
         if (valid) {
             quantize_row_thread<NB>(qb + (int64_t)i * p.q.sN, hd, bf16, flush, rq,
-                                    p.q_codes ? p.q_codes + row * hd : nullptr);
+                                    p.q_codes ? p.q_codes + row * hd : nullptr,
+                                    q_op ? q_op + q_op_offset(OL, i, 0) : nullptr, K2T * 16);
             if (p.q_exps) {
 #pragma unroll
                 for (int b = 0; b < NB; ++b) p.q_exps[row * NB + b] = (int8_t)rq.e[b];

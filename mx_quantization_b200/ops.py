@@ -172,17 +172,19 @@ def sparse_attention(q_codes, q_exps, k_codes, k_exps, v: torch.Tensor, mask: to
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((B, H, Nq, hd), dtype=torch.float32, device=dev)
+        ws_bytes = lib.mxp_sparse_attention_workspace_bytes(B, H, Nq, Nk, hd)
+        ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
         rc = lib.mxp_sparse_attention(_ptr(q_codes), _ptr(q_exps), _ptr(k_codes), _ptr(k_exps),
                                       _ptr(v), *_strides(v), _ptr(mask), B, H, Nq, Nk, hd,
                                       scale, sp.bfloat_bits, int(sp.flush),
-                                      _ptr(out), *_strides(out), c_void_p(0), 0, _stream())
+                                      _ptr(out), *_strides(out), _ptr(ws), ws_bytes, _stream())
     _lib.check(rc, "mxp_sparse_attention")
     return out
 
 
 def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs, top_k: int,
                      scale: Optional[float] = None, return_mask: bool = False,
-                     out: Optional[torch.Tensor] = None):
+                     out: Optional[torch.Tensor] = None, _kernel_ms: Optional[list] = None):
     """MXINT8 exponent-sign predicted top-k attention: q,k,v (B,H,N,hd) fp32 -> out (B,H,Nq,hd).
 
     Drop-in for lines 101-152 of workloads/deit/scripts/main.py (DiT models.py:168-225, PixArt
@@ -206,8 +208,15 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
         mask = torch.empty((B, H, Nq, (Nk + 31) // 32), dtype=torch.int32, device=dev) if return_mask else None
         ws_bytes = lib.mxp_pruned_attention_workspace_bytes(B, H, Nq, Nk, hd)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        rc = lib.mxp_pruned_attention(_ptr(q), *_strides(q), _ptr(k), *_strides(k), _ptr(v), *_strides(v),
-                                      B, H, Nq, Nk, hd, int(top_k), scale, sp.bfloat_bits, int(sp.flush),
-                                      _ptr(out), *_strides(out), _ptr(mask), _ptr(ws), ws_bytes, _stream())
+        args = (_ptr(q), *_strides(q), _ptr(k), *_strides(k), _ptr(v), *_strides(v),
+                B, H, Nq, Nk, hd, int(top_k), scale, sp.bfloat_bits, int(sp.flush),
+                _ptr(out), *_strides(out), _ptr(mask), _ptr(ws), ws_bytes, _stream())
+        if _kernel_ms is None:
+            rc = lib.mxp_pruned_attention(*args)
+        else:       # measurement aid: per-kernel CUDA-event times (synchronises)
+            import ctypes
+            ms = (ctypes.c_float * 3)()
+            rc = lib.mxp_pruned_attention_profile(*args, ms)
+            _kernel_ms[:] = [float(x) for x in ms]
     _lib.check(rc, "mxp_pruned_attention")
     return (out, mask) if return_mask else out

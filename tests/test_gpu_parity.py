@@ -195,3 +195,26 @@ def test_error_behaviour(mxq):
         mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), bad, 8)
     with pytest.raises(ValueError):
         mxq.pruned_attention(q.cuda().double(), k.cuda(), v.cuda(), specs, 8)
+
+
+LONG_SHAPES = [  # B, H, N, hd, bfloat  -- key counts beyond one key block (Nk > 256): online softmax path
+    (1, 2, 512, 72, 32),
+    (1, 1, 1000, 64, 32),
+    (1, 2, 300, 72, 16),
+    (1, 1, 2048, 72, 32),
+]
+
+
+@pytest.mark.parametrize("B,H,N,hd,bfloat", LONG_SHAPES)
+def test_exact_attention_long_sequences(mxq, B, H, N, hd, bfloat):
+    """Exact stage on key counts above 256 (C5 sweep territory), kept set taken from the oracle."""
+    top_k = max(1, int(0.25 * N))
+    q, k, v = make_qkv(B, H, N, hd, seed=6, kind="randn")
+    specs = mx_specs(bfloat, False)
+    ref = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, integer_scores=True)
+    mask = O.idx_to_mask_words(ref["idx"], N)
+    mask_i32 = torch.where(mask >= 2 ** 31, mask - 2 ** 32, mask).to(torch.int32)
+    out = mxq.sparse_attention(ref["q_codes"].cuda(), ref["q_exps"].cuda(), ref["k_codes"].cuda(),
+                               ref["k_exps"].cuda(), v.cuda(), mask_i32.cuda(), specs,
+                               scale=O.default_scale(hd)).cpu()
+    assert_out_close(out, ref, v, N, bfloat, OUT_TOL)
