@@ -432,7 +432,26 @@ inline int pick_kpl(int Nk) {
 }
 
 template <int NB>
+int launch_predict_topk_long(const PredParams& p, cudaStream_t st) {
+    const K1LSmem L = k1l_smem_layout(NB, p.Nk);
+    if (L.total > 200 * 1024)
+        return fail(MXP_E_UNSUPPORTED, "Nk=%d: key records need %zu bytes of shared memory (limit 200 KiB)", p.Nk, L.total);
+    cudaError_t e = cudaFuncSetAttribute(k_predict_topk_long<NB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int heads = p.B * p.H;
+    const int tiles = (p.Nq + K1T - 1) / K1T;
+    int splits = (148 * 2 + heads - 1) / heads;
+    if (splits > tiles) splits = tiles;
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)heads, (unsigned)splits);
+    k_predict_topk_long<NB><<<grid, K1T, L.total, st>>>(p);
+    return check_launch("k_predict_topk_long");
+}
+
+template <int NB>
 int launch_predict_topk_nb(const PredParams& p, cudaStream_t st) {
+    if (p.Nk > K1_MAX_KEYS) return launch_predict_topk_long<NB>(p, st);
     const K1Smem L = k1_smem_layout(NB, p.Nk);
     cudaError_t e = cudaFuncSetAttribute(k_predict_topk_rows<NB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
@@ -540,7 +559,7 @@ int mxp_set_attention_path(int path) {
 const char* mxp_last_error(void) { return g_err; }
 int mxp_last_launch_count(void) { return g_launches; }
 void mxp_limits(int* max_keys, int* max_head_dim) {
-    if (max_keys) *max_keys = MAX_KEYS_FUSED;
+    if (max_keys) *max_keys = 8192;
     if (max_head_dim) *max_head_dim = MAX_HD;
 }
 
@@ -619,8 +638,6 @@ int mxp_predict_scores(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
 size_t mxp_predict_topk_workspace_bytes(int, int, int, int, int) { return 0; }
 
 static int predict_topk_impl(const PredParams& p, cudaStream_t st) {
-    if (p.Nk > MAX_KEYS_FUSED)
-        return fail(MXP_E_UNSUPPORTED, "Nk=%d: fused predictor covers Nk <= %d", p.Nk, MAX_KEYS_FUSED);
     switch ((p.hd + 31) / 32) {
         case 1: return launch_predict_topk_nb<1>(p, st);
         case 2: return launch_predict_topk_nb<2>(p, st);

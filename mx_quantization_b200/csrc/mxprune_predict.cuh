@@ -434,4 +434,238 @@ k_predict_topk_rows(const PredParams p) {
     }
 }
 
+
+// ==========================================================================================
+// K1-long: the same fused quantizer + predictor + exact top-k for Nk > 256 (long-sequence sweep).
+//
+// A row's keys no longer fit in shared memory next to 127 other rows, so nothing per-row is
+// stored: each thread re-derives its keys from the staged K records in every pass and the k-th
+// largest is found by a most-significant-digit radix select over per-thread histograms
+// (64 bins x 6 bits per level, [bin][thread] in shared memory => conflict-free, no atomics):
+//   level 0..L-1   histogram of the current 6-bit digit among keys whose higher digits equal the
+//                  prefix found so far; scan from the top bin to locate the digit of the k-th key
+//   emit           keys > T kept, keys == T kept in ascending index until top_k
+// Keys are the exact 15-bit integers of the short kernel when the exponent window allows
+// (L = 3 levels) and order-preserving fp32 keys otherwise (L = 6) - chosen per row.
+// K record per key: NB sign words + one word of per-block shifts (ek_b - kmin_b), 16 bytes.
+// ==========================================================================================
+constexpr int K1L_BINS = 64;
+
+struct K1LSmem {
+    int rw;                         // 32-bit words per key record
+    size_t off_hist, off_misc, total;
+};
+__host__ __device__ inline K1LSmem k1l_smem_layout(int nb, int Nk) {
+    K1LSmem L;
+    L.rw = nb <= 3 ? 4 : 8;
+    size_t o = (size_t)Nk * L.rw * 4;
+    o = (o + 15) & ~(size_t)15;
+    L.off_hist = o; o += (size_t)K1L_BINS * K1T * 4;
+    L.off_misc = o; o += 64;
+    L.total = o;
+    return L;
+}
+
+template <int NB>
+struct LongRow {
+    uint32_t sign[NB];
+    int mq[NB];          // fast: integer row multipliers 2^(eq_b + kmin_b - g)
+    float wq[NB];        // slow: 2^eq_b
+    int moff;
+    bool fast;
+};
+
+template <int NB>
+__device__ __forceinline__ uint32_t long_key(const LongRow<NB>& R, const uint32_t* rec, const int (&kmin)[NB], int hd) {
+    const uint32_t shw = rec[NB];
+    if (R.fast) {
+        int S = R.moff;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int nbw = (b < NB - 1) ? 32 : hd - 32 * (NB - 1);
+            const int c = nbw - 2 * __popc(R.sign[b] ^ rec[b]);
+            S += (c << ((shw >> (8 * b)) & 0xffu)) * R.mq[b];
+        }
+        return ((uint32_t)S >> 1) + 1u;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int nbw = (b < NB - 1) ? 32 : hd - 32 * (NB - 1);
+        const float cnt = (float)(nbw - 2 * __popc(R.sign[b] ^ rec[b]));
+        const float t = exp2i(kmin[b] + (int)((shw >> (8 * b)) & 0xffu)) * cnt;
+        s = (b == 0) ? t * R.wq[0] : fmaf(t, R.wq[b], s);
+    }
+    return ordered_key(s);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(K1T)
+k_predict_topk_long(const PredParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
+    const K1LSmem L = k1l_smem_layout(NB, Nk);
+    const int RW = L.rw;
+    uint32_t* s_rec = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + L.off_hist);
+    int* s_kmin = reinterpret_cast<int*>(smem_raw + L.off_misc);
+    int* s_kmax = s_kmin + 4;
+    const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
+    const int tid = threadIdx.x;
+    const bool bf16 = p.bf16, flush = p.flush;
+    const bool write_k = p.k_codes != nullptr && blockIdx.y == 0;
+    const bool write_kop = p.k_op != nullptr && blockIdx.y == 0;
+    const OpsLayout OL = ops_layout(Nq, Nk, hd);
+    unsigned char* k_op = p.k_op ? p.k_op + (size_t)head * OL.k_head_bytes : nullptr;
+    unsigned char* q_op = p.q_op ? p.q_op + (size_t)head * OL.q_head_bytes : nullptr;
+
+    if (tid < 4) { s_kmin[tid] = 0x7fffffff; s_kmax[tid] = -0x7fffffff; }
+    __syncthreads();
+    {
+        const float* kb = p.k.p + bb * p.k.sB + hh * p.k.sH;
+        for (int j = tid; j < Nk; j += K1T) {
+            RowQ<NB> kq;
+            const int64_t krow = (int64_t)head * Nk + j;
+            quantize_row_thread<NB>(kb + (int64_t)j * p.k.sN, hd, bf16, flush, kq,
+                                    write_k ? p.k_codes + krow * hd : nullptr,
+                                    write_kop ? k_op + k_op_offset(OL, j, 0) : nullptr, OL.kb_rows * 16);
+            uint32_t epw = 0u;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                s_rec[j * RW + b] = kq.sign[b];
+                epw |= (uint32_t)(kq.ep[b] + 128) << (8 * b);        // provisional: biased exponent
+                atomicMin(&s_kmin[b], kq.ep[b]);
+                atomicMax(&s_kmax[b], kq.ep[b]);
+                if (write_k) p.k_exps[krow * NB + b] = (int8_t)kq.e[b];
+            }
+            s_rec[j * RW + NB] = epw;
+        }
+        if (write_kop) {
+            const int kch = OL.hdp >> 3, rows_pad = OL.nblk * OL.kb_rows;
+            for (int t = tid; t < rows_pad * kch; t += K1T) {
+                const int j = t % rows_pad, kc = t / rows_pad;
+                if (j >= Nk || kc * 8 >= hd)
+                    *reinterpret_cast<uint4*>(k_op + k_op_offset(OL, j, kc)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    }
+    __syncthreads();
+    int kmin[NB], spread[NB];
+    bool wide = false;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        kmin[b] = s_kmin[b];
+        spread[b] = s_kmax[b] - kmin[b];
+        wide |= spread[b] > K1_MAX_SPREAD;
+    }
+    for (int j = tid; j < Nk; j += K1T) {           // biased exponents -> shifts relative to kmin
+        const uint32_t epw = s_rec[j * RW + NB];
+        uint32_t shw = 0u;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) shw |= (uint32_t)((int)((epw >> (8 * b)) & 0xffu) - 128 - kmin[b]) << (8 * b);
+        s_rec[j * RW + NB] = shw;
+    }
+    __syncthreads();
+
+    const float* qb = p.q.p + bb * p.q.sB + hh * p.q.sH;
+    const int NW = (Nk + 31) >> 5;
+    uint32_t* my_hist = s_hist + tid;               // bin b at my_hist[b * K1T]
+
+    for (int i0 = blockIdx.y * K1T; i0 < Nq; i0 += K1T * gridDim.y) {
+        const int i = i0 + tid;
+        const bool valid = i < Nq;
+        const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
+        RowQ<NB> rq;
+        if (q_op) {
+            for (int kc = 0; kc < (OL.hdp >> 3); ++kc)
+                if (!valid || kc * 8 >= hd)
+                    *reinterpret_cast<uint4*>(q_op + q_op_offset(OL, i, kc)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (valid) {
+            quantize_row_thread<NB>(qb + (int64_t)i * p.q.sN, hd, bf16, flush, rq,
+                                    p.q_codes ? p.q_codes + row * hd : nullptr,
+                                    q_op ? q_op + q_op_offset(OL, i, 0) : nullptr, K2T * 16);
+            if (p.q_exps) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) p.q_exps[row * NB + b] = (int8_t)rq.e[b];
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) { rq.sign[b] = 0u; rq.e[b] = 0; rq.ep[b] = 0; }
+        }
+        LongRow<NB> R;
+        int g = 0x7fffffff;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) g = min(g, rq.ep[b] + kmin[b]);
+        R.fast = !wide;
+        long long M = 0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            int sh = rq.ep[b] + kmin[b] - g;
+            if (sh > K1_MAX_SPREAD) { R.fast = false; sh = K1_MAX_SPREAD; }
+            R.sign[b] = rq.sign[b];
+            R.mq[b] = 1 << sh;
+            R.wq[b] = exp2i(rq.ep[b]);
+            const int nbw = (b < NB - 1) ? 32 : hd - 32 * (NB - 1);
+            M += (long long)nbw << (sh + min(spread[b], K1_MAX_SPREAD));
+        }
+        if (M > 32766) R.fast = false;
+        R.moff = R.fast ? (((int)M + 1) & ~1) : 0;
+        const int wtot = R.fast ? 32 - __clz(R.moff + 1) : 32;       // key width in bits
+        int nlev = (wtot + 5) / 6;
+        nlev = __reduce_max_sync(FULL, nlev);
+
+        // ---- MSD radix select over per-thread histograms
+        uint32_t prefix = 0u;       // digits found so far (right-aligned)
+        int krem = kk;
+        for (int lev = 0; lev < nlev; ++lev) {
+            const int my_lev = (wtot + 5) / 6;
+            const int lo = 6 * (my_lev - 1 - lev);              // < 0: this row already has its full key
+            for (int b = 0; b < K1L_BINS; ++b) my_hist[b * K1T] = 0u;
+            if (lo >= 0) {
+                for (int j = 0; j < Nk; ++j) {
+                    const uint32_t u = long_key<NB>(R, s_rec + j * RW, kmin, hd);
+                    const uint32_t hi = (lo + 6 >= 32) ? 0u : (u >> (lo + 6));
+                    if (hi == prefix) my_hist[((u >> lo) & 63u) * K1T] += 1u;
+                }
+                int cum = 0, bin = K1L_BINS - 1;
+                for (; bin > 0; --bin) {
+                    const int h = (int)my_hist[bin * K1T];
+                    if (cum + h >= krem) break;
+                    cum += h;
+                }
+                krem -= cum;
+                prefix = (prefix << 6) | (uint32_t)bin;
+            }
+        }
+        const uint32_t T = prefix;
+
+        // ---- emit: keys > T, then keys == T in ascending index until top_k (krem ties wanted)
+        {
+            int rem = krem, pos = 0;
+            uint32_t word = 0u;
+            for (int j = 0; j < Nk; ++j) {
+                const uint32_t u = long_key<NB>(R, s_rec + j * RW, kmin, hd);
+                bool keep = u > T;
+                if (u == T && rem > 0) { keep = true; --rem; }
+                word |= (keep ? 1u : 0u) << (j & 31);
+                if ((j & 31) == 31 || j == Nk - 1) {
+                    if (valid) {
+                        p.mask[row * NW + (j >> 5)] = word;
+                        if (p.idx) {
+                            uint32_t w2 = word;
+                            while (w2) {
+                                const int bpos = __ffs(w2) - 1;
+                                w2 &= w2 - 1u;
+                                p.idx[row * kk + pos++] = (j & ~31) + bpos;
+                            }
+                        }
+                    }
+                    word = 0u;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace mxp

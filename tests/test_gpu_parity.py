@@ -218,3 +218,25 @@ def test_exact_attention_long_sequences(mxq, B, H, N, hd, bfloat):
                                ref["k_exps"].cuda(), v.cuda(), mask_i32.cuda(), specs,
                                scale=O.default_scale(hd)).cpu()
     assert_out_close(out, ref, v, N, bfloat, OUT_TOL)
+
+
+@pytest.mark.parametrize("B,H,N,hd,kind,bfloat,kfrac", [
+    (1, 2, 512, 72, "randn", 32, 0.1),
+    (1, 1, 1000, 64, "lognormal", 32, 0.25),
+    (1, 2, 300, 64, "edges", 32, 0.5),
+    (1, 1, 1024, 72, "randn", 16, 0.5),
+    (1, 1, 2048, 72, "randn", 32, 0.1),
+])
+def test_long_sequence_end_to_end(mxq, B, H, N, hd, kind, bfloat, kfrac):
+    """Config C5 territory (Nk > 256): long-sequence predictor + key-blocked exact attention."""
+    top_k = max(1, int(kfrac * N))
+    q, k, v = make_qkv(B, H, N, hd, seed=8, kind=kind)
+    specs = mx_specs(bfloat, False)
+    out, mask = mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), specs, top_k, return_mask=True)
+    ref = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, integer_scores=True)
+    want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], N), N)
+    assert torch.equal(unpack_mask(mask, N), want)
+    assert_out_close(out.cpu(), ref, v, N, bfloat, OUT_TOL)
+    r = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k, return_idx=True, return_codes=True)
+    assert torch.equal(r["idx"].cpu().to(torch.int64), torch.sort(ref["idx"], dim=-1).values)
+    assert torch.equal(r["k_codes"].cpu(), ref["k_codes"]) and torch.equal(r["q_exps"].cpu(), ref["q_exps"])
