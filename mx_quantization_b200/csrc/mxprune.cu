@@ -511,7 +511,14 @@ int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     if (splits > O.q_tiles) splits = O.q_tiles;
     if (splits < 1) splits = 1;
     dim3 grid((unsigned)heads, (unsigned)splits);
-    k_attend_umma<<<grid, K2T, L.total, st>>>(p);
+    // Never let more CTAs become resident on an SM than its 512 TMEM columns can serve: a CTA
+    // whose tcgen05.alloc cannot be satisfied would sit blocked inside the allocator.  Residency is
+    // bounded through the dynamic shared-memory request (227 KiB per SM).
+    const int max_ctas = 512 / L.tmem_cols;
+    size_t dyn = L.total;
+    const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
+    if (dyn < floor_bytes) dyn = floor_bytes;
+    k_attend_umma<<<grid, K2T, dyn, st>>>(p);
     return check_launch("k_attend_umma");
 }
 

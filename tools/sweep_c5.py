@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""BASELINE.json config 5: sequence-length sweep 256-4096 tokens (DiT-style, 16 heads, head_dim 72,
+constant 65536 tokens per batch), top-k ratio 0.1-0.5.  Prints one JSON line per point:
+heads/s, tokens/s, per-kernel ms, GB/s against the HBM roofline, and (N <= 1024) a bit-exact
+mask check + output check of one head against the CPU oracle.
+    python tools/sweep_c5.py [--reps 3] [--check]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import mx_quantization_b200 as mxq  # noqa: E402
+from bench import bytes_per_head, hbm_peak, mx_specs  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--ns", default="256,512,1024,2048,4096")
+    ap.add_argument("--ratios", default="0.1,0.25,0.5")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    specs = mx_specs(32, False)
+    H, hd = 16, 72
+    peak, _ = hbm_peak()
+    for N in [int(x) for x in args.ns.split(",")]:
+        B = max(1, 65536 // N)
+        g = torch.Generator(device=dev).manual_seed(N)
+        qkv = torch.randn(B, N, 3, H, hd, device=dev, generator=g).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        out = torch.empty(B, N, H, hd, device=dev).permute(0, 2, 1, 3)
+        for r in [float(x) for x in args.ratios.split(",")]:
+            top_k = max(1, int(-(-r * N // 1)))
+            for _ in range(2):
+                mxq.pruned_attention(q, k, v, specs, top_k, out=out)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.reps):
+                mxq.pruned_attention(q, k, v, specs, top_k, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.reps
+            km = []
+            mxq.pruned_attention(q, k, v, specs, top_k, out=out, _kernel_ms=km)
+            bph = bytes_per_head(N, hd)
+            line = {"N": N, "B": B, "H": H, "hd": hd, "ratio": r, "top_k": top_k, "ms": ms,
+                    "heads_per_s": B * H / (ms * 1e-3), "tokens_per_s": B * N / (ms * 1e-3),
+                    "kernel_ms": {"predict_topk": km[0], "prep_v": km[1], "exact_attention": km[2]},
+                    "predict_topk_gbs": bph["predict_topk"] * B * H / (km[0] * 1e-3) / 1e9,
+                    "predict_topk_frac_of_hbm": bph["predict_topk"] * B * H / (km[0] * 1e-3) / 1e9 / peak,
+                    "full_path_gbs": bph["full"] * B * H / (ms * 1e-3) / 1e9}
+            if args.check and N <= 1024:
+                from oracle import mxint8_oracle as O
+                print("check: gpu slice", file=sys.stderr, flush=True)
+                o2, mask = mxq.pruned_attention(q[:1, :1], k[:1, :1], v[:1, :1], specs, top_k, return_mask=True)
+                torch.cuda.synchronize()
+                print("check: oracle", file=sys.stderr, flush=True)
+                ref = O.pruned_attention(q[:1, :1].cpu(), k[:1, :1].cpu(), v[:1, :1].cpu(), top_k, integer_scores=True)
+                print("check: compare", file=sys.stderr, flush=True)
+                want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], N), N)
+                got = O.mask_words_to_dense(mask.cpu().to(torch.int64) & 0xFFFFFFFF, N)
+                line["mask_bit_exact"] = bool(torch.equal(got, want))
+                line["out_max_abs_err_rel"] = float((o2.cpu() - ref["out"]).abs().max() / ref["out"].abs().max())
+            print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
