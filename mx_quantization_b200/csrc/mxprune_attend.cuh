@@ -204,7 +204,7 @@ k_attend_umma(const AttnParams p) {
             tcgen05_fence_after_sync();
 
             // pass A (A7: bf16 rounding of the matmul output, * scale)
-            float mb = -INFINITY;
+            float mb4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 chains: no serial dependency
             for (int w = 0; w < nwb; ++w) {
                 const uint32_t mw = pick8(mreg, w);
                 uint32_t r[32];
@@ -215,14 +215,15 @@ k_attend_umma(const AttnParams p) {
                     float s = __uint_as_float(r[c]);
                     if (bf16) s = bf16_half_away(s);
                     const float tv = __fmul_rn(s, p.scale);
-                    mb = fmaxf(mb, ((mw >> c) & 1u) ? tv : -INFINITY);
+                    mb4[c & 3] = fmaxf(mb4[c & 3], ((mw >> c) & 1u) ? tv : -INFINITY);
                 }
             }
+            const float mb = fmaxf(fmaxf(mb4[0], mb4[1]), fmaxf(mb4[2], mb4[3]));
             const float m_new = fmaxf(m, mb);
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;     // no kept key so far
             if (m != -INFINITY) l *= exp_nonpos(m - m_use);
             // pass B: exp(t - m) on kept keys; single block: written back over S for pass 2
-            float sum = 0.f;
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
             for (int w = 0; w < nwb; ++w) {
                 const uint32_t mw = pick8(mreg, w);
                 uint32_t r[32];
@@ -232,14 +233,16 @@ k_attend_umma(const AttnParams p) {
                 for (int c = 0; c < 32; ++c) {
                     float s = __uint_as_float(r[c]);
                     if (bf16) s = bf16_half_away(s);
-                    const float ev = ((mw >> c) & 1u) ? exp_nonpos(__fsub_rn(__fmul_rn(s, p.scale), m_use)) : 0.f;
-                    sum += ev;
+                    // evaluated for every position (branch-free), zeroed where the key is pruned
+                    const float ex = exp_nonpos(__fsub_rn(__fmul_rn(s, p.scale), m_use));
+                    const float ev = ((mw >> c) & 1u) ? ex : 0.f;
+                    sum4[c & 3] += ev;
                     r[c] = __float_as_uint(ev);
                 }
                 if (single) tmem_st_32x32b_x32(my_tmem + w * 32, r);
             }
             if (single) tmem_st_wait();
-            l += sum;
+            l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
             m = m_new;
             if (!single) {                          // S columns and sK are reused by the next block
                 tcgen05_fence_before_sync();
@@ -297,19 +300,21 @@ k_attend_umma(const AttnParams p) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(my_tmem + w * 32, r);
                     tmem_ld_wait();
-                    uint32_t mx = 0u;
+                    uint32_t mx4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         float ev = __uint_as_float(r[c]);
                         if (!single) {
                             if (bf16) ev = bf16_half_away(ev);
-                            ev = ((mw >> c) & 1u) ? exp_nonpos(__fsub_rn(__fmul_rn(ev, p.scale), m_fin)) : 0.f;
+                            const float ex = exp_nonpos(__fsub_rn(__fmul_rn(ev, p.scale), m_fin));
+                            ev = ((mw >> c) & 1u) ? ex : 0.f;
                         }
                         uint32_t pb = __float_as_uint(ev * inv);
                         if (bf16) pb = bf16_half_away(pb);
                         r[c] = pb;
-                        mx = max(mx, pb);          // p >= 0: bit patterns order like the values
+                        mx4[c & 3] = max(mx4[c & 3], pb);      // p >= 0: bit patterns order like the values
                     }
+                    const uint32_t mx = max(max(mx4[0], mx4[1]), max(mx4[2], mx4[3]));
                     const int e = mx_shared_exp(mx);
                     const bool dead = (flush && e <= -127) || mx == 0u;
                     const float s1 = exp2i(-e), wgt = exp2i(e - 6);
