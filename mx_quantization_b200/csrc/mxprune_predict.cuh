@@ -66,24 +66,32 @@ template <int NB>
 __device__ __forceinline__ void quantize_row_thread(const float* __restrict__ row, int hd, bool bf16,
                                                     bool flush, RowQ<NB>& rq, int8_t* codes_out,
                                                     unsigned char* op_row = nullptr, int op_stride = 0) {
+    // all loads of the row are issued before the first use: one exposed memory latency per row
+    uint32_t xall[NB][32];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int nd = min(32, hd - 32 * b);
-        uint32_t xb[32];
-        uint32_t mx = 0u;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
             if (4 * v < nd) f = __ldg(reinterpret_cast<const float4*>(row + 32 * b) + v);
-            uint32_t w[4] = {__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z),
-                             __float_as_uint(f.w)};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                if (bf16) w[t] = bf16_half_away(w[t]);
-                xb[4 * v + t] = w[t];
-                mx = max(mx, w[t] & 0x7fffffffu);
-            }
+            xall[b][4 * v + 0] = __float_as_uint(f.x);
+            xall[b][4 * v + 1] = __float_as_uint(f.y);
+            xall[b][4 * v + 2] = __float_as_uint(f.z);
+            xall[b][4 * v + 3] = __float_as_uint(f.w);
         }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int nd = min(32, hd - 32 * b);
+        uint32_t (&xb)[32] = xall[b];
+        uint32_t mx4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            if (bf16) xb[t] = bf16_half_away(xb[t]);
+            mx4[t & 3] = max(mx4[t & 3], xb[t] & 0x7fffffffu);
+        }
+        const uint32_t mx = max(max(mx4[0], mx4[1]), max(mx4[2], mx4[3]));
         const int e = mx_shared_exp(mx);
         const bool dead = flush && e <= -127;
         const float s1 = exp2i(-e);
@@ -128,6 +136,11 @@ __device__ __forceinline__ void quantize_row_thread(const float* __restrict__ ro
                 if (4 * v < nd) dst[v] = cw[v];
         }
     }
+}
+
+// ask L2 for the hd fp32 values of a row this thread will quantize later
+__device__ __forceinline__ void prefetch_row_l2(const float* row, int hd) {
+    for (int o = 0; o < hd; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
 }
 
 // number of this thread's keys >= cand (keys are stored as (u | 0x8000), two per word)
@@ -226,7 +239,7 @@ __device__ __noinline__ void predict_row_generic(uint32_t* __restrict__ mask_out
 }
 
 template <int NB>
-__global__ void __launch_bounds__(K1T)
+__global__ void __launch_bounds__(K1T, (NB <= 2 ? 4 : 3))
 k_predict_topk_rows(const PredParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
@@ -252,7 +265,12 @@ k_predict_topk_rows(const PredParams p) {
     __syncthreads();
     {
         const float* kb = p.k.p + bb * p.k.sB + hh * p.k.sH;
+        {   // first query row of this thread: in L2 by the time the keys are staged
+            const int iq = blockIdx.y * K1T + tid;
+            if (iq < Nq) prefetch_row_l2(p.q.p + bb * p.q.sB + hh * p.q.sH + (int64_t)iq * p.q.sN, hd);
+        }
         for (int j = tid; j < nkp; j += K1T) {
+            if (j + K1T < Nk) prefetch_row_l2(kb + (int64_t)(j + K1T) * p.k.sN, hd);
             if (j < Nk) {
                 RowQ<NB> kq;
                 const int64_t krow = (int64_t)head * Nk + j;
@@ -306,6 +324,7 @@ k_predict_topk_rows(const PredParams p) {
         const bool valid = i < Nq;
         const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
         RowQ<NB> rq;
+        if (i + K1T * (int)gridDim.y < Nq) prefetch_row_l2(qb + (int64_t)(i + K1T * (int)gridDim.y) * p.q.sN, hd);
         if (q_op) {             // padding of the A-operand tile: rows past Nq, head_dim up to 16
             for (int kc = 0; kc < (OL.hdp >> 3); ++kc)
                 if (!valid || kc * 8 >= hd)
