@@ -22,6 +22,8 @@
 // fp32 scores cooperatively and radix-selects on order-preserving float keys.  Both paths return
 // identical sets wherever both apply.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "mxprune_device.cuh"
 #include "mxprune_attend.cuh"
 
@@ -143,24 +145,38 @@ __device__ __forceinline__ void prefetch_row_l2(const float* row, int hd) {
     for (int o = 0; o < hd; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
 }
 
-// number of this thread's keys >= cand (keys are stored as (u | 0x8000), two per word)
-__device__ __forceinline__ int swar_count_ge(const uint32_t* sc, int ng, uint32_t cand) {
-    const uint32_t c2 = cand * 0x00010001u;
-    int cnt = 0;
+// Keys are stored two per 32-bit word as u + K1_KEY_BIAS (<= 0x7BFF): as fp16 BIT PATTERNS they
+// are finite, normal, positive numbers whose float order equals their integer order, so one
+// HSET2.GE compares two keys and one HADD2 accumulates both counts - on the half/FMA pipe, which
+// the rest of this ALU-bound kernel leaves idle.  Padding keys are stored as 0 (below any
+// candidate).  Counts stay exact: at most 128 per half lane, far below fp16's 2048.
+constexpr uint32_t K1_KEY_BIAS = 0x0400u;        // first normal fp16 bit pattern
+constexpr int K1_MAX_M = 0x7BFF - 0x0400 - 2;    // largest |S| bound that keeps biased keys finite fp16
+
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t x) {
+    return *reinterpret_cast<const __half2*>(&x);
+}
+// number of this thread's keys >= cand (cand given WITH bias)
+__device__ __forceinline__ int h2_count_ge(const uint32_t* sc, int ng, uint32_t cand) {
+    const __half2 c2 = u32_as_h2(cand * 0x00010001u);
+    __half2 a0 = u32_as_h2(0u), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll 4
     for (int jg = 0; jg < ng; ++jg) {
         const uint4 w = *reinterpret_cast<const uint4*>(sc + jg * 4);
-        const uint32_t x = ((w.x - c2) & SW_H) | (((w.y - c2) & SW_H) >> 1) |
-                           (((w.z - c2) & SW_H) >> 2) | (((w.w - c2) & SW_H) >> 3);
-        cnt += __popc(x);
+        a0 = __hadd2(a0, __hge2(u32_as_h2(w.x), c2));
+        a1 = __hadd2(a1, __hge2(u32_as_h2(w.y), c2));
+        a2 = __hadd2(a2, __hge2(u32_as_h2(w.z), c2));
+        a3 = __hadd2(a3, __hge2(u32_as_h2(w.w), c2));
     }
-    return cnt;
+    const __half2 t = __hadd2(__hadd2(a0, a1), __hadd2(a2, a3));
+    return (int)(__low2float(t) + __high2float(t));
 }
 
 // (key >= cand) flags of one group of 8 keys, bit t = key t of the group
 __device__ __forceinline__ uint32_t swar_flags8(const uint4& w, uint32_t c2) {
-    const uint32_t x = (((w.x - c2) & SW_H) >> 15) | (((w.y - c2) & SW_H) >> 14) |
-                       (((w.z - c2) & SW_H) >> 13) | (((w.w - c2) & SW_H) >> 12);
+    // (key | 0x8000) - cand keeps bit 15 of each half iff key >= cand (keys, cand < 0x8000)
+    const uint32_t x = ((((w.x | SW_H) - c2) & SW_H) >> 15) | ((((w.y | SW_H) - c2) & SW_H) >> 14) |
+                       ((((w.z | SW_H) - c2) & SW_H) >> 13) | ((((w.w | SW_H) - c2) & SW_H) >> 12);
     return (x & 0xFu) | ((x >> 12) & 0xF0u);
 }
 
@@ -357,7 +373,7 @@ k_predict_topk_rows(const PredParams p) {
             const int nbw = (b < NB - 1) ? 32 : hd - 32 * (NB - 1);
             M += (long long)nbw << (sh + min(spread[b], K1_MAX_SPREAD));
         }
-        if (M > 32766) fast = false;
+        if (M > K1_MAX_M) fast = false;
         if (!fast) {
             M = 0;
 #pragma unroll
@@ -380,12 +396,12 @@ k_predict_topk_rows(const PredParams p) {
                     const int c = nbw - 2 * __popc(rq.sign[b] ^ rec.x);
                     S += (c * (int)rec.y) * mq[b];
                 }
-                us[t] = (((uint32_t)S >> 1) + 1u) | 0x8000u;
+                us[t] = ((uint32_t)S >> 1) + 1u + K1_KEY_BIAS;
             }
             if (jg == ng - 1) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t)
-                    if (jg * 8 + t >= Nk) us[t] = 0x8000u;
+                    if (jg * 8 + t >= Nk) us[t] = 0u;
             }
             *reinterpret_cast<uint4*>(my_sc + jg * 4) =
                 make_uint4(us[0] | (us[4] << 16), us[1] | (us[5] << 16), us[2] | (us[6] << 16),
@@ -395,13 +411,14 @@ k_predict_topk_rows(const PredParams p) {
         // ---- select: T = top_k-th largest key, bit-wise bisection (warp-uniform trip count)
         int wbits = 32 - __clz(moff + 1);
         wbits = __reduce_max_sync(FULL, wbits);
-        uint32_t T = 0u;
+        uint32_t Tv = 0u;                                   // unbiased key value
         for (int bit = wbits - 1; bit >= 0; --bit) {
-            const uint32_t cand = T | (1u << bit);
-            if (swar_count_ge(my_sc, ng, cand) >= kk) T = cand;
+            const uint32_t cand = Tv | (1u << bit);
+            if (h2_count_ge(my_sc, ng, cand + K1_KEY_BIAS) >= kk) Tv = cand;
         }
-        const bool has_gt = T < 0x7fffu;
-        const int ngt = has_gt ? swar_count_ge(my_sc, ng, T + 1u) : 0;
+        const uint32_t T = Tv + K1_KEY_BIAS;
+        const bool has_gt = true;                           // T + 1 <= 0x7C00 - 1 by construction of K1_MAX_M
+        const int ngt = h2_count_ge(my_sc, ng, T + 1u);
 
         // ---- emit the row bitmask (ties: ascending key index)
         {

@@ -1,0 +1,20 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, then the bench on both headline workloads (no CPU leg).
+#   gpurun --timeout 900 -- 'bash tools/gpu_check.sh TAG'
+TAG=${1:-dev}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_gpu_$TAG.txt
+tail -3 gpurun_out/pytest_gpu_$TAG.txt
+for W in deit_base_c2 dit_xl2_c3; do
+  python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline --no-e2e \
+      > gpurun_out/bench_${TAG}_$W.json 2> gpurun_out/bench_${TAG}_$W.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/bench_${TAG}_$W.json"))
+    ks = d["roofline"]["kernels"]
+    print("$W", int(d["value"]), round(d["ms_per_step"], 2), {k: (round(v["avg_ms"], 3), round(v["frac"], 3)) for k, v in ks.items()})
+except Exception as e:
+    print("$W bench failed:", e)
+PY
+done
