@@ -166,6 +166,16 @@ int mxp_pruned_attention_profile(const float* q, int64_t q_sB, int64_t q_sH, int
  */
 int mxp_set_attention_path(int path);
 
+/*
+ * Which kernel scores the predictor (funcs/exponent_based_prediction.py:44-94 + the caller's
+ * `ex_q @ ex_k^T`, workloads/deit/scripts/main.py:118) when Nk <= 256:
+ *   0 (default)  +-2^e bf16 operands on the tcgen05 tensor cores (exact inside the integer-key window),
+ *                keys selected in registers; needs head_dim % 8 == 0 and head_dim >= 32
+ *   1            XOR/POPC on CUDA cores (also used automatically outside the domain of path 0)
+ * Both return identical masks.  Process-wide; returns MXP_E_BADARG for any other value.
+ */
+int mxp_set_predict_path(int path);
+
 /* Number of kernel launches the last successful call on this thread enqueued (bench.py's
  * gpu_launches claim is counted from this). */
 int mxp_last_launch_count(void);

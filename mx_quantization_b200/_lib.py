@@ -19,6 +19,7 @@ _SIGNATURES = {
     "mxp_last_error": (ctypes.c_char_p, []),
     "mxp_last_launch_count": (c_int, []),
     "mxp_set_attention_path": (c_int, [c_int]),
+    "mxp_set_predict_path": (c_int, [c_int]),
     "mxp_limits": (None, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "mxp_quantize_mxint8": (c_int, _VIEW + [c_int] * 6 + [c_void_p] * 4),
     "mxp_exp_sign_approx": (c_int, _VIEW + [c_int] * 6 + [c_void_p] * 2),

@@ -9,6 +9,7 @@
 #include "mxprune_device.cuh"
 #include "mxprune_predict.cuh"
 #include "mxprune_attend.cuh"
+#include "mxprune_predict_tc.cuh"
 
 using namespace mxp;
 
@@ -550,6 +551,107 @@ inline OpsBytes ops_bytes(int B, int H, int Nq, int Nk, int hd) {
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// ---- K1-TC: tensor maps over the strided (B,H,N,hd) fp32 views + launch ----------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// main map: dims {32 floats, N, hd/32, H, B}, box {32, 64, hd/32, 1, 1}, SWIZZLE_128B;
+// tail map (hd % 32 floats at column 32*(hd/32)): dims {tail, N, H, B}, box {tail, 64, 1, 1}.
+static bool make_view_maps(const View& v, int B, int H, int N, int hd, CUtensorMap* m_main, CUtensorMap* m_tail) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const int nfull = hd >> 5, tail = hd & 31;
+    const cuuint64_t sN = (cuuint64_t)v.sN * 4, sH = (cuuint64_t)(H > 1 ? v.sH : hd) * 4,
+                     sB = (cuuint64_t)(B > 1 ? v.sB : (int64_t)N * v.sN) * 4;
+    if (!sN || !sH || !sB || (sN >> 40) || (sH >> 40) || (sB >> 40)) return false;
+    if (nfull) {
+        cuuint64_t dims[5] = {32, (cuuint64_t)N, (cuuint64_t)nfull, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[4] = {sN, 128, sH, sB};
+        cuuint32_t box[5] = {32, (cuuint32_t)K1C_ROWS, (cuuint32_t)nfull, 1, 1}, es[5] = {1, 1, 1, 1, 1};
+        if (enc(m_main, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)v.p, dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    if (tail) {
+        cuuint64_t dims[4] = {(cuuint64_t)tail, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {sN, sH, sB};
+        cuuint32_t box[4] = {(cuuint32_t)tail, (cuuint32_t)K1C_ROWS, 1, 1}, es[4] = {1, 1, 1, 1};
+        if (enc(m_tail, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(v.p + 32 * nfull), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
+template <int NC, bool CODES>
+static int launch_predict_topk_tc_one(const PredParams& p, const K1cMaps& maps, const K1cSmem& L, size_t dyn,
+                                      dim3 grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_tc<NC, CODES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    k_predict_topk_tc<NC, CODES><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring);
+    return check_launch("k_predict_topk_tc");
+}
+
+int g_predict_path = 0;  // 0 = tensor-core scoring (default where it applies), 1 = CUDA-core XOR/POPC kernel
+
+// returns 1 if the shape is outside the tensor-core kernel's domain (caller uses the CUDA-core kernel)
+static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out) {
+    if (g_predict_path != 0 || p.Nk > 256 || p.hd < 32 || (p.hd & 7)) return 1;
+    K1cMaps maps;
+    if (!make_view_maps(p.q, p.B, p.H, p.Nq, p.hd, &maps.q_main, &maps.q_tail)) return 1;
+    if (!make_view_maps(p.k, p.B, p.H, p.Nk, p.hd, &maps.k_main, &maps.k_tail)) return 1;
+    // ring depth: as many 64-row slots as fit with two CTAs per SM
+    const size_t per_cta2 = 232448 / 2 - 1024, per_cta1 = 232448 - 1024;
+    int ring = K1C_MAXR;
+    while (ring > 2 && k1c_smem_layout(p.hd, p.Nk, ring).total > per_cta2) --ring;
+    K1cSmem L = k1c_smem_layout(p.hd, p.Nk, ring);
+    if (L.total > per_cta1) return 1;
+    const int heads = p.B * p.H;
+    const int tiles = (p.Nq + K1C_T - 1) / K1C_T;
+    int splits = (148 * 2 + heads - 1) / heads;
+    if (splits > tiles) splits = tiles;
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)heads, (unsigned)splits);
+    // residency bounded by the 512 TMEM columns of an SM (see launch_attend_umma)
+    const int max_ctas = 512 / L.tmem_cols;
+    size_t dyn = L.total;
+    const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
+    if (dyn < floor_bytes) dyn = floor_bytes;
+    const bool codes = p.q_codes != nullptr || p.k_codes != nullptr;
+    const int nc = p.Nk <= 32 ? 1 : p.Nk <= 64 ? 2 : p.Nk <= 128 ? 4 : p.Nk <= 224 ? 7 : 8;
+#define MXP_TC(NC_)                                                                                     \
+    *rc_out = codes ? launch_predict_topk_tc_one<NC_, true>(p, maps, L, dyn, grid, st)                  \
+                    : launch_predict_topk_tc_one<NC_, false>(p, maps, L, dyn, grid, st)
+    switch (nc) {
+        case 1: MXP_TC(1); break;
+        case 2: MXP_TC(2); break;
+        case 4: MXP_TC(4); break;
+        case 7: MXP_TC(7); break;
+        default: MXP_TC(8); break;
+    }
+#undef MXP_TC
+    return 0;
+}
+
 }  // namespace
 
 // ======================================================================================
@@ -561,6 +663,11 @@ int mxp_abi_version(void) { return MXP_ABI_VERSION; }
 int mxp_set_attention_path(int path) {
     if (path != 0 && path != 1) return fail(MXP_E_BADARG, "attention path %d: 0 = tcgen05, 1 = CUDA-core dp4a", path);
     g_attn_path = path;
+    return MXP_OK;
+}
+int mxp_set_predict_path(int path) {
+    if (path != 0 && path != 1) return fail(MXP_E_BADARG, "predict path %d: 0 = tensor-core scoring, 1 = CUDA-core XOR/POPC", path);
+    g_predict_path = path;
     return MXP_OK;
 }
 const char* mxp_last_error(void) { return g_err; }
@@ -645,6 +752,8 @@ int mxp_predict_scores(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
 size_t mxp_predict_topk_workspace_bytes(int, int, int, int, int) { return 0; }
 
 static int predict_topk_impl(const PredParams& p, cudaStream_t st) {
+    int rc = MXP_OK;
+    if (try_predict_topk_tc(p, st, &rc) == 0) return rc;
     switch ((p.hd + 31) / 32) {
         case 1: return launch_predict_topk_nb<1>(p, st);
         case 2: return launch_predict_topk_nb<2>(p, st);

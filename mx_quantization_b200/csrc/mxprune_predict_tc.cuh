@@ -1,0 +1,619 @@
+// K1-TC: fused MX quantizer + exponent-sign predictor + exact per-row top-k for Nk <= 256,
+// scored on the tensor cores, selected in registers.
+//
+// The reference's predictor is a dense fp32 matmul of +-2^e operands
+// (workloads/deit/scripts/main.py:118, funcs/exponent_based_prediction.py:44-94).  +-2^e is exact
+// in bf16 and every partial sum of one (query, key) pair is an integer multiple of 2^g inside a
+// 16-bit window, so tcgen05.mma kind::f16 with fp32 accumulators returns the reference's score
+// bit for bit (tools/umma_exact_test.cu: exact up to a 20-bit window on B200).  XOR+POPC scoring on
+// CUDA cores costs ~12 instructions per (row, key); the tensor core makes it free and leaves the
+// CUDA cores to the quantizer and the selection.
+//
+// One CTA (128 threads) per (head, row split), two CTAs resident per SM.
+//   stage    Q/K fp32 rows arrive by TMA (cp.async.bulk.tensor) straight from the strided
+//            (B,H,N,hd) view: tensor map dims {32 floats, N, hd/32, H, B}, box {32, 64 rows, hd/32},
+//            SWIZZLE_128B, out-of-range rows zero-filled; a second, unswizzled map covers hd % 32.
+//            A ring of 64-row slots keeps the next chunks in flight while the current one is used.
+//   quantize one thread per 32-wide MX block (conflict-free 128-bit reads of the swizzled slot):
+//            A1 + A2 -> exact bf16 operand c*2^(e-6) for the attention kernel (HBM, MMA-ready),
+//            predictor operand +-2^e (shared memory, MMA-ready), sign word + exponent (shared
+//            memory, for the generic path), optional int8 codes / exponents (HBM).
+//            No float<->int conversion instructions: floor() is an FADD.RM against 2^23 and the
+//            bf16 value comes from one packed HFMA2.BF16 on the (128 + c) bit patterns.
+//   score    S[128 x Nk] = Qp . Kp^T, hd/16 tcgen05.mma (M = 128, N = Nk rounded to 16), fp32 in TMEM
+//   keys     thread t owns query row t == TMEM lane t: score * 2^(-g-1) + offset is the same 15-bit
+//            integer key as the CUDA-core kernel (mxprune_predict.cuh), stored as an fp16 BIT
+//            PATTERN, two per register - the whole row lives in <= 128 registers
+//   select   bit-wise bisection for the top_k-th largest key: per step one HSET2.GE + one HADD2
+//            per two keys, no memory traffic
+//   emit     keys > T kept, keys == T kept in ascending key index until top_k (stable-sort rule)
+// Rows outside the integer window (all-zero block, > 2^14 spread) take the same warp-cooperative
+// fp32 path as the CUDA-core kernel, from the sign words kept in shared memory.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "mxprune_predict.cuh"
+
+namespace mxp {
+
+constexpr int K1C_T = 128;            // threads per CTA == query rows per tile
+constexpr int K1C_ROWS = 64;          // rows per staged chunk
+constexpr int K1C_MAXR = 4;           // ring slots
+
+struct K1cSmem {
+    int nfull, tail, nb, hdp, n_mma, tmem_cols, ring;
+    size_t slot_main, slot_bytes;
+    size_t off_kop, off_qop, off_ksign, off_kexp, off_qsign, off_qexp, off_misc, total;
+};
+
+__host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int Nk, int ring) {
+    K1cSmem L;
+    L.nfull = hd >> 5;
+    L.tail = hd & 31;
+    L.nb = (hd + 31) >> 5;
+    L.hdp = (hd + 15) & ~15;
+    L.n_mma = (Nk + 15) & ~15;
+    int c = 32;
+    while (c < L.n_mma) c <<= 1;
+    L.tmem_cols = c;
+    L.ring = ring;
+    L.slot_main = (size_t)K1C_ROWS * L.nfull * 128;
+    L.slot_bytes = (L.slot_main + (size_t)K1C_ROWS * L.tail * 4 + 1023) & ~(size_t)1023;
+    size_t o = L.slot_bytes * ring;
+    L.off_kop = o;   o += (size_t)(L.hdp >> 3) * L.n_mma * 16;
+    L.off_qop = o;   o += (size_t)(L.hdp >> 3) * K1C_T * 16;
+    L.off_ksign = o; o += (size_t)4 * 256 * 4;
+    L.off_kexp = o;  o += (size_t)4 * 256;
+    L.off_qsign = o; o += (size_t)4 * K1C_T * 4;
+    L.off_qexp = o;  o += (size_t)4 * K1C_T;
+    L.off_misc = o;  o += 128;
+    L.total = o + 1024;                                   // slack to align the base to 1024 bytes
+    return L;
+}
+
+struct K1cMaps {
+    CUtensorMap q_main, q_tail, k_main, k_tail;
+};
+
+// ---- TMA tensor loads (tile mode), completion counted on an mbarrier
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5,%6}], [%7];" ::
+        "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+        "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];" ::
+        "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ __nv_bfloat162 u32_as_bf2(uint32_t x) {
+    return *reinterpret_cast<const __nv_bfloat162*>(&x);
+}
+__device__ __forceinline__ uint32_t bf2_as_u32(__nv_bfloat162 x) {
+    return *reinterpret_cast<const uint32_t*>(&x);
+}
+// bf16 bit pattern of 2^e, e in [-133, 127]
+__device__ __forceinline__ uint32_t bf16_pow2_bits(int e) {
+    return e >= -126 ? (uint32_t)(e + 127) << 7 : 0x40u >> (-127 - e);
+}
+
+// Results of quantizing one MX block (<= 32 elements) held by one thread.
+struct BlockQ {
+    int e, ep;              // A2 exponent, predictor exponent
+    uint32_t sign;          // predictor sign bits, element (8c + 2p + h) at bit 4c + p + 16h
+    uint4 op[4];            // exact operand  c * 2^(e-6), 8 bf16 per chunk
+    uint4 pp[4];            // predictor operand +-2^ep
+    uint32_t cw[8];         // int8 codes, 4 per word (only when CODES)
+};
+
+// xv: the block's 32 fp32 bit patterns (elements >= nd are zero).  A1 + A2 + operand formation.
+template <bool CODES>
+__device__ __forceinline__ void quantize_block_thread(uint32_t (&xv)[32], int nd, bool bf16, bool flush, BlockQ& r) {
+    if (bf16) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) xv[t] = bf16_half_away(xv[t]);
+    }
+    float mx4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 32; ++t) mx4[t & 3] = fmaxf(mx4[t & 3], fabsf(__uint_as_float(xv[t])));
+    const uint32_t mx = __float_as_uint(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
+    const int e = mx_shared_exp(mx);
+    const bool dead = flush && e <= -127;
+    r.e = e;
+    r.ep = dead ? ZERO_BLOCK_EXP : e;
+    const uint32_t e2 = bf16_pow2_bits(r.ep) * 0x00010001u;
+    uint32_t sw = 0u;
+    if (!dead && e >= -120 && e <= 126) {
+        // floor(|x| * 2^(6-e) + 0.5) without F2I: RN add of 0.5 (as the reference rounds it), clamp,
+        // then an add rounded toward -inf against 2^23 + 0x4300 leaves 0x4300 + c in the low 16
+        // bits == the bf16 bit pattern of 128 + c;  (128 + c) * w - 128 * w = c * w exactly.
+        const float s1 = exp2i(6 - e);
+        const uint32_t wb = bf16_pow2_bits(e - 6) * 0x00010001u;
+        const __nv_bfloat162 w2 = u32_as_bf2(wb);
+        const __nv_bfloat162 nw2 = u32_as_bf2((bf16_pow2_bits(e + 1) | 0x8000u) * 0x00010001u);   // -128 * 2^(e-6)
+        const __nv_bfloat162 zero2 = u32_as_bf2(0u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t ow[4], pw[4], fl[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                float v = fmaf(fabsf(__uint_as_float(xv[8 * c + t])), s1, 0.5f);
+                v = fminf(v, 127.0f);
+                fl[t] = __float_as_uint(__fadd_rd(v, 8405760.0f));          // 2^23 + 0x4300
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const uint32_t v2 = __byte_perm(fl[2 * p], fl[2 * p + 1], 0x5410);
+                const uint32_t sx = __byte_perm(xv[8 * c + 2 * p], xv[8 * c + 2 * p + 1], 0x7632) & 0x80008000u;
+                const uint32_t rr = bf2_as_u32(__hfma2(u32_as_bf2(v2), w2, nw2)) ^ sx;
+                const uint32_t m = __hlt2_mask(u32_as_bf2(rr), zero2);      // -0 is not < 0: zero codes count as +
+                ow[p] = rr;
+                pw[p] = (m & 0x80008000u) | e2;
+                sw |= m & (0x00010001u << (4 * c + p));
+            }
+            r.op[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            r.pp[c] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+            if (CODES) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t word = 0u;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int el = 8 * c + 4 * h + t;
+                        const int cm = (int)(fl[4 * h + t] & 0x7fu);
+                        const int sc = (xv[el] >> 31) ? -cm : cm;
+                        word |= ((uint32_t)sc & 0xffu) << (8 * t);
+                    }
+                    r.cw[2 * c + h] = word;
+                }
+            }
+        }
+    } else {
+        // rare: zero / flushed / extreme-exponent block - scalar arithmetic of mxprune_device.cuh
+        const float wgt = exp2i(e - 6);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t ow[4], pw[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int c0 = mx_code(xv[8 * c + 2 * p], e, dead), c1 = mx_code(xv[8 * c + 2 * p + 1], e, dead);
+                ow[p] = pack_bf16_trunc((float)c0 * wgt, (float)c1 * wgt);
+                const uint32_t m = (c0 < 0 ? 0x0000ffffu : 0u) | (c1 < 0 ? 0xffff0000u : 0u);
+                pw[p] = (m & 0x80008000u) | e2;
+                sw |= m & (0x00010001u << (4 * c + p));
+                if (CODES) {
+                    const uint32_t two = ((uint32_t)c0 & 0xffu) | (((uint32_t)c1 & 0xffu) << 8);
+                    if (p & 1) r.cw[2 * c + (p >> 1)] |= two << 16;
+                    else r.cw[2 * c + (p >> 1)] = two;
+                }
+            }
+            r.op[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            r.pp[c] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        }
+    }
+    // padding lanes of a partial block carry no sign and no predictor weight
+    if (nd < 32) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (8 * c >= nd) r.pp[c] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    r.sign = sw;
+}
+
+// number of keys >= cand among NW2 register words (two fp16-pattern keys per word)
+template <int NW2>
+__device__ __forceinline__ int count_ge_regs(const uint32_t (&kw)[NW2], uint32_t cand) {
+    const __half2 c2 = u32_as_h2(cand * 0x00010001u);
+    __half2 a0 = u32_as_h2(0u), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+    for (int w = 0; w < NW2; w += 4) {
+        a0 = __hadd2(a0, __hge2(u32_as_h2(kw[w]), c2));
+        a1 = __hadd2(a1, __hge2(u32_as_h2(kw[w + 1]), c2));
+        a2 = __hadd2(a2, __hge2(u32_as_h2(kw[w + 2]), c2));
+        a3 = __hadd2(a3, __hge2(u32_as_h2(kw[w + 3]), c2));
+    }
+    const __half2 t = __hadd2(__hadd2(a0, a1), __hadd2(a2, a3));
+    return (int)(__low2float(t) + __high2float(t));
+}
+
+// keep only the m lowest set bits of x (0 <= m <= 32), branch-free binary search
+__device__ __forceinline__ uint32_t keep_lowest_bits_fast(uint32_t x, int m) {
+    if (m <= 0) return 0u;
+    if (m >= __popc(x)) return x;
+    int pos = 0;                                    // bits [0, pos) hold fewer than m set bits
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const int c = __popc(x & (((1u << s) - 1u) << pos));
+        if (c < m) { m -= c; pos += s; }
+    }
+    // bit `pos` is the m-th remaining set bit's position or lower; include it
+    return x & ((2u << pos) - 1u);
+}
+
+// Generic path (any exponents), warp-cooperative, one row: fp32 scores, same summation order as
+// predict_row_generic in mxprune_predict.cuh.  s_ksign / s_kexp: [b][256].
+__device__ __noinline__ void predict_row_generic_tc(uint32_t* __restrict__ mask_out, int32_t* __restrict__ idx_out,
+                                                    int Nk, int kk, int hd, int nb, int64_t row, const uint32_t* sq,
+                                                    const int* ep, const uint32_t* s_ksign,
+                                                    const signed char* s_kexp) {
+    constexpr int KPL = 8;
+    const int lane = threadIdx.x & 31;
+    uint32_t u[KPL];
+    uint32_t aor = 0u, aand = 0xffffffffu;
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) {
+        const int j = r * 32 + lane;
+        const bool valid = j < Nk;
+        float s = 0.f;
+        if (valid) {
+            for (int b = 0; b < nb; ++b) {
+                const int nbw = min(32, hd - 32 * b);
+                const float cnt = (float)(nbw - 2 * __popc(s_ksign[b * 256 + j] ^ sq[b]));
+                const float t = exp2i((int)s_kexp[b * 256 + j]) * cnt;
+                s = (b == 0) ? t * exp2i(ep[0]) : fmaf(t, exp2i(ep[b]), s);
+            }
+        }
+        u[r] = valid ? ordered_key(s) : 0u;
+        aor |= u[r];
+        aand &= valid ? u[r] : 0xffffffffu;
+    }
+    aor = __reduce_or_sync(FULL, aor);
+    aand = __reduce_and_sync(FULL, aand);
+    uint32_t T = aand, vary = aor & ~aand;
+    while (vary) {
+        const uint32_t m1 = 1u << (31 - __clz(vary));
+        vary ^= m1;
+        const uint32_t cand = T | m1;
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) c += (u[r] >= cand) ? 1 : 0;
+        c = __reduce_add_sync(FULL, c);
+        if (c >= kk) T = cand;
+    }
+    uint32_t ge[KPL], gt[KPL];
+    int ngt = 0;
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) {
+        ge[r] = __ballot_sync(FULL, u[r] >= T);
+        gt[r] = __ballot_sync(FULL, u[r] > T);
+        ngt += __popc(gt[r]);
+    }
+    int rem = kk - ngt, base = 0;
+    uint32_t myword = 0u;
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) {
+        const uint32_t eq = ge[r] & ~gt[r];
+        const int c = __popc(eq);
+        uint32_t take;
+        if (c <= rem) { take = eq; rem -= c; }
+        else { take = keep_lowest_bits(eq, rem); rem = 0; }
+        const uint32_t w = gt[r] | take;
+        if (lane == r) myword = w;
+        if (idx_out) {
+            if ((w >> lane) & 1u) idx_out[row * kk + base + __popc(w & ((1u << lane) - 1u))] = r * 32 + lane;
+            base += __popc(w);
+        }
+    }
+    const int NW = (Nk + 31) >> 5;
+    if (lane < NW) mask_out[row * NW + lane] = myword;
+}
+
+// NC = number of 32-key TMEM chunks a row's keys occupy (Nk <= 32 * NC).
+template <int NC, bool CODES>
+__global__ void __launch_bounds__(K1C_T, 2)
+k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring) {
+    extern __shared__ unsigned char smem_raw_tc[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw_tc + 1023) & ~(uintptr_t)1023);
+    const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
+    const K1cSmem L = k1c_smem_layout(hd, Nk, ring);
+    const int nfull = L.nfull, tail = L.tail, nb = L.nb, n_mma = L.n_mma;
+    const int kch = L.hdp >> 3;                                     // 16-byte chunks per operand row
+    unsigned char* s_kop = smem + L.off_kop;
+    unsigned char* s_qop = smem + L.off_qop;
+    uint32_t* s_ksign = reinterpret_cast<uint32_t*>(smem + L.off_ksign);
+    signed char* s_kexp = reinterpret_cast<signed char*>(smem + L.off_kexp);
+    uint32_t* s_qsign = reinterpret_cast<uint32_t*>(smem + L.off_qsign);
+    signed char* s_qexp = reinterpret_cast<signed char*>(smem + L.off_qexp);
+    int* s_kmin = reinterpret_cast<int*>(smem + L.off_misc);        // [4]
+    int* s_kmax = s_kmin + 4;                                       // [4]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_kmax + 4);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_misc + 64);   // [K1C_MAXR]
+    uint64_t* bar_mma = bar_full + K1C_MAXR;
+
+    const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const bool bf16 = p.bf16, flush = p.flush;
+    const bool write_k = p.k_codes != nullptr && blockIdx.y == 0;
+    const bool write_kop = p.k_op != nullptr && blockIdx.y == 0;
+    const OpsLayout OL = ops_layout(Nq, Nk, hd);
+    unsigned char* k_op = p.k_op ? p.k_op + (size_t)head * OL.k_head_bytes : nullptr;
+    unsigned char* q_op = p.q_op ? p.q_op + (size_t)head * OL.q_head_bytes : nullptr;
+
+    // ---- chunk schedule of this CTA: K chunks first, then two Q chunks per tile
+    const int nkc = (Nk + K1C_ROWS - 1) / K1C_ROWS;
+    const int tiles = (Nq + K1C_T - 1) / K1C_T;
+    const int my_tiles = (tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int nchunks = nkc + 2 * my_tiles;
+    const uint32_t slot_tx = (uint32_t)(L.slot_main + (size_t)K1C_ROWS * tail * 4);
+
+    auto issue = [&](int c) {                                      // one thread
+        unsigned char* slot = smem + (size_t)(c % ring) * L.slot_bytes;
+        uint64_t* bar = &bar_full[c % ring];
+        const bool is_k = c < nkc;
+        int row0;
+        if (is_k) row0 = c * K1C_ROWS;
+        else {
+            const int qc = c - nkc;
+            row0 = ((int)blockIdx.y + (qc >> 1) * (int)gridDim.y) * K1C_T + (qc & 1) * K1C_ROWS;
+        }
+        mbar_expect_tx(bar, slot_tx);
+        if (nfull) tma_load_5d(slot, is_k ? &maps.k_main : &maps.q_main, 0, row0, 0, hh, bb, bar);
+        if (tail) tma_load_4d(slot + L.slot_main, is_k ? &maps.k_tail : &maps.q_tail, 0, row0, hh, bb, bar);
+    };
+
+    if (tid == 0) {
+        for (int r = 0; r < ring; ++r) mbar_init(&bar_full[r], 1);
+        mbar_init(bar_mma, 1);
+        prefetch_tmap(&maps.k_main); prefetch_tmap(&maps.q_main);
+        if (tail) { prefetch_tmap(&maps.k_tail); prefetch_tmap(&maps.q_tail); }
+    }
+    if (tid < 4) { s_kmin[tid] = 0x7fffffff; s_kmax[tid] = -0x7fffffff; }
+    if (warp == 0) tmem_alloc(s_tmem, (uint32_t)L.tmem_cols);
+    tcgen05_fence_before_sync();
+    __syncthreads();
+    tcgen05_fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) {
+        const int pre = min(ring, nchunks);
+        for (int c = 0; c < pre; ++c) issue(c);
+    }
+    const uint32_t idesc = umma_idesc_bf16_f32(128, n_mma);
+    const int NW = (Nk + 31) >> 5;
+    uint32_t ph_mma = 0;
+
+    for (int c = 0; c < nchunks; ++c) {
+        const bool is_k = c < nkc;
+        const int qc = c - nkc;
+        const int tile = is_k ? 0 : (int)blockIdx.y + (qc >> 1) * (int)gridDim.y;
+        const int row0 = is_k ? c * K1C_ROWS : tile * K1C_T + (qc & 1) * K1C_ROWS;
+        const int nrows = is_k ? Nk : Nq;
+        const unsigned char* slot = smem + (size_t)(c % ring) * L.slot_bytes;
+        mbar_wait(&bar_full[c % ring], (uint32_t)((c / ring) & 1));
+
+        // -------- quantize the chunk: one thread per MX block
+        const int ntask = K1C_ROWS * nb;
+        for (int t = tid; t < ntask; t += K1C_T) {
+            const int b = t >> 6, rl = t & 63;                      // block-major: consecutive lanes, consecutive rows
+            const int row = row0 + rl;
+            const bool in_range = row < nrows;
+            const bool full = b < nfull;
+            const int nd = full ? 32 : tail;
+            uint32_t xv[32];
+            if (full) {
+                const unsigned char* src = slot + (size_t)t * 128;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(src + ((s ^ (t & 7)) << 4));
+                    xv[4 * s] = v.x; xv[4 * s + 1] = v.y; xv[4 * s + 2] = v.z; xv[4 * s + 3] = v.w;
+                }
+            } else {
+                const unsigned char* src = slot + L.slot_main + (size_t)rl * tail * 4;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (4 * s < tail) v = *reinterpret_cast<const uint4*>(src + (s << 4));
+                    xv[4 * s] = v.x; xv[4 * s + 1] = v.y; xv[4 * s + 2] = v.z; xv[4 * s + 3] = v.w;
+                }
+            }
+            BlockQ r;
+            quantize_block_thread<CODES>(xv, nd, bf16, flush, r);
+            const int nchunk = full ? 4 : (kch - 4 * nfull);       // 16-byte operand chunks this block owns
+            if (is_k) {
+                if (row < n_mma) {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        if (ch < nchunk)
+                            *reinterpret_cast<uint4*>(s_kop + ((size_t)(4 * b + ch) * n_mma + row) * 16) = r.pp[ch];
+                }
+                s_ksign[b * 256 + row] = r.sign;
+                s_kexp[b * 256 + row] = (signed char)r.ep;
+                {   // b is warp-uniform (64 tasks per block index): one shared-memory atomic per warp
+                    const int lo = __reduce_min_sync(FULL, in_range ? r.ep : 0x7fffffff);
+                    const int hi = __reduce_max_sync(FULL, in_range ? r.ep : -0x7fffffff);
+                    if ((tid & 31) == 0) { atomicMin(&s_kmin[b], lo); atomicMax(&s_kmax[b], hi); }
+                }
+                if (write_kop && row < OL.kb_rows) {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        if (ch < nchunk)
+                            *reinterpret_cast<uint4*>(k_op + k_op_offset(OL, row, 4 * b + ch)) = r.op[ch];
+                }
+                if (CODES && write_k && in_range) {
+                    const int64_t krow = (int64_t)head * Nk + row;
+                    p.k_exps[krow * nb + b] = (int8_t)r.e;
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(p.k_codes + krow * hd + 32 * b);
+#pragma unroll
+                    for (int v = 0; v < 8; ++v)
+                        if (4 * v < nd) dst[v] = r.cw[v];
+                }
+            } else {
+                const int rt = row - tile * K1C_T;                  // row within the tile
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    if (ch < nchunk)
+                        *reinterpret_cast<uint4*>(s_qop + ((size_t)(4 * b + ch) * K1C_T + rt) * 16) = r.pp[ch];
+                s_qsign[b * K1C_T + rt] = r.sign;
+                s_qexp[b * K1C_T + rt] = (signed char)r.ep;
+                if (q_op) {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        if (ch < nchunk)
+                            *reinterpret_cast<uint4*>(q_op + q_op_offset(OL, row, 4 * b + ch)) = r.op[ch];
+                }
+                if (CODES && p.q_codes && in_range) {
+                    const int64_t qrow = (int64_t)head * Nq + row;
+                    p.q_exps[qrow * nb + b] = (int8_t)r.e;
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(p.q_codes + qrow * hd + 32 * b);
+#pragma unroll
+                    for (int v = 0; v < 8; ++v)
+                        if (4 * v < nd) dst[v] = r.cw[v];
+                }
+            }
+        }
+        fence_proxy_async_smem();                                   // operand stores -> visible to the MMA
+        __syncthreads();                                            // slot consumed; operands complete
+        if (tid == 0 && c + ring < nchunks) issue(c + ring);
+        if (is_k || (qc & 1) == 0) continue;
+
+        // =============== a full query tile is quantized: score, select, emit
+        if (tid == 0) {
+            tcgen05_fence_after_sync();
+            for (int ks = 0; ks < (L.hdp >> 4); ++ks) {
+                const uint64_t da = umma_smem_desc(smem_u32(s_qop + (size_t)(2 * ks) * K1C_T * 16), K1C_T * 16, 128);
+                const uint64_t db = umma_smem_desc(smem_u32(s_kop + (size_t)(2 * ks) * n_mma * 16), n_mma * 16, 128);
+                umma_bf16_ss(tmem, da, db, idesc, ks > 0);
+            }
+            umma_commit(bar_mma);
+        }
+        // ---- integer-key parameters of this thread's row (same window rules as mxprune_predict.cuh)
+        const int i = tile * K1C_T + tid;
+        const bool valid = i < Nq;
+        const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
+        int kmin[4], spread[4], epq[4];
+        uint32_t sq[4];
+        bool wide = false;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            kmin[b] = b < nb ? s_kmin[b] : 0;
+            spread[b] = b < nb ? s_kmax[b] - kmin[b] : 0;
+            wide |= spread[b] > K1_MAX_SPREAD;
+            epq[b] = b < nb ? (int)s_qexp[b * K1C_T + tid] : 0;
+            sq[b] = b < nb ? s_qsign[b * K1C_T + tid] : 0u;
+        }
+        int g = 0x7fffffff;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (b < nb) g = min(g, epq[b] + kmin[b]);
+        bool fast = valid && !wide && g >= -100 && g <= 80;
+        long long M = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (b < nb) {
+                int sh = epq[b] + kmin[b] - g;
+                if (sh > K1_MAX_SPREAD) { fast = false; sh = K1_MAX_SPREAD; }
+                const int nbw = min(32, hd - 32 * b);
+                M += (long long)nbw << (sh + min(spread[b], K1_MAX_SPREAD));
+            }
+        }
+        if (M > K1_MAX_M) fast = false;
+        if (!fast) M = 0;
+        const int moff = ((int)M + 1) & ~1;
+        const float scl = fast ? exp2i(-g - 1) : 0.f;
+        const float cadd = 8388608.0f + (float)((moff >> 1) + 1 + (int)K1_KEY_BIAS);
+
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1u;
+        tcgen05_fence_after_sync();
+
+        // ---- scores -> fp16-pattern keys in registers: word 16w + t = keys (32w + t, 32w + 16 + t)
+        uint32_t kw[NC * 16];
+#pragma unroll
+        for (int w = 0; w < NC; ++w) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(my_tmem + w * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const uint32_t lo = __float_as_uint(fmaf(__uint_as_float(r[t]), scl, cadd));
+                const uint32_t hi = __float_as_uint(fmaf(__uint_as_float(r[t + 16]), scl, cadd));
+                uint32_t word = __byte_perm(lo, hi, 0x5410);
+                if (32 * w + 32 > Nk) {                             // padding keys -> 0 (below every candidate)
+                    if (32 * w + t >= Nk) word &= 0xffff0000u;
+                    if (32 * w + 16 + t >= Nk) word &= 0x0000ffffu;
+                }
+                kw[16 * w + t] = word;
+            }
+        }
+        // every thread has its row parameters and its keys in registers: TMEM and the Q-side shared
+        // memory may be reused by the next tile from here on (warps run the selection unsynchronised)
+        tcgen05_fence_before_sync();
+        __syncthreads();
+
+        // ---- select: T = top_k-th largest key (warp-uniform trip count)
+        int wbits = 32 - __clz(moff + 1);
+        wbits = __reduce_max_sync(FULL, wbits);
+        uint32_t Tv = 0u;
+        for (int bit = wbits - 1; bit >= 0; --bit) {
+            const uint32_t cand = Tv | (1u << bit);
+            if (count_ge_regs<NC * 16>(kw, cand + K1_KEY_BIAS) >= kk) Tv = cand;
+        }
+        const uint32_t T = Tv + K1_KEY_BIAS;
+        const int ngt = count_ge_regs<NC * 16>(kw, T + 1u);
+
+        // ---- emit the row bitmask (ties: ascending key index)
+        {
+            int rem = kk - ngt, pos = 0;
+            const __half2 t2 = u32_as_h2(T * 0x00010001u);
+            const bool store = valid && fast;
+#pragma unroll
+            for (int w = 0; w < NC; ++w) {
+                uint32_t gt = 0u, eq = 0u;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const __half2 kv = u32_as_h2(kw[16 * w + t]);
+                    gt |= __hgt2_mask(kv, t2) & (0x00010001u << t);
+                    eq |= __heq2_mask(kv, t2) & (0x00010001u << t);
+                }
+                const int cnt = __popc(eq);
+                uint32_t take = eq;
+                if (cnt > rem) take = keep_lowest_bits_fast(eq, rem);
+                rem -= min(cnt, rem);
+                const uint32_t word = gt | take;
+                if (store && w < NW) {
+                    p.mask[row * NW + w] = word;
+                    if (p.idx) {
+                        uint32_t w2 = word;
+                        while (w2) {
+                            const int bpos = __ffs(w2) - 1;
+                            w2 &= w2 - 1u;
+                            p.idx[row * kk + pos++] = w * 32 + bpos;
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- rows outside the integer-key window: warp-cooperative generic path
+        unsigned todo = __ballot_sync(FULL, valid && !fast);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            uint32_t gsq[4];
+            int gep[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                gsq[b] = __shfl_sync(FULL, sq[b], l);
+                gep[b] = __shfl_sync(FULL, epq[b], l);
+            }
+            const int64_t grow = (int64_t)head * Nq + (tile * K1C_T + (tid & ~31) + l);
+            predict_row_generic_tc(p.mask, p.idx, Nk, kk, hd, nb, grow, gsq, gep, s_ksign, s_kexp);
+        }
+    }
+    tcgen05_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)L.tmem_cols);
+}
+
+}  // namespace mxp

@@ -62,6 +62,15 @@ def set_attention_path(path: str) -> None:
     _lib.check(_lib.load().mxp_set_attention_path(codes[path]), "mxp_set_attention_path")
 
 
+def set_predict_path(path: str) -> None:
+    """'tcgen05' (default: predictor scored on the tensor cores, keys selected in registers) or
+    'cuda_core' (XOR/POPC kernel; also used automatically outside the tensor-core kernel's domain)."""
+    codes = {"tcgen05": 0, "cuda_core": 1}
+    if path not in codes:
+        raise ValueError(f"predict path must be one of {sorted(codes)}")
+    _lib.check(_lib.load().mxp_set_predict_path(codes[path]), "mxp_set_predict_path")
+
+
 def last_launch_count() -> int:
     return _lib.load().mxp_last_launch_count()
 

@@ -68,13 +68,21 @@ def test_pred_scores_bit_exact(mxq, B, H, N, hd, kind, bfloat, flush):
     assert torch.equal(s, O.pred_scores_integer(qc, qe, kc, ke))
 
 
+@pytest.mark.parametrize("pred_path", ["tcgen05", "cuda_core"])
 @pytest.mark.parametrize("B,H,N,hd,kind,bfloat,flush", SHAPES)
 @pytest.mark.parametrize("kfrac", [0.0, 0.15, 0.6, 1.0])
-def test_topk_mask_bit_exact(mxq, B, H, N, hd, kind, bfloat, flush, kfrac):
+def test_topk_mask_bit_exact(mxq, B, H, N, hd, kind, bfloat, flush, kfrac, pred_path):
+    """Both predictor kernels (tensor-core scoring / CUDA-core XOR+POPC) against the oracle."""
     top_k = max(1, min(N, int(round(kfrac * N))))
     q, k, _ = make_qkv(B, H, N, hd, seed=3, kind=kind)
     specs = mx_specs(bfloat, flush)
-    r = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k, return_idx=True, return_codes=True)
+    mxq.set_predict_path(pred_path)
+    try:
+        r = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k, return_idx=True, return_codes=True)
+        r_nocodes = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k)
+    finally:
+        mxq.set_predict_path("tcgen05")
+    assert torch.equal(r_nocodes["mask"], r["mask"])
     qc, qe = O.quantize_mxint8(q, 32, bfloat, flush)
     kc, ke = O.quantize_mxint8(k, 32, bfloat, flush)
     idx = O.canonical_topk(O.pred_scores_integer(qc, qe, kc, ke), top_k)
@@ -167,6 +175,13 @@ def test_full_size_properties(mxq):
     # deterministic
     out2, mask2 = mxq.pruned_attention(q, k, v, specs, top_k, return_mask=True)
     assert torch.equal(out, out2) and torch.equal(mask, mask2)
+    # the CUDA-core predictor kernel selects the same sets on all 4096 heads
+    mxq.set_predict_path("cuda_core")
+    try:
+        _, mask3 = mxq.pruned_attention(q, k, v, specs, top_k, return_mask=True)
+    finally:
+        mxq.set_predict_path("tcgen05")
+    assert torch.equal(mask, mask3)
     # head independence: a (batch, head) slice computed alone gives the same bits
     sl = (slice(17, 19), slice(5, 8))
     out_s, mask_s = mxq.pruned_attention(q[sl], k[sl], v[sl], specs, top_k, return_mask=True)
