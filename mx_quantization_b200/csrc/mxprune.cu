@@ -621,9 +621,10 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
     if (!make_view_maps(p.k, p.B, p.H, p.Nk, p.hd, &maps.k_main, &maps.k_tail)) return 1;
     // ring depth: as many 64-row slots as fit with two CTAs per SM
     const size_t per_cta2 = 232448 / 2 - 1024, per_cta1 = 232448 - 1024;
+    const int nc = p.Nk <= 32 ? 1 : p.Nk <= 64 ? 2 : p.Nk <= 128 ? 4 : p.Nk <= 224 ? 7 : 8;
     int ring = K1C_MAXR;
-    while (ring > 2 && k1c_smem_layout(p.hd, p.Nk, ring).total > per_cta2) --ring;
-    K1cSmem L = k1c_smem_layout(p.hd, p.Nk, ring);
+    while (ring > 2 && k1c_smem_layout(p.hd, nc, ring).total > per_cta2) --ring;
+    K1cSmem L = k1c_smem_layout(p.hd, nc, ring);
     if (L.total > per_cta1) return 1;
     const int heads = p.B * p.H;
     const int tiles = (p.Nq + K1C_T - 1) / K1C_T;
@@ -637,7 +638,6 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
     const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
     if (dyn < floor_bytes) dyn = floor_bytes;
     const bool codes = p.q_codes != nullptr || p.k_codes != nullptr;
-    const int nc = p.Nk <= 32 ? 1 : p.Nk <= 64 ? 2 : p.Nk <= 128 ? 4 : p.Nk <= 224 ? 7 : 8;
 #define MXP_TC(NC_)                                                                                     \
     *rc_out = codes ? launch_predict_topk_tc_one<NC_, true>(p, maps, L, dyn, grid, st)                  \
                     : launch_predict_topk_tc_one<NC_, false>(p, maps, L, dyn, grid, st)

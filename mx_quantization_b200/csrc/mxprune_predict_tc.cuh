@@ -48,13 +48,15 @@ struct K1cSmem {
     size_t off_kop, off_qop, off_ksign, off_kexp, off_qsign, off_qexp, off_misc, total;
 };
 
-__host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int Nk, int ring) {
+// nc = number of 32-key chunks (the kernel's NC): the MMA covers 32 * nc key columns, rows past Nk
+// of the predictor operand are zero so that padding keys score exactly 0.
+__host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring) {
     K1cSmem L;
     L.nfull = hd >> 5;
     L.tail = hd & 31;
     L.nb = (hd + 31) >> 5;
     L.hdp = (hd + 15) & ~15;
-    L.n_mma = (Nk + 15) & ~15;
+    L.n_mma = 32 * nc;
     int c = 32;
     while (c < L.n_mma) c <<= 1;
     L.tmem_cols = c;
@@ -133,7 +135,18 @@ __device__ __forceinline__ void quantize_block_thread(uint32_t (&xv)[32], int nd
     r.ep = dead ? ZERO_BLOCK_EXP : e;
     const uint32_t e2 = bf16_pow2_bits(r.ep) * 0x00010001u;
     uint32_t sw = 0u;
-    if (!dead && e >= -120 && e <= 126) {
+    if (mx == 0u) {
+        // all-zero block (also every out-of-range row the TMA zero-filled): codes 0, signs +
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            r.op[c] = make_uint4(0u, 0u, 0u, 0u);
+            r.pp[c] = make_uint4(e2, e2, e2, e2);
+        }
+        if (CODES) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) r.cw[v] = 0u;
+        }
+    } else if (!dead && e >= -120 && e <= 126) {
         // floor(|x| * 2^(6-e) + 0.5) without F2I: RN add of 0.5 (as the reference rounds it), clamp,
         // then an add rounded toward -inf against 2^23 + 0x4300 leaves 0x4300 + c in the low 16
         // bits == the bf16 bit pattern of 128 + c;  (128 + c) * w - 128 * w = c * w exactly.
@@ -309,16 +322,18 @@ __device__ __noinline__ void predict_row_generic_tc(uint32_t* __restrict__ mask_
     if (lane < NW) mask_out[row * NW + lane] = myword;
 }
 
-// NC = number of 32-key TMEM chunks a row's keys occupy (Nk <= 32 * NC).
+// NC = number of 32-key TMEM chunks a row's keys occupy (Nk <= 32 * NC); the MMA's N is 32 * NC.
 template <int NC, bool CODES>
 __global__ void __launch_bounds__(K1C_T, 2)
 k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring) {
     extern __shared__ unsigned char smem_raw_tc[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw_tc + 1023) & ~(uintptr_t)1023);
+    constexpr int NMMA = 32 * NC;
     const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
-    const K1cSmem L = k1c_smem_layout(hd, Nk, ring);
-    const int nfull = L.nfull, tail = L.tail, nb = L.nb, n_mma = L.n_mma;
+    const K1cSmem L = k1c_smem_layout(hd, NC, ring);
+    const int nfull = L.nfull, tail = L.tail, nb = L.nb;
     const int kch = L.hdp >> 3;                                     // 16-byte chunks per operand row
+    const int tail_chunks = kch - 4 * nfull;                        // operand chunks the partial block owns
     unsigned char* s_kop = smem + L.off_kop;
     unsigned char* s_qop = smem + L.off_qop;
     uint32_t* s_ksign = reinterpret_cast<uint32_t*>(smem + L.off_ksign);
@@ -331,14 +346,16 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_misc + 64);   // [K1C_MAXR]
     uint64_t* bar_mma = bar_full + K1C_MAXR;
 
-    const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
+    const int head = blockIdx.x, bb = head / p.H, hh = head - bb * p.H;
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool bf16 = p.bf16, flush = p.flush;
-    const bool write_k = p.k_codes != nullptr && blockIdx.y == 0;
+    const bool write_k = CODES && p.k_codes != nullptr && blockIdx.y == 0;
+    const bool write_q = CODES && p.q_codes != nullptr;
     const bool write_kop = p.k_op != nullptr && blockIdx.y == 0;
     const OpsLayout OL = ops_layout(Nq, Nk, hd);
     unsigned char* k_op = p.k_op ? p.k_op + (size_t)head * OL.k_head_bytes : nullptr;
     unsigned char* q_op = p.q_op ? p.q_op + (size_t)head * OL.q_head_bytes : nullptr;
+    const int kb_rows = OL.kb_rows;
 
     // ---- chunk schedule of this CTA: K chunks first, then two Q chunks per tile
     const int nkc = (Nk + K1C_ROWS - 1) / K1C_ROWS;
@@ -346,10 +363,11 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     const int my_tiles = (tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
     const int nchunks = nkc + 2 * my_tiles;
     const uint32_t slot_tx = (uint32_t)(L.slot_main + (size_t)K1C_ROWS * tail * 4);
+    const uint32_t slot_bytes = (uint32_t)L.slot_bytes, slot_main = (uint32_t)L.slot_main;
 
-    auto issue = [&](int c) {                                      // one thread
-        unsigned char* slot = smem + (size_t)(c % ring) * L.slot_bytes;
-        uint64_t* bar = &bar_full[c % ring];
+    auto issue = [&](int c, int slot_i) {                           // one thread
+        unsigned char* slot = smem + (size_t)slot_i * slot_bytes;
+        uint64_t* bar = &bar_full[slot_i];
         const bool is_k = c < nkc;
         int row0;
         if (is_k) row0 = c * K1C_ROWS;
@@ -359,7 +377,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
         }
         mbar_expect_tx(bar, slot_tx);
         if (nfull) tma_load_5d(slot, is_k ? &maps.k_main : &maps.q_main, 0, row0, 0, hh, bb, bar);
-        if (tail) tma_load_4d(slot + L.slot_main, is_k ? &maps.k_tail : &maps.q_tail, 0, row0, hh, bb, bar);
+        if (tail) tma_load_4d(slot + slot_main, is_k ? &maps.k_tail : &maps.q_tail, 0, row0, hh, bb, bar);
     };
 
     if (tid == 0) {
@@ -377,39 +395,45 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
     if (tid == 0) {
         const int pre = min(ring, nchunks);
-        for (int c = 0; c < pre; ++c) issue(c);
+        for (int c = 0; c < pre; ++c) issue(c, c);
     }
-    const uint32_t idesc = umma_idesc_bf16_f32(128, n_mma);
+    const uint32_t idesc = umma_idesc_bf16_f32(128, NMMA);
     const int NW = (Nk + 31) >> 5;
+    const int npad = NMMA - Nk;                                     // padding key columns (score exactly 0)
     uint32_t ph_mma = 0;
+    int slot_i = 0;
+    uint32_t slot_par = 0;
+    int tile = (int)blockIdx.y - (int)gridDim.y;                    // advanced at the first chunk of every tile
 
     for (int c = 0; c < nchunks; ++c) {
         const bool is_k = c < nkc;
-        const int qc = c - nkc;
-        const int tile = is_k ? 0 : (int)blockIdx.y + (qc >> 1) * (int)gridDim.y;
-        const int row0 = is_k ? c * K1C_ROWS : tile * K1C_T + (qc & 1) * K1C_ROWS;
+        const bool q_second = !is_k && ((c - nkc) & 1);
+        if (!is_k && !q_second) tile += (int)gridDim.y;
+        const int row0 = is_k ? c * K1C_ROWS : tile * K1C_T + (q_second ? K1C_ROWS : 0);
         const int nrows = is_k ? Nk : Nq;
-        const unsigned char* slot = smem + (size_t)(c % ring) * L.slot_bytes;
-        mbar_wait(&bar_full[c % ring], (uint32_t)((c / ring) & 1));
+        const unsigned char* slot = smem + (size_t)slot_i * slot_bytes;
+        mbar_wait(&bar_full[slot_i], slot_par);
 
-        // -------- quantize the chunk: one thread per MX block
+        // -------- quantize the chunk: one thread per MX block, block-major task order
+        // (consecutive lanes <-> consecutive rows of one block index: conflict-free reads of the
+        //  swizzled slot, conflict-free / coalesced operand stores)
         const int ntask = K1C_ROWS * nb;
         for (int t = tid; t < ntask; t += K1C_T) {
-            const int b = t >> 6, rl = t & 63;                      // block-major: consecutive lanes, consecutive rows
+            const int b = t >> 6, rl = t & 63;
             const int row = row0 + rl;
             const bool in_range = row < nrows;
             const bool full = b < nfull;
-            const int nd = full ? 32 : tail;
             uint32_t xv[32];
             if (full) {
-                const unsigned char* src = slot + (size_t)t * 128;
+                const unsigned char* src = slot + t * 128;
+                const int sw7 = (t & 7) << 4;
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(src + ((s ^ (t & 7)) << 4));
+                    const uint4 v = *reinterpret_cast<const uint4*>(src + ((s << 4) ^ sw7));
                     xv[4 * s] = v.x; xv[4 * s + 1] = v.y; xv[4 * s + 2] = v.z; xv[4 * s + 3] = v.w;
                 }
             } else {
-                const unsigned char* src = slot + L.slot_main + (size_t)rl * tail * 4;
+                const unsigned char* src = slot + slot_main + rl * tail * 4;
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -418,14 +442,16 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                 }
             }
             BlockQ r;
-            quantize_block_thread<CODES>(xv, nd, bf16, flush, r);
-            const int nchunk = full ? 4 : (kch - 4 * nfull);       // 16-byte operand chunks this block owns
+            quantize_block_thread<CODES>(xv, full ? 32 : tail, bf16, flush, r);
+            const int nchunk = full ? 4 : tail_chunks;
             if (is_k) {
-                if (row < n_mma) {
+                if (row < NMMA) {
+                    unsigned char* dst = s_kop + ((size_t)(4 * b) * NMMA + row) * 16;
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch)
                         if (ch < nchunk)
-                            *reinterpret_cast<uint4*>(s_kop + ((size_t)(4 * b + ch) * n_mma + row) * 16) = r.pp[ch];
+                            *reinterpret_cast<uint4*>(dst + ch * (NMMA * 16)) =
+                                in_range ? r.pp[ch] : make_uint4(0u, 0u, 0u, 0u);
                 }
                 s_ksign[b * 256 + row] = r.sign;
                 s_kexp[b * 256 + row] = (signed char)r.ep;
@@ -434,11 +460,11 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                     const int hi = __reduce_max_sync(FULL, in_range ? r.ep : -0x7fffffff);
                     if ((tid & 31) == 0) { atomicMin(&s_kmin[b], lo); atomicMax(&s_kmax[b], hi); }
                 }
-                if (write_kop && row < OL.kb_rows) {
+                if (write_kop && row < kb_rows) {
+                    unsigned char* dst = k_op + ((size_t)(4 * b) * kb_rows + row) * 16;
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch)
-                        if (ch < nchunk)
-                            *reinterpret_cast<uint4*>(k_op + k_op_offset(OL, row, 4 * b + ch)) = r.op[ch];
+                        if (ch < nchunk) *reinterpret_cast<uint4*>(dst + (size_t)ch * kb_rows * 16) = r.op[ch];
                 }
                 if (CODES && write_k && in_range) {
                     const int64_t krow = (int64_t)head * Nk + row;
@@ -446,43 +472,44 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                     uint32_t* dst = reinterpret_cast<uint32_t*>(p.k_codes + krow * hd + 32 * b);
 #pragma unroll
                     for (int v = 0; v < 8; ++v)
-                        if (4 * v < nd) dst[v] = r.cw[v];
+                        if (4 * v < (full ? 32 : tail)) dst[v] = r.cw[v];
                 }
             } else {
-                const int rt = row - tile * K1C_T;                  // row within the tile
+                const int rt = rl + (q_second ? K1C_ROWS : 0);      // row within the tile
+                unsigned char* dst = s_qop + ((size_t)(4 * b) * K1C_T + rt) * 16;
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch)
-                    if (ch < nchunk)
-                        *reinterpret_cast<uint4*>(s_qop + ((size_t)(4 * b + ch) * K1C_T + rt) * 16) = r.pp[ch];
+                    if (ch < nchunk) *reinterpret_cast<uint4*>(dst + ch * (K1C_T * 16)) = r.pp[ch];
                 s_qsign[b * K1C_T + rt] = r.sign;
                 s_qexp[b * K1C_T + rt] = (signed char)r.ep;
                 if (q_op) {
+                    unsigned char* gdst = q_op + (size_t)tile * OL.q_tile_bytes + ((size_t)(4 * b) * K1C_T + rt) * 16;
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch)
-                        if (ch < nchunk)
-                            *reinterpret_cast<uint4*>(q_op + q_op_offset(OL, row, 4 * b + ch)) = r.op[ch];
+                        if (ch < nchunk) *reinterpret_cast<uint4*>(gdst + ch * (K1C_T * 16)) = r.op[ch];
                 }
-                if (CODES && p.q_codes && in_range) {
+                if (CODES && write_q && in_range) {
                     const int64_t qrow = (int64_t)head * Nq + row;
                     p.q_exps[qrow * nb + b] = (int8_t)r.e;
-                    uint32_t* dst = reinterpret_cast<uint32_t*>(p.q_codes + qrow * hd + 32 * b);
+                    uint32_t* dst2 = reinterpret_cast<uint32_t*>(p.q_codes + qrow * hd + 32 * b);
 #pragma unroll
                     for (int v = 0; v < 8; ++v)
-                        if (4 * v < nd) dst[v] = r.cw[v];
+                        if (4 * v < (full ? 32 : tail)) dst2[v] = r.cw[v];
                 }
             }
         }
         fence_proxy_async_smem();                                   // operand stores -> visible to the MMA
         __syncthreads();                                            // slot consumed; operands complete
-        if (tid == 0 && c + ring < nchunks) issue(c + ring);
-        if (is_k || (qc & 1) == 0) continue;
+        if (tid == 0 && c + ring < nchunks) issue(c + ring, slot_i);
+        if (++slot_i == ring) { slot_i = 0; slot_par ^= 1u; }
+        if (!q_second) continue;
 
         // =============== a full query tile is quantized: score, select, emit
         if (tid == 0) {
             tcgen05_fence_after_sync();
             for (int ks = 0; ks < (L.hdp >> 4); ++ks) {
                 const uint64_t da = umma_smem_desc(smem_u32(s_qop + (size_t)(2 * ks) * K1C_T * 16), K1C_T * 16, 128);
-                const uint64_t db = umma_smem_desc(smem_u32(s_kop + (size_t)(2 * ks) * n_mma * 16), n_mma * 16, 128);
+                const uint64_t db = umma_smem_desc(smem_u32(s_kop + (size_t)(2 * ks) * NMMA * 16), NMMA * 16, 128);
                 umma_bf16_ss(tmem, da, db, idesc, ks > 0);
             }
             umma_commit(bar_mma);
@@ -521,13 +548,15 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
         if (!fast) M = 0;
         const int moff = ((int)M + 1) & ~1;
         const float scl = fast ? exp2i(-g - 1) : 0.f;
-        const float cadd = 8388608.0f + (float)((moff >> 1) + 1 + (int)K1_KEY_BIAS);
+        const uint32_t key0 = (uint32_t)((moff >> 1) + 1) + K1_KEY_BIAS;    // key of a score of exactly 0
+        const float cadd = 8388608.0f + (float)key0;
 
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1u;
         tcgen05_fence_after_sync();
 
-        // ---- scores -> fp16-pattern keys in registers: word 16w + t = keys (32w + t, 32w + 16 + t)
+        // ---- scores -> fp16-pattern keys in registers: word 16w + t = keys (32w + t, 32w + 16 + t).
+        // Padding columns (key index >= Nk) score exactly 0 -> key0; they are discounted below.
         uint32_t kw[NC * 16];
 #pragma unroll
         for (int w = 0; w < NC; ++w) {
@@ -538,12 +567,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
             for (int t = 0; t < 16; ++t) {
                 const uint32_t lo = __float_as_uint(fmaf(__uint_as_float(r[t]), scl, cadd));
                 const uint32_t hi = __float_as_uint(fmaf(__uint_as_float(r[t + 16]), scl, cadd));
-                uint32_t word = __byte_perm(lo, hi, 0x5410);
-                if (32 * w + 32 > Nk) {                             // padding keys -> 0 (below every candidate)
-                    if (32 * w + t >= Nk) word &= 0xffff0000u;
-                    if (32 * w + 16 + t >= Nk) word &= 0x0000ffffu;
-                }
-                kw[16 * w + t] = word;
+                kw[16 * w + t] = __byte_perm(lo, hi, 0x5410);
             }
         }
         // every thread has its row parameters and its keys in registers: TMEM and the Q-side shared
@@ -555,12 +579,14 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
         int wbits = 32 - __clz(moff + 1);
         wbits = __reduce_max_sync(FULL, wbits);
         uint32_t Tv = 0u;
+#pragma unroll 1
         for (int bit = wbits - 1; bit >= 0; --bit) {
-            const uint32_t cand = Tv | (1u << bit);
-            if (count_ge_regs<NC * 16>(kw, cand + K1_KEY_BIAS) >= kk) Tv = cand;
+            const uint32_t cand = (Tv | (1u << bit)) + K1_KEY_BIAS;
+            const int cnt = count_ge_regs<NC * 16>(kw, cand) - (key0 >= cand ? npad : 0);
+            if (cnt >= kk) Tv |= 1u << bit;
         }
         const uint32_t T = Tv + K1_KEY_BIAS;
-        const int ngt = count_ge_regs<NC * 16>(kw, T + 1u);
+        const int ngt = count_ge_regs<NC * 16>(kw, T + 1u) - (key0 > T ? npad : 0);
 
         // ---- emit the row bitmask (ties: ascending key index)
         {
@@ -576,6 +602,10 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                     gt |= __hgt2_mask(kv, t2) & (0x00010001u << t);
                     eq |= __heq2_mask(kv, t2) & (0x00010001u << t);
                 }
+                const int nv = Nk - 32 * w;                         // valid key columns in this chunk
+                const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : (1u << nv) - 1u);
+                gt &= vm;
+                eq &= vm;
                 const int cnt = __popc(eq);
                 uint32_t take = eq;
                 if (cnt > rem) take = keep_lowest_bits_fast(eq, rem);
