@@ -71,7 +71,7 @@ __host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring) {
     L.off_qsign = o; o += (size_t)4 * K1C_T * 4;
     L.off_qexp = o;  o += (size_t)4 * K1C_T;
     L.off_misc = o;  o += 128;
-    L.total = o + 1024;                                   // slack to align the base to 1024 bytes
+    L.total = o;
     return L;
 }
 
@@ -326,8 +326,8 @@ __device__ __noinline__ void predict_row_generic_tc(uint32_t* __restrict__ mask_
 template <int NC, bool CODES>
 __global__ void __launch_bounds__(K1C_T, 2)
 k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring) {
-    extern __shared__ unsigned char smem_raw_tc[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw_tc + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem_k1c[];     // 1024-byte aligned: SWIZZLE_128B boxes
+    unsigned char* const smem = smem_k1c;
     constexpr int NMMA = 32 * NC;
     const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
     const K1cSmem L = k1c_smem_layout(hd, NC, ring);
