@@ -10,6 +10,7 @@
 #include "mxprune_predict.cuh"
 #include "mxprune_attend.cuh"
 #include "mxprune_predict_tc.cuh"
+#include "mxprune_predict_long_tc.cuh"
 
 using namespace mxp;
 
@@ -652,6 +653,95 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
     return 0;
 }
 
+// ---- K1-long-TC (Nk > 256): operand pre-pass + tensor-core radix select + CUDA-core clean-up ----
+struct LongWsLayout { size_t q_pp, k_pp, q_ep, head_meta, flags, total; };
+inline LongWsLayout long_ws_layout(int B, int H, int Nq, int Nk, int hd) {
+    LongWsLayout W{};
+    if (Nk <= K1_MAX_KEYS || hd < 32 || (hd & 7)) return W;
+    const OpsLayout O = ops_layout(Nq, Nk, hd);
+    const size_t bh = (size_t)B * H;
+    size_t o = 0;
+    W.q_pp = o;      o += align256(bh * O.q_head_bytes);
+    W.k_pp = o;      o += align256(bh * O.k_head_bytes);
+    W.q_ep = o;      o += align256(bh * (size_t)O.q_tiles * KL_T * 4);
+    W.head_meta = o; o += align256(bh * 32);
+    W.flags = o;     o += align256(bh * (size_t)Nq);
+    W.total = o;
+    return W;
+}
+
+// returns 1 if the shape is outside this path's domain or no workspace was supplied
+static int try_predict_topk_long_tc(const PredParams& p, cudaStream_t st, int* rc_out) {
+    if (g_predict_path != 0) return 1;
+    const LongWsLayout W = long_ws_layout(p.B, p.H, p.Nq, p.Nk, p.hd);
+    if (W.total == 0 || !p.long_ws || p.long_ws_bytes < W.total || ((uintptr_t)p.long_ws & 255)) return 1;
+    const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
+    const KLSmem L = kl_smem_layout(O);
+    if (L.total > 232448 / 2 - 1024) return 1;
+    unsigned char* w = (unsigned char*)p.long_ws;
+    const int heads = p.B * p.H, nb = (p.hd + 31) / 32;
+    uint32_t* head_meta = (uint32_t*)(w + W.head_meta);
+    uint8_t* flags = (uint8_t*)(w + W.flags);
+    if (cudaMemsetAsync(head_meta, 0xFF, (size_t)heads * 32, st) != cudaSuccess) {
+        *rc_out = fail(MXP_E_CUDA, "cudaMemsetAsync failed");
+        return 0;
+    }
+    const bool codes = p.q_codes != nullptr || p.k_codes != nullptr;
+    for (int which = 1; which >= 0; --which) {          // keys first (head_meta), then queries
+        QuantOpsParams qp{};
+        qp.x = which ? p.k : p.q;
+        qp.H = p.H; qp.N = which ? p.Nk : p.Nq;
+        qp.rows_pad = which ? O.nblk * O.kb_rows : O.q_tiles * KL_T;
+        qp.hd = p.hd; qp.bf16 = p.bf16; qp.flush = p.flush; qp.which = which; qp.Nq = p.Nq; qp.Nk = p.Nk;
+        qp.op = which ? p.k_op : p.q_op;
+        qp.pp = w + (which ? W.k_pp : W.q_pp);
+        qp.ep = which ? nullptr : (int8_t*)(w + W.q_ep);
+        qp.head_meta = which ? head_meta : nullptr;
+        qp.codes = which ? p.k_codes : p.q_codes;
+        qp.exps = which ? p.k_exps : p.q_exps;
+        const int ntask = qp.rows_pad * nb;
+        int gy = (ntask + 255) / 256;
+        const int want = (148 * 8 + heads - 1) / heads;
+        if (gy > want) gy = want;
+        dim3 grid((unsigned)heads, (unsigned)gy);
+        if (codes) k_quantize_ops<true><<<grid, 256, 0, st>>>(qp);
+        else k_quantize_ops<false><<<grid, 256, 0, st>>>(qp);
+        if ((*rc_out = check_launch("k_quantize_ops"))) return 0;
+    }
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(k_select_long_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) { *rc_out = fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 0; }
+            attr_set = true;
+        }
+        LongSelParams sp{};
+        sp.q_pp = w + W.q_pp; sp.k_pp = w + W.k_pp; sp.q_ep = (const int8_t*)(w + W.q_ep);
+        sp.head_meta = head_meta; sp.flags = flags; sp.mask = p.mask; sp.idx = p.idx;
+        sp.H = p.H; sp.Nq = p.Nq; sp.Nk = p.Nk; sp.hd = p.hd; sp.top_k = p.top_k;
+        int splits = (148 * 2 + heads - 1) / heads;
+        if (splits > O.q_tiles) splits = O.q_tiles;
+        if (splits < 1) splits = 1;
+        size_t dyn = L.total;
+        const size_t floor_bytes = (size_t)232448 / 3 + 1024;       // two CTAs per SM: 2 x 256 TMEM columns
+        if (dyn < floor_bytes) dyn = floor_bytes;
+        k_select_long_tc<<<dim3((unsigned)heads, (unsigned)splits), KL_T, dyn, st>>>(sp);
+        if ((*rc_out = check_launch("k_select_long_tc"))) return 0;
+    }
+    // rows outside the integer-key window: the CUDA-core kernel, restricted to the flagged rows
+    PredParams pf = p;
+    pf.q_op = nullptr; pf.k_op = nullptr;
+    pf.q_codes = nullptr; pf.q_exps = nullptr; pf.k_codes = nullptr; pf.k_exps = nullptr;
+    pf.row_filter = flags;
+    switch (nb) {
+        case 1: *rc_out = launch_predict_topk_long<1>(pf, st); break;
+        case 2: *rc_out = launch_predict_topk_long<2>(pf, st); break;
+        case 3: *rc_out = launch_predict_topk_long<3>(pf, st); break;
+        default: *rc_out = launch_predict_topk_long<4>(pf, st); break;
+    }
+    return 0;
+}
+
 }  // namespace
 
 // ======================================================================================
@@ -749,11 +839,14 @@ int mxp_predict_scores(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
     return check_launch("k_predict_scores");
 }
 
-size_t mxp_predict_topk_workspace_bytes(int, int, int, int, int) { return 0; }
+size_t mxp_predict_topk_workspace_bytes(int B, int H, int Nq, int Nk, int hd) {
+    return long_ws_layout(B, H, Nq, Nk, hd).total;
+}
 
 static int predict_topk_impl(const PredParams& p, cudaStream_t st) {
     int rc = MXP_OK;
     if (try_predict_topk_tc(p, st, &rc) == 0) return rc;
+    if (try_predict_topk_long_tc(p, st, &rc) == 0) return rc;
     switch ((p.hd + 31) / 32) {
         case 1: return launch_predict_topk_nb<1>(p, st);
         case 2: return launch_predict_topk_nb<2>(p, st);
@@ -766,7 +859,7 @@ int mxp_predict_topk(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
                      const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
                      int B, int H, int Nq, int Nk, int hd, int top_k, int bfloat_bits, int flush,
                      uint32_t* mask, int32_t* idx, int8_t* q_codes, int8_t* q_exps,
-                     int8_t* k_codes, int8_t* k_exps, void*, size_t, void* stream) {
+                     int8_t* k_codes, int8_t* k_exps, void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
     int rc = check_shape(B, H, Nq, Nk, hd, bfloat_bits);
     if (rc) return rc;
@@ -783,6 +876,7 @@ int mxp_predict_topk(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
     p.bf16 = bfloat_bits == 16; p.flush = flush != 0;
     p.mask = mask; p.idx = idx;
     p.q_codes = q_codes; p.q_exps = q_exps; p.k_codes = k_codes; p.k_exps = k_exps;
+    p.long_ws = workspace; p.long_ws_bytes = workspace_bytes;
     return predict_topk_impl(p, (cudaStream_t)stream);
 }
 
@@ -853,7 +947,7 @@ size_t mxp_pruned_attention_workspace_bytes(int B, int H, int Nq, int Nk, int hd
     const OpsBytes ob = ops_bytes(B, H, Nq, Nk, hd);
     const size_t ops = align256(ob.q) + align256(ob.k) + align256(ob.v);
     const size_t codes = align256(bh * Nq * hd) + align256(bh * Nq * nb) + align256(bh * Nk * hd) + align256(bh * Nk * nb);
-    return (ops > codes ? ops : codes) + align256(bh * Nq * nw * 4);
+    return (ops > codes ? ops : codes) + align256(bh * Nq * nw * 4) + long_ws_layout(B, H, Nq, Nk, hd).total;
 }
 
 int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
@@ -879,7 +973,8 @@ int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_s
     const size_t bh = (size_t)B * H, nb = (size_t)(hd + 31) / 32, nw = (size_t)(Nk + 31) / 32;
     const OpsBytes ob = ops_bytes(B, H, Nq, Nk, hd);
     unsigned char* w = (unsigned char*)workspace;
-    uint32_t* mask = mask_out ? mask_out : (uint32_t*)(w + need - align256(bh * Nq * nw * 4));
+    const size_t long_bytes = long_ws_layout(B, H, Nq, Nk, hd).total;
+    uint32_t* mask = mask_out ? mask_out : (uint32_t*)(w + need - long_bytes - align256(bh * Nq * nw * 4));
     cudaStream_t st = (cudaStream_t)stream;
 
     PredParams pp{};
@@ -888,6 +983,8 @@ int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_s
     pp.B = B; pp.H = H; pp.Nq = Nq; pp.Nk = Nk; pp.hd = hd; pp.top_k = top_k;
     pp.bf16 = bfloat_bits == 16; pp.flush = flush != 0;
     pp.mask = mask; pp.idx = nullptr;
+    pp.long_ws = long_bytes ? w + need - long_bytes : nullptr;
+    pp.long_ws_bytes = long_bytes;
     if (tc) {
         unsigned char* q_op = w; w += align256(ob.q);
         unsigned char* k_op = w; w += align256(ob.k);

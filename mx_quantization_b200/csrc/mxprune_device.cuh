@@ -31,6 +31,9 @@ struct PredParams {
     int8_t *q_codes, *q_exps, *k_codes, *k_exps;
     unsigned char *q_op, *k_op;   // MMA-ready bf16 operands for the exact-attention kernel (may be null)
     float* scores;   // dense debug output (k_predict_scores only)
+    const uint8_t* row_filter;   // k_predict_topk_long only: [heads][Nq], process rows with a non-zero flag (null = all)
+    void* long_ws;               // host side: workspace of the long-sequence tensor-core path (may be null)
+    size_t long_ws_bytes;
 };
 
 // 2^e as fp32 for e in [-149, 127] (subnormal below -126).

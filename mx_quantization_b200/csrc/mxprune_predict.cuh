@@ -555,6 +555,11 @@ k_predict_topk_long(const PredParams p) {
     unsigned char* k_op = p.k_op ? p.k_op + (size_t)head * OL.k_head_bytes : nullptr;
     unsigned char* q_op = p.q_op ? p.q_op + (size_t)head * OL.q_head_bytes : nullptr;
 
+    if (p.row_filter) {              // only flagged rows are processed; nothing to do -> skip the K staging too
+        int any = 0;
+        for (int i = blockIdx.y * K1T + tid; i < Nq; i += K1T * gridDim.y) any |= p.row_filter[(int64_t)head * Nq + i];
+        if (!__syncthreads_or(any)) return;
+    }
     if (tid < 4) { s_kmin[tid] = 0x7fffffff; s_kmax[tid] = -0x7fffffff; }
     __syncthreads();
     {
@@ -609,7 +614,7 @@ k_predict_topk_long(const PredParams p) {
 
     for (int i0 = blockIdx.y * K1T; i0 < Nq; i0 += K1T * gridDim.y) {
         const int i = i0 + tid;
-        const bool valid = i < Nq;
+        const bool valid = i < Nq && (!p.row_filter || p.row_filter[(int64_t)head * Nq + i]);
         const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
         RowQ<NB> rq;
         if (q_op) {

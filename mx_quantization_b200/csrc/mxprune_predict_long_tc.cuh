@@ -1,0 +1,333 @@
+// K1-long-TC: the fused quantizer + exponent-sign predictor + exact top-k for Nk > 256 (the
+// long-sequence sweep, config C5) with the scores on the tensor cores.
+//
+// A row's keys no longer fit in registers or shared memory, so the selection is a most-significant-
+// digit radix select that RE-SCORES the row in every pass - which is what the tensor core makes
+// cheap: a pass streams the head's predictor operand Kp (bf16 +-2^e, MMA-ready, written once per
+// head by k_quantize_ops) through shared memory in blocks of 128 keys, one tcgen05.mma per block
+// into one of two TMEM buffers, and the 128 row threads read their scores back with tcgen05.ld.
+//   pass 0..L-1  per-thread histogram (64 bins x 6 bits per level, [bin][thread] in shared memory:
+//                conflict-free, no atomics) of the current digit among keys whose higher digits
+//                equal the prefix found so far; scan from the top bin for the digit of the k-th key
+//   last pass    emit: keys > T kept, keys == T kept in ascending index until top_k
+// Keys are the exact 15-bit integers of the short kernels (score * 2^(-g-1) + offset, read from the
+// low mantissa bits of one FFMA).  Rows outside that window are flagged and left to the CUDA-core
+// kernel (k_predict_topk_long, row-filtered), which handles any exponents.
+// Pipeline per pass: TMA bulk copy of block j+2 and the MMA of block j+1 run while the threads
+// histogram block j.
+#pragma once
+#include "mxprune_predict_tc.cuh"
+
+namespace mxp {
+
+constexpr int KL_T = 128;             // threads == query rows per tile
+constexpr int KL_BINS = 64;
+
+// ------------------------------------------------------------------------------------------
+// k_quantize_ops: fp32 (B,H,N,hd) view -> MMA-ready bf16 operands in HBM, one thread per MX block.
+//   op   exact operand  c * 2^(e-6)   (for the attention kernel; may be null)
+//   pp   predictor operand +-2^e
+//   ep   predictor exponents  int8 [heads][rows_pad][4]        (query side: row parameters)
+//   head_meta u32 [heads][8]: min over keys of (ep_b + 200) and of (200 - ep_b)   (key side)
+// which = 0: query layout (tiles of 128 rows), 1: key layout (blocks of OL.kb_rows rows).
+// ------------------------------------------------------------------------------------------
+struct QuantOpsParams {
+    View x;
+    int H, N, rows_pad, hd, bf16, flush, which, Nq, Nk;
+    unsigned char *op, *pp;
+    int8_t* ep;
+    uint32_t* head_meta;
+    int8_t *codes, *exps;
+};
+
+template <bool CODES>
+__global__ void __launch_bounds__(256)
+k_quantize_ops(const QuantOpsParams p) {
+    const OpsLayout OL = ops_layout(p.Nq, p.Nk, p.hd);
+    const int head = blockIdx.x, bb = head / p.H, hh = head - bb * p.H;
+    const int hd = p.hd, nb = (hd + 31) >> 5, nfull = hd >> 5, tail = hd & 31;
+    const int kch = OL.hdp >> 3, tail_chunks = kch - 4 * nfull;
+    const float* xb = p.x.p + bb * p.x.sB + hh * p.x.sH;
+    const size_t head_bytes = p.which == 0 ? OL.q_head_bytes : OL.k_head_bytes;
+    unsigned char* op = p.op ? p.op + (size_t)head * head_bytes : nullptr;
+    unsigned char* pp = p.pp + (size_t)head * head_bytes;
+    const int ntask = p.rows_pad * nb;                  // rows_pad is a multiple of 128: b is warp-uniform
+    for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < ntask; t += gridDim.y * blockDim.x) {
+        const int b = t / p.rows_pad, row = t - b * p.rows_pad;
+        const bool in_range = row < p.N;
+        const bool full = b < nfull;
+        const int nd = full ? 32 : tail;
+        uint32_t xv[32];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in_range && 4 * s < nd) f = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)row * p.x.sN + 32 * b) + s);
+            xv[4 * s] = __float_as_uint(f.x); xv[4 * s + 1] = __float_as_uint(f.y);
+            xv[4 * s + 2] = __float_as_uint(f.z); xv[4 * s + 3] = __float_as_uint(f.w);
+        }
+        BlockQ r;
+        quantize_block_thread<CODES>(xv, nd, p.bf16, p.flush, r);
+        const int nchunk = full ? 4 : tail_chunks;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            if (ch < nchunk) {
+                const size_t off = p.which == 0 ? q_op_offset(OL, row, 4 * b + ch) : k_op_offset(OL, row, 4 * b + ch);
+                *reinterpret_cast<uint4*>(pp + off) = in_range ? r.pp[ch] : make_uint4(0u, 0u, 0u, 0u);
+                if (op) *reinterpret_cast<uint4*>(op + off) = r.op[ch];
+            }
+        }
+        if (p.ep) p.ep[((size_t)head * p.rows_pad + row) * 4 + b] = (int8_t)r.ep;
+        if (p.head_meta) {
+            const uint32_t lo = __reduce_min_sync(FULL, in_range ? (uint32_t)(r.ep + 200) : 0xffffffffu);
+            const uint32_t hi = __reduce_min_sync(FULL, in_range ? (uint32_t)(200 - r.ep) : 0xffffffffu);
+            if ((threadIdx.x & 31) == 0) {
+                atomicMin(&p.head_meta[head * 8 + b], lo);
+                atomicMin(&p.head_meta[head * 8 + 4 + b], hi);
+            }
+        }
+        if (CODES && p.codes && in_range) {
+            const int64_t grow = (int64_t)head * p.N + row;
+            p.exps[grow * nb + b] = (int8_t)r.e;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(p.codes + grow * hd + 32 * b);
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+                if (4 * v < nd) dst[v] = r.cw[v];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_select_long_tc
+// ------------------------------------------------------------------------------------------
+struct LongSelParams {
+    const unsigned char *q_pp, *k_pp;
+    const int8_t* q_ep;             // [heads][q_rows_pad][4]
+    const uint32_t* head_meta;      // [heads][8]
+    uint8_t* flags;                 // [heads][Nq]: 1 = row left to the CUDA-core kernel
+    uint32_t* mask;
+    int32_t* idx;
+    int H, Nq, Nk, hd, top_k;
+};
+
+struct KLSmem {
+    size_t off_k, off_hist, off_misc, total;
+};
+__host__ __device__ inline KLSmem kl_smem_layout(const OpsLayout& O) {
+    KLSmem L;
+    size_t o = O.q_tile_bytes;
+    L.off_k = o;    o += 2 * O.k_blk_bytes;
+    L.off_hist = o; o += (size_t)KL_BINS * KL_T * 2;
+    L.off_misc = o; o += 128;
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(KL_T, 2)
+k_select_long_tc(const LongSelParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_kl[];
+    unsigned char* const smem = smem_kl;
+    const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
+    const OpsLayout O = ops_layout(Nq, Nk, hd);
+    const KLSmem L = kl_smem_layout(O);
+    const int nb = (hd + 31) >> 5, nblk = O.nblk;
+    unsigned char* sQ = smem;
+    unsigned char* sK = smem + L.off_k;
+    unsigned short* s_hist = reinterpret_cast<unsigned short*>(smem + L.off_hist);
+    uint64_t* bar_k = reinterpret_cast<uint64_t*>(smem + L.off_misc);       // [2]
+    uint64_t* bar_mma = bar_k + 2;                                          // [2]
+    uint64_t* bar_q = bar_k + 4;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_k + 5);
+    int* s_nlev = reinterpret_cast<int*>(s_tmem + 1);
+
+    const int head = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const unsigned char* q_pp = p.q_pp + (size_t)head * O.q_head_bytes;
+    const unsigned char* k_pp = p.k_pp + (size_t)head * O.k_head_bytes;
+    const int q_rows_pad = O.q_tiles * KL_T;
+
+    if (tid == 0) {
+        mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1);
+        mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1);
+        mbar_init(bar_q, 1);
+    }
+    if (warp == 0) tmem_alloc(s_tmem, 256u);
+    tcgen05_fence_before_sync();
+    __syncthreads();
+    tcgen05_fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t my_lane = (uint32_t)(warp * 32) << 16;
+    const uint32_t idesc = umma_idesc_bf16_f32(128, 128);
+    uint32_t ph_k[2] = {0u, 0u}, ph_m[2] = {0u, 0u}, ph_q = 0u;
+
+    int kmin[4], spread[4];
+    bool wide = false;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        kmin[b] = b < nb ? (int)p.head_meta[head * 8 + b] - 200 : 0;
+        const int kmax = b < nb ? 200 - (int)p.head_meta[head * 8 + 4 + b] : 0;
+        spread[b] = kmax - kmin[b];
+        wide |= spread[b] > K1_MAX_SPREAD;
+    }
+    const int NW = (Nk + 31) >> 5;
+    const int npad = nblk * 128 - Nk;                   // zero rows of Kp: score exactly 0
+    unsigned short* my_hist = s_hist + tid;             // bin b at my_hist[b * KL_T]
+
+    for (int tile = blockIdx.y; tile < O.q_tiles; tile += gridDim.y) {
+        const int i = tile * KL_T + tid;
+        const bool valid = i < Nq;
+        const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
+        if (tid == 0) {
+            *s_nlev = 0;
+            mbar_expect_tx(bar_q, (uint32_t)O.q_tile_bytes);
+            tma_bulk_g2s(sQ, q_pp + (size_t)tile * O.q_tile_bytes, (uint32_t)O.q_tile_bytes, bar_q);
+        }
+        // ---- integer-key parameters of this thread's row (same window rules as the short kernels)
+        int epq[4];
+        {
+            const int8_t* e4 = p.q_ep + ((size_t)head * q_rows_pad + i) * 4;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) epq[b] = b < nb ? (int)e4[b] : 0;
+        }
+        int g = 0x7fffffff;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (b < nb) g = min(g, epq[b] + kmin[b]);
+        bool fast = valid && !wide && g >= -100 && g <= 80;
+        long long M = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (b < nb) {
+                int sh = epq[b] + kmin[b] - g;
+                if (sh > K1_MAX_SPREAD) { fast = false; sh = K1_MAX_SPREAD; }
+                const int nbw = min(32, hd - 32 * b);
+                M += (long long)nbw << (sh + min(spread[b], K1_MAX_SPREAD));
+            }
+        }
+        if (M > 32766) fast = false;
+        if (valid) p.flags[row] = fast ? 0 : 1;
+        if (!fast) M = 0;
+        const int moff = ((int)M + 1) & ~1;
+        const float scl = fast ? exp2i(-g - 1) : 0.f;
+        const uint32_t key0 = (uint32_t)((moff >> 1) + 1);          // key of a score of exactly 0
+        const float cadd = 8388608.0f + (float)key0;
+        const int wtot = 32 - __clz(moff + 1);                      // key width in bits
+        const int my_lev = (wtot + 5) / 6;
+        __syncthreads();                                            // *s_nlev = 0 visible
+        {
+            const int wl = __reduce_max_sync(FULL, fast ? my_lev : 0);
+            if ((tid & 31) == 0) atomicMax(s_nlev, wl);
+        }
+        __syncthreads();
+        const int nlev = *s_nlev;
+        mbar_wait(bar_q, ph_q);
+        ph_q ^= 1u;
+
+        uint32_t prefix = 0u;
+        int krem = kk;
+        // passes 0..nlev-1: histogram levels; pass nlev: emit (skipped when no row of the tile is fast)
+        const int npass = nlev > 0 ? nlev + 1 : 0;
+        for (int pass = 0; pass < npass; ++pass) {
+            const bool emit = pass == nlev;
+            const int lo = 6 * (my_lev - 1 - pass);                 // < 0: this row already has its full key
+            const bool counting = !emit && fast && lo >= 0;
+            if (!emit) {
+                for (int b = 0; b < KL_BINS; ++b) my_hist[b * KL_T] = 0;
+            }
+            int rem = krem, pos = 0;                                // emit state
+            const uint32_t T = prefix;
+            if (tid == 0) {
+                const int pre = min(2, nblk);
+                for (int b = 0; b < pre; ++b) {
+                    mbar_expect_tx(&bar_k[b], (uint32_t)O.k_blk_bytes);
+                    tma_bulk_g2s(sK + (size_t)b * O.k_blk_bytes, k_pp + (size_t)b * O.k_blk_bytes, (uint32_t)O.k_blk_bytes, &bar_k[b]);
+                }
+            }
+            for (int it = 0; it <= nblk; ++it) {
+                if (it < nblk) {
+                    const int s = it & 1;
+                    mbar_wait(&bar_k[s], ph_k[s]);
+                    ph_k[s] ^= 1u;
+                    if (tid == 0) {
+                        tcgen05_fence_after_sync();
+                        const unsigned char* kb = sK + (size_t)s * O.k_blk_bytes;
+                        for (int ks = 0; ks < (O.hdp >> 4); ++ks) {
+                            const uint64_t da = umma_smem_desc(smem_u32(sQ + (size_t)(2 * ks) * KL_T * 16), KL_T * 16, 128);
+                            const uint64_t db = umma_smem_desc(smem_u32(kb + (size_t)(2 * ks) * 128 * 16), 128 * 16, 128);
+                            umma_bf16_ss(tmem + (uint32_t)(s * 128), da, db, idesc, ks > 0);
+                        }
+                        umma_commit(&bar_mma[s]);
+                    }
+                }
+                if (it > 0) {
+                    const int j = it - 1, s = j & 1;
+                    mbar_wait(&bar_mma[s], ph_m[s]);
+                    ph_m[s] ^= 1u;
+                    tcgen05_fence_after_sync();
+                    if (tid == 0 && j + 2 < nblk) {                 // MMA j has finished reading sK[s]
+                        mbar_expect_tx(&bar_k[s], (uint32_t)O.k_blk_bytes);
+                        tma_bulk_g2s(sK + (size_t)s * O.k_blk_bytes, k_pp + (size_t)(j + 2) * O.k_blk_bytes,
+                                     (uint32_t)O.k_blk_bytes, &bar_k[s]);
+                    }
+                    const uint32_t tbase = tmem + my_lane + (uint32_t)(s * 128);
+#pragma unroll 1
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tbase + q4 * 32, r);
+                        tmem_ld_wait();
+                        if (!emit) {
+                            if (counting) {
+#pragma unroll
+                                for (int c = 0; c < 32; ++c) {
+                                    const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0xffffu;
+                                    if ((u >> (lo + 6)) == prefix) my_hist[((u >> lo) & 63u) * KL_T] += 1;
+                                }
+                            }
+                        } else {
+                            const int j0 = j * 128 + q4 * 32;       // first key of this word
+                            uint32_t word = 0u;
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0xffffu;
+                                bool keep = u > T;
+                                if (u == T && rem > 0 && j0 + c < Nk) { keep = true; --rem; }
+                                word |= (keep ? 1u : 0u) << c;
+                            }
+                            const int nv = Nk - j0;
+                            if (nv < 32) word &= nv <= 0 ? 0u : (1u << nv) - 1u;
+                            if (valid && fast && (j0 >> 5) < NW) {
+                                p.mask[row * NW + (j0 >> 5)] = word;
+                                if (p.idx) {
+                                    uint32_t w2 = word;
+                                    while (w2) {
+                                        const int bpos = __ffs(w2) - 1;
+                                        w2 &= w2 - 1u;
+                                        p.idx[row * kk + pos++] = j0 + bpos;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tcgen05_fence_before_sync();
+                __syncthreads();                                    // TMEM buffer of block j is free again
+            }
+            if (counting) {
+                // the npad zero rows of Kp all scored key0: discount them
+                if (npad > 0 && (key0 >> (lo + 6)) == prefix) my_hist[((key0 >> lo) & 63u) * KL_T] -= (unsigned short)npad;
+                int cum = 0, bin = KL_BINS - 1;
+                for (; bin > 0; --bin) {
+                    const int h = (int)my_hist[bin * KL_T];
+                    if (cum + h >= krem) break;
+                    cum += h;
+                }
+                krem -= cum;
+                prefix = (prefix << 6) | (uint32_t)bin;
+            }
+        }
+    }
+    tcgen05_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256u);
+}
+
+}  // namespace mxp

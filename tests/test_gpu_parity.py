@@ -241,12 +241,25 @@ def test_exact_attention_long_sequences(mxq, B, H, N, hd, bfloat):
     (1, 2, 300, 64, "edges", 32, 0.5),
     (1, 1, 1024, 72, "randn", 16, 0.5),
     (1, 1, 2048, 72, "randn", 32, 0.1),
+    (2, 2, 700, 96, "randn", 32, 0.3),
+    (1, 3, 333, 64, "randn", 16, 0.2),
 ])
-def test_long_sequence_end_to_end(mxq, B, H, N, hd, kind, bfloat, kfrac):
-    """Config C5 territory (Nk > 256): long-sequence predictor + key-blocked exact attention."""
+@pytest.mark.parametrize("pred_path", ["tcgen05", "cuda_core"])
+def test_long_sequence_end_to_end(mxq, B, H, N, hd, kind, bfloat, kfrac, pred_path):
+    """Config C5 territory (Nk > 256): long-sequence predictor (tensor-core radix select with the
+    CUDA-core kernel for rows outside the integer window / CUDA-core kernel alone) + key-blocked
+    exact attention."""
     top_k = max(1, int(kfrac * N))
     q, k, v = make_qkv(B, H, N, hd, seed=8, kind=kind)
     specs = mx_specs(bfloat, False)
+    mxq.set_predict_path(pred_path)
+    try:
+        _long_e2e(mxq, q, k, v, specs, top_k, N, bfloat)
+    finally:
+        mxq.set_predict_path("tcgen05")
+
+
+def _long_e2e(mxq, q, k, v, specs, top_k, N, bfloat):
     out, mask = mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), specs, top_k, return_mask=True)
     ref = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, integer_scores=True)
     want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], N), N)
