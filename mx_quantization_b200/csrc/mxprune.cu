@@ -503,7 +503,9 @@ int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     const K2Smem L = k2_smem_layout(O);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attend_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_attend_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_attend_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
@@ -520,7 +522,8 @@ int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     size_t dyn = L.total;
     const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
     if (dyn < floor_bytes) dyn = floor_bytes;
-    k_attend_umma<<<grid, K2T, dyn, st>>>(p);
+    if (O.single) k_attend_umma<true><<<grid, K2T, dyn, st>>>(p);
+    else k_attend_umma<false><<<grid, K2T, dyn, st>>>(p);
     return check_launch("k_attend_umma");
 }
 
@@ -719,7 +722,9 @@ static int try_predict_topk_long_tc(const PredParams& p, cudaStream_t st, int* r
         sp.q_pp = w + W.q_pp; sp.k_pp = w + W.k_pp; sp.q_ep = (const int8_t*)(w + W.q_ep);
         sp.head_meta = head_meta; sp.flags = flags; sp.mask = p.mask; sp.idx = p.idx;
         sp.H = p.H; sp.Nq = p.Nq; sp.Nk = p.Nk; sp.hd = p.hd; sp.top_k = p.top_k;
-        int splits = (148 * 2 + heads - 1) / heads;
+        // a tile is ~Nk/256 times the work of a short-kernel tile: spread tiles over enough CTAs for
+        // >= 8 waves of the 296 resident CTAs (a CTA's fixed cost is small next to one tile)
+        int splits = (148 * 2 * 8 + heads - 1) / heads;
         if (splits > O.q_tiles) splits = O.q_tiles;
         if (splits < 1) splits = 1;
         size_t dyn = L.total;

@@ -119,6 +119,7 @@ __device__ __forceinline__ uint32_t pick8(const uint32_t (&r)[8], int w) {
     return (w & 4) ? cd : ab;
 }
 
+template <bool SINGLE>      // SINGLE: Nk <= 256, one key block; otherwise key blocks of 128 with online softmax
 __global__ void __launch_bounds__(K2T)
 k_attend_umma(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -128,7 +129,7 @@ k_attend_umma(const AttnParams p) {
     const OpsLayout O = ops_layout(Nq, Nk, hd);
     const K2Smem L = k2_smem_layout(O);
     const int hdp = O.hdp, NW = O.nw, kbr = O.kb_rows;
-    const bool single = O.single;
+    constexpr bool single = SINGLE;
     unsigned char* sK = smem;
     unsigned char* sV = smem + L.off_v;
     unsigned char* sP = smem + L.off_p;
@@ -317,19 +318,44 @@ k_attend_umma(const AttnParams p) {
                     const uint32_t mx = max(max(mx4[0], mx4[1]), max(mx4[2], mx4[3]));
                     const int e = mx_shared_exp(mx);
                     const bool dead = (flush && e <= -127) || mx == 0u;
-                    const float s1 = exp2i(-e), wgt = exp2i(e - 6);
+                    unsigned char* pdst = sP + ((size_t)((w - g0) * 4) * K2T + tid) * 16;
+                    if (single && (dead || e >= -120)) {
+                        // p >= 0.  code = min(127, floor(p * 2^(6-e) + 0.5)) without F2I / I2F: the
+                        // add rounded toward -inf against 2^23 + 0x4300 leaves the bf16 pattern of
+                        // 128 + code in the low 16 bits; (128 + code) * w - 128 * w = code * w exactly.
+                        // A dead window (no kept key / flushed) runs the same code with scale 0: code 0.
+                        const int ec = max(e, -120);
+                        const float s1 = dead ? 0.f : exp2i(6 - ec);
+                        const __nv_bfloat162 w2 = u32_as_bf2(bf16_pow2_bits(ec - 6) * 0x00010001u);
+                        const __nv_bfloat162 nw2 = u32_as_bf2((bf16_pow2_bits(ec + 1) | 0x8000u) * 0x00010001u);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float f[8];
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t ow[4];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const float rr = __uint_as_float(r[q * 8 + t]) * s1 * 64.0f + 0.5f;
-                            const int c = dead ? 0 : min(__float2int_rz(rr), 127);
-                            f[t] = (float)c * wgt;
+                            for (int h = 0; h < 4; ++h) {
+                                const float v0 = fminf(fmaf(__uint_as_float(r[q * 8 + 2 * h]), s1, 0.5f), 127.0f);
+                                const float v1 = fminf(fmaf(__uint_as_float(r[q * 8 + 2 * h + 1]), s1, 0.5f), 127.0f);
+                                const uint32_t v2 = __byte_perm(__float_as_uint(__fadd_rd(v0, 8405760.0f)),
+                                                                __float_as_uint(__fadd_rd(v1, 8405760.0f)), 0x5410);
+                                ow[h] = bf2_as_u32(__hfma2(u32_as_bf2(v2), w2, nw2));
+                            }
+                            *reinterpret_cast<uint4*>(pdst + (size_t)q * K2T * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                         }
-                        *reinterpret_cast<uint4*>(sP + ((size_t)((w - g0) * 4 + q) * K2T + tid) * 16) =
-                            make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]),
-                                       pack_bf16_trunc(f[4], f[5]), pack_bf16_trunc(f[6], f[7]));
+                    } else {
+                        const float s1 = exp2i(-e), wgt = exp2i(e - 6);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float f[8];
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                const float rr = __uint_as_float(r[q * 8 + t]) * s1 * 64.0f + 0.5f;
+                                const int c = dead ? 0 : min(__float2int_rz(rr), 127);
+                                f[t] = (float)c * wgt;
+                            }
+                            *reinterpret_cast<uint4*>(pdst + (size_t)q * K2T * 16) =
+                                make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]),
+                                           pack_bf16_trunc(f[4], f[5]), pack_bf16_trunc(f[6], f[7]));
+                        }
                     }
                 }
                 fence_proxy_async_smem();

@@ -203,14 +203,15 @@ k_select_long_tc(const LongSelParams p) {
                 M += (long long)nbw << (sh + min(spread[b], K1_MAX_SPREAD));
             }
         }
-        if (M > 32766) fast = false;
+        if (M > K1_MAX_M) fast = false;
         if (valid) p.flags[row] = fast ? 0 : 1;
         if (!fast) M = 0;
         const int moff = ((int)M + 1) & ~1;
         const float scl = fast ? exp2i(-g - 1) : 0.f;
-        const uint32_t key0 = (uint32_t)((moff >> 1) + 1);          // key of a score of exactly 0
+        // keys carry the fp16 bias of the short kernel (two keys per word compare with one HSET2)
+        const uint32_t key0 = (uint32_t)((moff >> 1) + 1) + K1_KEY_BIAS;    // key of a score of exactly 0
         const float cadd = 8388608.0f + (float)key0;
-        const int wtot = 32 - __clz(moff + 1);                      // key width in bits
+        const int wtot = 32 - __clz(moff + 1 + (int)K1_KEY_BIAS);   // key width in bits
         const int my_lev = (wtot + 5) / 6;
         __syncthreads();                                            // *s_nlev = 0 visible
         {
@@ -276,24 +277,42 @@ k_select_long_tc(const LongSelParams p) {
                         tmem_ld_wait();
                         if (!emit) {
                             if (counting) {
+                                if (pass == 0) {                    // no prefix yet: every key counts
 #pragma unroll
-                                for (int c = 0; c < 32; ++c) {
-                                    const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0xffffu;
-                                    if ((u >> (lo + 6)) == prefix) my_hist[((u >> lo) & 63u) * KL_T] += 1;
+                                    for (int c = 0; c < 32; ++c) {
+                                        const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd));
+                                        my_hist[((u >> lo) & 63u) * KL_T] += 1;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < 32; ++c) {
+                                        const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0xffffu;
+                                        if ((u >> (lo + 6)) == prefix) my_hist[((u >> lo) & 63u) * KL_T] += 1;
+                                    }
                                 }
                             }
                         } else {
+                            // two keys per word (c, c + 16), compared as fp16 bit patterns
                             const int j0 = j * 128 + q4 * 32;       // first key of this word
-                            uint32_t word = 0u;
+                            const __half2 t2 = u32_as_h2(T * 0x00010001u);
+                            uint32_t gt = 0u, eq = 0u;
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) {
-                                const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0xffffu;
-                                bool keep = u > T;
-                                if (u == T && rem > 0 && j0 + c < Nk) { keep = true; --rem; }
-                                word |= (keep ? 1u : 0u) << c;
+                            for (int c = 0; c < 16; ++c) {
+                                const uint32_t fl = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd));
+                                const uint32_t fh = __float_as_uint(fmaf(__uint_as_float(r[c + 16]), scl, cadd));
+                                const __half2 kv = u32_as_h2(__byte_perm(fl, fh, 0x5410));
+                                gt |= __hgt2_mask(kv, t2) & (0x00010001u << c);
+                                eq |= __heq2_mask(kv, t2) & (0x00010001u << c);
                             }
                             const int nv = Nk - j0;
-                            if (nv < 32) word &= nv <= 0 ? 0u : (1u << nv) - 1u;
+                            const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : (1u << nv) - 1u);
+                            gt &= vm;
+                            eq &= vm;
+                            const int cnt = __popc(eq);
+                            uint32_t take = eq;
+                            if (cnt > rem) take = keep_lowest_bits_fast(eq, rem);
+                            rem -= min(cnt, rem);
+                            const uint32_t word = gt | take;
                             if (valid && fast && (j0 >> 5) < NW) {
                                 p.mask[row * NW + (j0 >> 5)] = word;
                                 if (p.idx) {

@@ -98,17 +98,6 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
-__device__ __forceinline__ __nv_bfloat162 u32_as_bf2(uint32_t x) {
-    return *reinterpret_cast<const __nv_bfloat162*>(&x);
-}
-__device__ __forceinline__ uint32_t bf2_as_u32(__nv_bfloat162 x) {
-    return *reinterpret_cast<const uint32_t*>(&x);
-}
-// bf16 bit pattern of 2^e, e in [-133, 127]
-__device__ __forceinline__ uint32_t bf16_pow2_bits(int e) {
-    return e >= -126 ? (uint32_t)(e + 127) << 7 : 0x40u >> (-127 - e);
-}
-
 // Results of quantizing one MX block (<= 32 elements) held by one thread.
 struct BlockQ {
     int e, ep;              // A2 exponent, predictor exponent

@@ -2,6 +2,7 @@
 // the exact-attention kernel.  One CTA, cta_group::1, operands in shared memory (K-major, no
 // swizzle: 8 x 16-byte core matrices), fp32 accumulators in tensor memory.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -14,6 +15,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // two fp32 values that are exactly representable in bf16 -> packed bf16x2 (lo = first)
 __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
     return (__float_as_uint(lo) >> 16) | (__float_as_uint(hi) & 0xffff0000u);
+}
+
+__device__ __forceinline__ __nv_bfloat162 u32_as_bf2(uint32_t x) {
+    return *reinterpret_cast<const __nv_bfloat162*>(&x);
+}
+__device__ __forceinline__ uint32_t bf2_as_u32(__nv_bfloat162 x) {
+    return *reinterpret_cast<const uint32_t*>(&x);
+}
+// bf16 bit pattern of 2^e, e in [-133, 127]
+__device__ __forceinline__ uint32_t bf16_pow2_bits(int e) {
+    return e >= -126 ? (uint32_t)(e + 127) << 7 : 0x40u >> (-127 - e);
 }
 
 // ---- mbarrier
