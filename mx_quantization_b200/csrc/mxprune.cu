@@ -503,9 +503,10 @@ int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     const K2Smem L = k2_smem_layout(O);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attend_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_attend_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_attend_umma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_umma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_umma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_umma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
@@ -522,8 +523,13 @@ int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     size_t dyn = L.total;
     const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
     if (dyn < floor_bytes) dyn = floor_bytes;
-    if (O.single) k_attend_umma<true><<<grid, K2T, dyn, st>>>(p);
-    else k_attend_umma<false><<<grid, K2T, dyn, st>>>(p);
+    if (O.single) {
+        if (p.bf16) k_attend_umma<true, true><<<grid, K2T, dyn, st>>>(p);
+        else k_attend_umma<true, false><<<grid, K2T, dyn, st>>>(p);
+    } else {
+        if (p.bf16) k_attend_umma<false, true><<<grid, K2T, dyn, st>>>(p);
+        else k_attend_umma<false, false><<<grid, K2T, dyn, st>>>(p);
+    }
     return check_launch("k_attend_umma");
 }
 
@@ -611,7 +617,7 @@ static int launch_predict_topk_tc_one(const PredParams& p, const K1cMaps& maps, 
         if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    k_predict_topk_tc<NC, CODES><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring);
+    k_predict_topk_tc<NC, CODES><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
     return check_launch("k_predict_topk_tc");
 }
 
@@ -623,15 +629,19 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
     K1cMaps maps;
     if (!make_view_maps(p.q, p.B, p.H, p.Nq, p.hd, &maps.q_main, &maps.q_tail)) return 1;
     if (!make_view_maps(p.k, p.B, p.H, p.Nk, p.hd, &maps.k_main, &maps.k_tail)) return 1;
-    // ring depth: as many 64-row slots as fit with two CTAs per SM
+    // step = 64 G rows (G = 2 when a 64-row box gives fewer than 256 block tasks); ring depth: as many
+    // slots as fit with two CTAs per SM
     const size_t per_cta2 = 232448 / 2 - 1024, per_cta1 = 232448 - 1024;
     const int nc = p.Nk <= 32 ? 1 : p.Nk <= 64 ? 2 : p.Nk <= 128 ? 4 : p.Nk <= 224 ? 7 : 8;
+    const int nb = (p.hd + 31) / 32;
+    int G = nb <= 2 ? 2 : 1;
+    if (k1c_smem_layout(p.hd, nc, 2, G).total > per_cta2) G = 1;
     int ring = K1C_MAXR;
-    while (ring > 2 && k1c_smem_layout(p.hd, nc, ring).total > per_cta2) --ring;
-    K1cSmem L = k1c_smem_layout(p.hd, nc, ring);
+    while (ring > 2 && k1c_smem_layout(p.hd, nc, ring, G).total > per_cta2) --ring;
+    K1cSmem L = k1c_smem_layout(p.hd, nc, ring, G);
     if (L.total > per_cta1) return 1;
     const int heads = p.B * p.H;
-    const int tiles = (p.Nq + K1C_T - 1) / K1C_T;
+    const int tiles = (p.Nq + K1C_TILE - 1) / K1C_TILE;
     int splits = (148 * 2 + heads - 1) / heads;
     if (splits > tiles) splits = tiles;
     if (splits < 1) splits = 1;

@@ -119,7 +119,7 @@ __device__ __forceinline__ uint32_t pick8(const uint32_t (&r)[8], int w) {
     return (w & 4) ? cd : ab;
 }
 
-template <bool SINGLE>      // SINGLE: Nk <= 256, one key block; otherwise key blocks of 128 with online softmax
+template <bool SINGLE, bool BF16>   // SINGLE: Nk <= 256, one key block (else blocks of 128, online softmax); BF16: A1 rounding on
 __global__ void __launch_bounds__(K2T)
 k_attend_umma(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -135,7 +135,8 @@ k_attend_umma(const AttnParams p) {
     unsigned char* sP = smem + L.off_p;
     const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const bool bf16 = p.bf16, flush = p.flush;
+    constexpr bool bf16 = BF16;
+    const bool flush = p.flush;
     const unsigned char* q_op = p.q_op + (size_t)head * O.q_head_bytes;
     const unsigned char* k_op = p.k_op + (size_t)head * O.k_head_bytes;
     const unsigned char* v_op = p.v_op + (size_t)head * O.v_head_bytes;

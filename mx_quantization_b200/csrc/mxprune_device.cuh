@@ -42,8 +42,10 @@ __device__ __forceinline__ float exp2i(int e) {
 }
 
 // A1: round-half-away to bf16 on the fp32 bit pattern (sign preserved).
+// Adding half a bf16 ulp to the magnitude never carries into the sign bit for finite values and
+// infinities, so the sign needs no separate handling (NaN is outside the path's contract).
 __device__ __forceinline__ uint32_t bf16_half_away(uint32_t b) {
-    return (((b & 0x7fffffffu) + 0x8000u) & 0xffff0000u) | (b & 0x80000000u);
+    return (b + 0x8000u) & 0xffff0000u;
 }
 __device__ __forceinline__ float bf16_half_away(float x) {
     return __uint_as_float(bf16_half_away(__float_as_uint(x)));

@@ -9,23 +9,26 @@
 // CUDA cores costs ~12 instructions per (row, key); the tensor core makes it free and leaves the
 // CUDA cores to the quantizer and the selection.
 //
-// One CTA (128 threads) per (head, row split), two CTAs resident per SM.
+// One CTA (256 threads) per (head, row split), two CTAs resident per SM (16 warps; TMEM - 256
+// columns per CTA - and the register-resident keys are what bound the residency).
 //   stage    Q/K fp32 rows arrive by TMA (cp.async.bulk.tensor) straight from the strided
 //            (B,H,N,hd) view: tensor map dims {32 floats, N, hd/32, H, B}, box {32, 64 rows, hd/32},
 //            SWIZZLE_128B, out-of-range rows zero-filled; a second, unswizzled map covers hd % 32.
-//            A ring of 64-row slots keeps the next chunks in flight while the current one is used.
+//            A ring of slots (64 or 128 rows) keeps the next rows in flight while the current ones
+//            are quantized.
 //   quantize one thread per 32-wide MX block (conflict-free 128-bit reads of the swizzled slot):
 //            A1 + A2 -> exact bf16 operand c*2^(e-6) for the attention kernel (HBM, MMA-ready),
 //            predictor operand +-2^e (shared memory, MMA-ready), sign word + exponent (shared
 //            memory, for the generic path), optional int8 codes / exponents (HBM).
 //            No float<->int conversion instructions: floor() is an FADD.RM against 2^23 and the
 //            bf16 value comes from one packed HFMA2.BF16 on the (128 + c) bit patterns.
-//   score    S[128 x Nk] = Qp . Kp^T, hd/16 tcgen05.mma (M = 128, N = Nk rounded to 16), fp32 in TMEM
-//   keys     thread t owns query row t == TMEM lane t: score * 2^(-g-1) + offset is the same 15-bit
-//            integer key as the CUDA-core kernel (mxprune_predict.cuh), stored as an fp16 BIT
-//            PATTERN, two per register - the whole row lives in <= 128 registers
-//   select   bit-wise bisection for the top_k-th largest key: per step one HSET2.GE + one HADD2
-//            per two keys, no memory traffic
+//   score    S[128 x 32 NC] = Qp . Kp^T, hd/16 tcgen05.mma (M = 128), fp32 in TMEM
+//   keys     a warp owns 16 query rows (TMEM lanes); lanes l and l + 16 share row l and split its key
+//            columns in two halves - tcgen05.ld.16x32bx2 delivers exactly that.  score * 2^(-g-1) +
+//            offset is the same 15-bit integer key as the CUDA-core kernel (mxprune_predict.cuh),
+//            stored as an fp16 BIT PATTERN, two per register (<= 64 registers per thread)
+//   select   bit-wise bisection for the top_k-th largest key: per step one HSET2.GE + one HADD2 per
+//            two keys, no memory traffic; the two lanes of a row add their counts with one SHFL
 //   emit     keys > T kept, keys == T kept in ascending key index until top_k (stable-sort rule)
 // Rows outside the integer window (all-zero block, > 2^14 spread) take the same warp-cooperative
 // fp32 path as the CUDA-core kernel, from the sign words kept in shared memory.
@@ -38,19 +41,21 @@
 
 namespace mxp {
 
-constexpr int K1C_T = 128;            // threads per CTA == query rows per tile
-constexpr int K1C_ROWS = 64;          // rows per staged chunk
+constexpr int K1C_T = 256;            // threads per CTA: two per query row of the tile
+constexpr int K1C_TILE = 128;         // query rows per tile == TMEM lanes
+constexpr int K1C_ROWS = 64;          // rows per TMA box
 constexpr int K1C_MAXR = 4;           // ring slots
 
 struct K1cSmem {
-    int nfull, tail, nb, hdp, n_mma, tmem_cols, ring;
-    size_t slot_main, slot_bytes;
+    int nfull, tail, nb, hdp, n_mma, tmem_cols, ring, G;
+    size_t box_main, box_tail, slot_bytes;
     size_t off_kop, off_qop, off_ksign, off_kexp, off_qsign, off_qexp, off_misc, total;
 };
 
 // nc = number of 32-key chunks (the kernel's NC): the MMA covers 32 * nc key columns, rows past Nk
 // of the predictor operand are zero so that padding keys score exactly 0.
-__host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring) {
+// G = TMA boxes (of 64 rows) per ring slot == per quantize step.
+__host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring, int G) {
     K1cSmem L;
     L.nfull = hd >> 5;
     L.tail = hd & 31;
@@ -58,18 +63,20 @@ __host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring) {
     L.hdp = (hd + 15) & ~15;
     L.n_mma = 32 * nc;
     int c = 32;
-    while (c < L.n_mma) c <<= 1;
+    while (c < 64 * ((nc + 1) / 2)) c <<= 1;              // both lane halves read (nc + 1) / 2 chunks
     L.tmem_cols = c;
     L.ring = ring;
-    L.slot_main = (size_t)K1C_ROWS * L.nfull * 128;
-    L.slot_bytes = (L.slot_main + (size_t)K1C_ROWS * L.tail * 4 + 1023) & ~(size_t)1023;
+    L.G = G;
+    L.box_main = (size_t)K1C_ROWS * L.nfull * 128;
+    L.box_tail = (size_t)K1C_ROWS * L.tail * 4;
+    L.slot_bytes = (G * (L.box_main + L.box_tail) + 1023) & ~(size_t)1023;
     size_t o = L.slot_bytes * ring;
     L.off_kop = o;   o += (size_t)(L.hdp >> 3) * L.n_mma * 16;
-    L.off_qop = o;   o += (size_t)(L.hdp >> 3) * K1C_T * 16;
-    L.off_ksign = o; o += (size_t)4 * 256 * 4;
-    L.off_kexp = o;  o += (size_t)4 * 256;
-    L.off_qsign = o; o += (size_t)4 * K1C_T * 4;
-    L.off_qexp = o;  o += (size_t)4 * K1C_T;
+    L.off_qop = o;   o += (size_t)(L.hdp >> 3) * K1C_TILE * 16;
+    L.off_ksign = o; o += (size_t)L.nb * 256 * 4;
+    L.off_kexp = o;  o += (size_t)L.nb * 256;
+    L.off_qsign = o; o += (size_t)L.nb * K1C_TILE * 4;
+    L.off_qexp = o;  o += (size_t)L.nb * K1C_TILE;
     L.off_misc = o;  o += 128;
     L.total = o;
     return L;
@@ -311,15 +318,27 @@ __device__ __noinline__ void predict_row_generic_tc(uint32_t* __restrict__ mask_
     if (lane < NW) mask_out[row * NW + lane] = myword;
 }
 
+// 16 TMEM lanes x 16 consecutive columns, twice: lanes 0-15 of the warp get columns [c, c+16) of
+// TMEM lanes L..L+15, lanes 16-31 get columns [c + SPLIT, c + SPLIT + 16) of the same TMEM lanes.
+template <int SPLIT>
+__device__ __forceinline__ void tmem_ld_16x32bx2_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x32bx2.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16], %17;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr), "n"(SPLIT));
+}
+
 // NC = number of 32-key TMEM chunks a row's keys occupy (Nk <= 32 * NC); the MMA's N is 32 * NC.
 template <int NC, bool CODES>
 __global__ void __launch_bounds__(K1C_T, 2)
-k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring) {
+k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring, const int G) {
     extern __shared__ __align__(1024) unsigned char smem_k1c[];     // 1024-byte aligned: SWIZZLE_128B boxes
     unsigned char* const smem = smem_k1c;
     constexpr int NMMA = 32 * NC;
+    constexpr int NCH = (NC + 1) / 2;                               // key chunks per thread
     const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
-    const K1cSmem L = k1c_smem_layout(hd, NC, ring);
+    const K1cSmem L = k1c_smem_layout(hd, NC, ring, G);
     const int nfull = L.nfull, tail = L.tail, nb = L.nb;
     const int kch = L.hdp >> 3;                                     // 16-byte chunks per operand row
     const int tail_chunks = kch - 4 * nfull;                        // operand chunks the partial block owns
@@ -336,7 +355,12 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     uint64_t* bar_mma = bar_full + K1C_MAXR;
 
     const int head = blockIdx.x, bb = head / p.H, hh = head - bb * p.H;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // selection mapping: warp w owns TMEM lanes [32 (w & 3) + 16 (w >> 2), +16); lanes l and l + 16
+    // of the warp share query row l of those and take the lower / upper half of its key columns
+    const int lane_base = 32 * (warp & 3) + 16 * (warp >> 2);
+    const int rr = lane_base + (lane & 15);                         // row of the tile
+    const int part = lane >> 4;
     const bool bf16 = p.bf16, flush = p.flush;
     const bool write_k = CODES && p.k_codes != nullptr && blockIdx.y == 0;
     const bool write_q = CODES && p.q_codes != nullptr;
@@ -346,27 +370,33 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     unsigned char* q_op = p.q_op ? p.q_op + (size_t)head * OL.q_head_bytes : nullptr;
     const int kb_rows = OL.kb_rows;
 
-    // ---- chunk schedule of this CTA: K chunks first, then two Q chunks per tile
-    const int nkc = (Nk + K1C_ROWS - 1) / K1C_ROWS;
-    const int tiles = (Nq + K1C_T - 1) / K1C_T;
+    // ---- step schedule of this CTA: CR = 64 G rows per step; K steps first, then the Q tiles
+    const int CR = K1C_ROWS * G, cr_shift = G == 2 ? 7 : 6;
+    const int nks = (NMMA + CR - 1) / CR;                           // every MMA row of the K operand is written
+    const int qsteps = K1C_TILE / CR;                               // steps per query tile (2 or 1)
+    const int tiles = (Nq + K1C_TILE - 1) / K1C_TILE;
     const int my_tiles = (tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
-    const int nchunks = nkc + 2 * my_tiles;
-    const uint32_t slot_tx = (uint32_t)(L.slot_main + (size_t)K1C_ROWS * tail * 4);
-    const uint32_t slot_bytes = (uint32_t)L.slot_bytes, slot_main = (uint32_t)L.slot_main;
+    const int nsteps = nks + qsteps * my_tiles;
+    const uint32_t box_main = (uint32_t)L.box_main, box_tail = (uint32_t)L.box_tail;
+    const uint32_t slot_tx = (uint32_t)G * (box_main + box_tail);
+    const uint32_t slot_bytes = (uint32_t)L.slot_bytes;
+    const uint32_t tail_base = (uint32_t)G * box_main;
 
     auto issue = [&](int c, int slot_i) {                           // one thread
         unsigned char* slot = smem + (size_t)slot_i * slot_bytes;
         uint64_t* bar = &bar_full[slot_i];
-        const bool is_k = c < nkc;
+        const bool is_k = c < nks;
         int row0;
-        if (is_k) row0 = c * K1C_ROWS;
+        if (is_k) row0 = c * CR;
         else {
-            const int qc = c - nkc;
-            row0 = ((int)blockIdx.y + (qc >> 1) * (int)gridDim.y) * K1C_T + (qc & 1) * K1C_ROWS;
+            const int qc = c - nks;
+            row0 = ((int)blockIdx.y + (qc / qsteps) * (int)gridDim.y) * K1C_TILE + (qc % qsteps) * CR;
         }
         mbar_expect_tx(bar, slot_tx);
-        if (nfull) tma_load_5d(slot, is_k ? &maps.k_main : &maps.q_main, 0, row0, 0, hh, bb, bar);
-        if (tail) tma_load_4d(slot + slot_main, is_k ? &maps.k_tail : &maps.q_tail, 0, row0, hh, bb, bar);
+        for (int g = 0; g < G; ++g) {
+            if (nfull) tma_load_5d(slot + g * box_main, is_k ? &maps.k_main : &maps.q_main, 0, row0 + g * K1C_ROWS, 0, hh, bb, bar);
+            if (tail) tma_load_4d(slot + tail_base + g * box_tail, is_k ? &maps.k_tail : &maps.q_tail, 0, row0 + g * K1C_ROWS, hh, bb, bar);
+        }
     };
 
     if (tid == 0) {
@@ -381,48 +411,53 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     __syncthreads();
     tcgen05_fence_after_sync();
     const uint32_t tmem = *s_tmem;
-    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t my_tmem = tmem + ((uint32_t)lane_base << 16);
     if (tid == 0) {
-        const int pre = min(ring, nchunks);
+        const int pre = min(ring, nsteps);
         for (int c = 0; c < pre; ++c) issue(c, c);
     }
     const uint32_t idesc = umma_idesc_bf16_f32(128, NMMA);
     const int NW = (Nk + 31) >> 5;
-    const int npad = NMMA - Nk;                                     // padding key columns (score exactly 0)
+    // padding key columns (index >= Nk, score exactly 0) among THIS thread's chunks [part NCH, part NCH + NCH)
+    const int my_cols_end = min(NC, (part + 1) * NCH) * 32, my_cols_beg = part * NCH * 32;
+    const int my_pad = max(0, my_cols_end - max(Nk, my_cols_beg));
     uint32_t ph_mma = 0;
     int slot_i = 0;
     uint32_t slot_par = 0;
-    int tile = (int)blockIdx.y - (int)gridDim.y;                    // advanced at the first chunk of every tile
+    int tile = (int)blockIdx.y - (int)gridDim.y;                    // advanced at the first step of every tile
+    int qstep = qsteps - 1;                                         // step within the tile
 
-    for (int c = 0; c < nchunks; ++c) {
-        const bool is_k = c < nkc;
-        const bool q_second = !is_k && ((c - nkc) & 1);
-        if (!is_k && !q_second) tile += (int)gridDim.y;
-        const int row0 = is_k ? c * K1C_ROWS : tile * K1C_T + (q_second ? K1C_ROWS : 0);
+    for (int c = 0; c < nsteps; ++c) {
+        const bool is_k = c < nks;
+        if (!is_k) {
+            if (++qstep == qsteps) { qstep = 0; tile += (int)gridDim.y; }
+        }
+        const int row0 = is_k ? c * CR : tile * K1C_TILE + qstep * CR;
         const int nrows = is_k ? Nk : Nq;
         const unsigned char* slot = smem + (size_t)slot_i * slot_bytes;
         mbar_wait(&bar_full[slot_i], slot_par);
 
-        // -------- quantize the chunk: one thread per MX block, block-major task order
+        // -------- quantize the step's rows: one thread per MX block, block-major task order
         // (consecutive lanes <-> consecutive rows of one block index: conflict-free reads of the
-        //  swizzled slot, conflict-free / coalesced operand stores)
-        const int ntask = K1C_ROWS * nb;
+        //  swizzled boxes, conflict-free / coalesced operand stores)
+        const int ntask = CR * nb;
         for (int t = tid; t < ntask; t += K1C_T) {
-            const int b = t >> 6, rl = t & 63;
+            const int b = t >> cr_shift, rl = t & (CR - 1);
+            const int g = rl >> 6, rl6 = rl & 63;
             const int row = row0 + rl;
             const bool in_range = row < nrows;
             const bool full = b < nfull;
             uint32_t xv[32];
             if (full) {
-                const unsigned char* src = slot + t * 128;
-                const int sw7 = (t & 7) << 4;
+                const unsigned char* src = slot + g * box_main + (b * 64 + rl6) * 128;
+                const int sw7 = (rl6 & 7) << 4;
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const uint4 v = *reinterpret_cast<const uint4*>(src + ((s << 4) ^ sw7));
                     xv[4 * s] = v.x; xv[4 * s + 1] = v.y; xv[4 * s + 2] = v.z; xv[4 * s + 3] = v.w;
                 }
             } else {
-                const unsigned char* src = slot + slot_main + rl * tail * 4;
+                const unsigned char* src = slot + tail_base + g * box_tail + rl6 * tail * 4;
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -435,7 +470,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
             const int nchunk = full ? 4 : tail_chunks;
             if (is_k) {
                 if (row < NMMA) {
-                    unsigned char* dst = s_kop + ((size_t)(4 * b) * NMMA + row) * 16;
+                    unsigned char* dst = s_kop + ((4 * b) * NMMA + row) * 16;
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch)
                         if (ch < nchunk)
@@ -444,10 +479,10 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                 }
                 s_ksign[b * 256 + row] = r.sign;
                 s_kexp[b * 256 + row] = (signed char)r.ep;
-                {   // b is warp-uniform (64 tasks per block index): one shared-memory atomic per warp
+                {   // b is warp-uniform (>= 64 tasks per block index): one shared-memory atomic per warp
                     const int lo = __reduce_min_sync(FULL, in_range ? r.ep : 0x7fffffff);
                     const int hi = __reduce_max_sync(FULL, in_range ? r.ep : -0x7fffffff);
-                    if ((tid & 31) == 0) { atomicMin(&s_kmin[b], lo); atomicMax(&s_kmax[b], hi); }
+                    if (lane == 0) { atomicMin(&s_kmin[b], lo); atomicMax(&s_kmax[b], hi); }
                 }
                 if (write_kop && row < kb_rows) {
                     unsigned char* dst = k_op + ((size_t)(4 * b) * kb_rows + row) * 16;
@@ -464,18 +499,18 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                         if (4 * v < (full ? 32 : tail)) dst[v] = r.cw[v];
                 }
             } else {
-                const int rt = rl + (q_second ? K1C_ROWS : 0);      // row within the tile
-                unsigned char* dst = s_qop + ((size_t)(4 * b) * K1C_T + rt) * 16;
+                const int rt = qstep * CR + rl;                     // row within the tile
+                unsigned char* dst = s_qop + ((4 * b) * K1C_TILE + rt) * 16;
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch)
-                    if (ch < nchunk) *reinterpret_cast<uint4*>(dst + ch * (K1C_T * 16)) = r.pp[ch];
-                s_qsign[b * K1C_T + rt] = r.sign;
-                s_qexp[b * K1C_T + rt] = (signed char)r.ep;
+                    if (ch < nchunk) *reinterpret_cast<uint4*>(dst + ch * (K1C_TILE * 16)) = r.pp[ch];
+                s_qsign[b * K1C_TILE + rt] = r.sign;
+                s_qexp[b * K1C_TILE + rt] = (signed char)r.ep;
                 if (q_op) {
-                    unsigned char* gdst = q_op + (size_t)tile * OL.q_tile_bytes + ((size_t)(4 * b) * K1C_T + rt) * 16;
+                    unsigned char* gdst = q_op + (size_t)tile * OL.q_tile_bytes + ((size_t)(4 * b) * K1C_TILE + rt) * 16;
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch)
-                        if (ch < nchunk) *reinterpret_cast<uint4*>(gdst + ch * (K1C_T * 16)) = r.op[ch];
+                        if (ch < nchunk) *reinterpret_cast<uint4*>(gdst + ch * (K1C_TILE * 16)) = r.op[ch];
                 }
                 if (CODES && write_q && in_range) {
                     const int64_t qrow = (int64_t)head * Nq + row;
@@ -489,22 +524,22 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
         }
         fence_proxy_async_smem();                                   // operand stores -> visible to the MMA
         __syncthreads();                                            // slot consumed; operands complete
-        if (tid == 0 && c + ring < nchunks) issue(c + ring, slot_i);
+        if (tid == 0 && c + ring < nsteps) issue(c + ring, slot_i);
         if (++slot_i == ring) { slot_i = 0; slot_par ^= 1u; }
-        if (!q_second) continue;
+        if (is_k || qstep != qsteps - 1) continue;
 
         // =============== a full query tile is quantized: score, select, emit
         if (tid == 0) {
             tcgen05_fence_after_sync();
             for (int ks = 0; ks < (L.hdp >> 4); ++ks) {
-                const uint64_t da = umma_smem_desc(smem_u32(s_qop + (size_t)(2 * ks) * K1C_T * 16), K1C_T * 16, 128);
+                const uint64_t da = umma_smem_desc(smem_u32(s_qop + (size_t)(2 * ks) * K1C_TILE * 16), K1C_TILE * 16, 128);
                 const uint64_t db = umma_smem_desc(smem_u32(s_kop + (size_t)(2 * ks) * NMMA * 16), NMMA * 16, 128);
                 umma_bf16_ss(tmem, da, db, idesc, ks > 0);
             }
             umma_commit(bar_mma);
         }
         // ---- integer-key parameters of this thread's row (same window rules as mxprune_predict.cuh)
-        const int i = tile * K1C_T + tid;
+        const int i = tile * K1C_TILE + rr;
         const bool valid = i < Nq;
         const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
         int kmin[4], spread[4], epq[4];
@@ -515,8 +550,8 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
             kmin[b] = b < nb ? s_kmin[b] : 0;
             spread[b] = b < nb ? s_kmax[b] - kmin[b] : 0;
             wide |= spread[b] > K1_MAX_SPREAD;
-            epq[b] = b < nb ? (int)s_qexp[b * K1C_T + tid] : 0;
-            sq[b] = b < nb ? s_qsign[b * K1C_T + tid] : 0u;
+            epq[b] = b < nb ? (int)s_qexp[b * K1C_TILE + rr] : 0;
+            sq[b] = b < nb ? s_qsign[b * K1C_TILE + rr] : 0u;
         }
         int g = 0x7fffffff;
 #pragma unroll
@@ -544,19 +579,26 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
         ph_mma ^= 1u;
         tcgen05_fence_after_sync();
 
-        // ---- scores -> fp16-pattern keys in registers: word 16w + t = keys (32w + t, 32w + 16 + t).
-        // Padding columns (key index >= Nk) score exactly 0 -> key0; they are discounted below.
-        uint32_t kw[NC * 16];
+        // ---- scores -> fp16-pattern keys in registers.  This thread's chunk w is key columns
+        // [32 (part NCH + w), +32); word 16w + t = keys (base + t, base + 16 + t).  Padding columns
+        // (key index >= Nk) score exactly 0 -> key0; they are discounted below.  A chunk past NC
+        // (odd NC, upper half) holds zeros, which no candidate reaches.
+        uint32_t kw[NCH * 16];
 #pragma unroll
-        for (int w = 0; w < NC; ++w) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(my_tmem + w * 32, r);
-            tmem_ld_wait();
+        for (int w = 0; w < NCH; ++w) {
+            const bool real = (w < NCH - 1) || (NC % 2 == 0) || part == 0;   // chunk index part * NCH + w < NC
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const uint32_t lo = __float_as_uint(fmaf(__uint_as_float(r[t]), scl, cadd));
-                const uint32_t hi = __float_as_uint(fmaf(__uint_as_float(r[t + 16]), scl, cadd));
-                kw[16 * w + t] = __byte_perm(lo, hi, 0x5410);
+            for (int h = 0; h < 2; ++h) {
+                uint32_t r[16];
+                tmem_ld_16x32bx2_x16<NCH * 32>(my_tmem + w * 32 + h * 16, r);
+                tmem_ld_wait();
+                // r[t] = key column 16h + t of the chunk: low halves come from h = 0, high halves from h = 1
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const uint32_t f = __float_as_uint(fmaf(__uint_as_float(r[t]), scl, cadd));
+                    if (h == 0) kw[16 * w + t] = f;
+                    else kw[16 * w + t] = real ? __byte_perm(kw[16 * w + t], f, 0x5410) : 0u;
+                }
             }
         }
         // every thread has its row parameters and its keys in registers: TMEM and the Q-side shared
@@ -564,26 +606,38 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
         tcgen05_fence_before_sync();
         __syncthreads();
 
-        // ---- select: T = top_k-th largest key (warp-uniform trip count)
+        // ---- select: T = top_k-th largest key; the row's two lanes add their counts
         int wbits = 32 - __clz(moff + 1);
         wbits = __reduce_max_sync(FULL, wbits);
         uint32_t Tv = 0u;
+        // keys >= T among this thread's columns / the partner's: every valid key is >= the smallest
+        // candidate, and each accepted candidate brings its own counts along
+        int nge_m = min(my_cols_end, max(Nk, my_cols_beg)) - my_cols_beg;
+        int nge_o = Nk - nge_m;
 #pragma unroll 1
         for (int bit = wbits - 1; bit >= 0; --bit) {
             const uint32_t cand = (Tv | (1u << bit)) + K1_KEY_BIAS;
-            const int cnt = count_ge_regs<NC * 16>(kw, cand) - (key0 >= cand ? npad : 0);
-            if (cnt >= kk) Tv |= 1u << bit;
+            const int mine = count_ge_regs<NCH * 16>(kw, cand) - (key0 >= cand ? my_pad : 0);
+            const int theirs = __shfl_xor_sync(FULL, mine, 16);
+            if (mine + theirs >= kk) { Tv |= 1u << bit; nge_m = mine; nge_o = theirs; }
         }
         const uint32_t T = Tv + K1_KEY_BIAS;
-        const int ngt = count_ge_regs<NC * 16>(kw, T + 1u) - (key0 > T ? npad : 0);
+        // keys > T among this thread's columns, and the partner's
+        const int ngt_m = count_ge_regs<NCH * 16>(kw, T + 1u) - (key0 > T ? my_pad : 0);
+        const int ngt_o = __shfl_xor_sync(FULL, ngt_m, 16);
 
-        // ---- emit the row bitmask (ties: ascending key index)
+        // ---- emit the row bitmask (ties: ascending key index; the lower lane owns the lower columns)
         {
-            int rem = kk - ngt, pos = 0;
+            const int rem_all = kk - (ngt_m + ngt_o);               // ties to keep in the whole row
+            const int ties0 = part == 0 ? nge_m - ngt_m : nge_o - ngt_o;
+            const int ngt0 = part == 0 ? ngt_m : ngt_o;
+            int rem = part == 0 ? rem_all : rem_all - min(rem_all, ties0);
+            int pos = part == 0 ? 0 : ngt0 + min(rem_all, ties0);   // kept keys below this thread's columns
             const __half2 t2 = u32_as_h2(T * 0x00010001u);
             const bool store = valid && fast;
 #pragma unroll
-            for (int w = 0; w < NC; ++w) {
+            for (int w = 0; w < NCH; ++w) {
+                const int gw = part * NCH + w;
                 uint32_t gt = 0u, eq = 0u;
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
@@ -591,7 +645,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                     gt |= __hgt2_mask(kv, t2) & (0x00010001u << t);
                     eq |= __heq2_mask(kv, t2) & (0x00010001u << t);
                 }
-                const int nv = Nk - 32 * w;                         // valid key columns in this chunk
+                const int nv = Nk - 32 * gw;                        // valid key columns in this chunk
                 const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : (1u << nv) - 1u);
                 gt &= vm;
                 eq &= vm;
@@ -600,22 +654,22 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                 if (cnt > rem) take = keep_lowest_bits_fast(eq, rem);
                 rem -= min(cnt, rem);
                 const uint32_t word = gt | take;
-                if (store && w < NW) {
-                    p.mask[row * NW + w] = word;
+                if (store && gw < NW) {
+                    p.mask[row * NW + gw] = word;
                     if (p.idx) {
                         uint32_t w2 = word;
                         while (w2) {
                             const int bpos = __ffs(w2) - 1;
                             w2 &= w2 - 1u;
-                            p.idx[row * kk + pos++] = w * 32 + bpos;
+                            p.idx[row * kk + pos++] = gw * 32 + bpos;
                         }
                     }
                 }
             }
         }
 
-        // ---- rows outside the integer-key window: warp-cooperative generic path
-        unsigned todo = __ballot_sync(FULL, valid && !fast);
+        // ---- rows outside the integer-key window: warp-cooperative generic path (16 rows per warp)
+        unsigned todo = __ballot_sync(FULL, valid && !fast) & 0xffffu;
         while (todo) {
             const int l = __ffs(todo) - 1;
             todo &= todo - 1u;
@@ -626,7 +680,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                 gsq[b] = __shfl_sync(FULL, sq[b], l);
                 gep[b] = __shfl_sync(FULL, epq[b], l);
             }
-            const int64_t grow = (int64_t)head * Nq + (tile * K1C_T + (tid & ~31) + l);
+            const int64_t grow = (int64_t)head * Nq + (tile * K1C_TILE + lane_base + l);
             predict_row_generic_tc(p.mask, p.idx, Nk, kk, hd, nb, grow, gsq, gep, s_ksign, s_kexp);
         }
     }
