@@ -503,8 +503,8 @@ int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     const K2Smem L = k2_smem_layout(O);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attend_umma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_umma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_attend_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_umma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_umma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -519,14 +519,15 @@ int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     // Never let more CTAs become resident on an SM than its 512 TMEM columns can serve: a CTA
     // whose tcgen05.alloc cannot be satisfied would sit blocked inside the allocator.  Residency is
     // bounded through the dynamic shared-memory request (227 KiB per SM).
-    const int max_ctas = 512 / L.tmem_cols;
+    const int tcols = O.single ? k2p_tmem_cols(O) : L.tmem_cols;
+    const int max_ctas = 512 / tcols;
     size_t dyn = L.total;
     const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
     if (dyn < floor_bytes) dyn = floor_bytes;
-    if (O.single) {
-        if (p.bf16) k_attend_umma<true, true><<<grid, K2T, dyn, st>>>(p);
-        else k_attend_umma<true, false><<<grid, K2T, dyn, st>>>(p);
-    } else {
+    if (O.single) {                 // one key block: two lanes per query row, 256 threads
+        if (p.bf16) k_attend_pair<true><<<grid, K2P_T, dyn, st>>>(p);
+        else k_attend_pair<false><<<grid, K2P_T, dyn, st>>>(p);
+    } else {                        // key blocks of 128 with online softmax, one thread per row
         if (p.bf16) k_attend_umma<false, true><<<grid, K2T, dyn, st>>>(p);
         else k_attend_umma<false, false><<<grid, K2T, dyn, st>>>(p);
     }

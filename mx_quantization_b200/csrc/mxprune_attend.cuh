@@ -411,6 +411,309 @@ k_attend_umma(const AttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// k_attend_pair: the single-key-block case (Nk <= 256) with TWO LANES PER QUERY ROW.
+// 256 threads per CTA, 16 warps per SM.  A warp owns 16 query rows (TMEM lanes); lanes l and l + 16
+// share row l.  Key windows (32 keys) are dealt in pairs: lane half h takes windows 4g + 2h and
+// 4g + 2h + 1 of every group g of four - tcgen05.ld/st.16x32bx2 with a column split of 64 reads and
+// writes exactly that.  Row maximum and row sum are combined with one SHFL each; every other step of
+// the epilogue is per window and needs no exchange.  The next window's tcgen05.ld is in flight
+// while the current one is processed.
+// ------------------------------------------------------------------------------------------
+constexpr int K2P_T = 256;
+
+__device__ __forceinline__ void tmem_ld_16x32bx2_s64_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x32bx2.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32], 64;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_16x32bx2_s64_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x32bx2.x32.b32 [%0], 64, {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+
+// TMEM columns the pair kernel allocates: the S tile plus whatever the 64-column split reads past it
+__host__ __device__ inline int k2p_tmem_cols(const OpsLayout& O) {
+    const int need = 128 * ((O.nw + 3) / 4);
+    int c = 32;
+    while (c < need || c < O.hdp) c <<= 1;
+    return c;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(K2P_T, 2)
+k_attend_pair(const AttnParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar_ld, bar_s, bar_o;
+    __shared__ uint32_t tmem_base_s;
+    constexpr bool bf16 = BF16;
+    const int Nk = p.Nk, Nq = p.Nq, hd = p.hd;
+    const OpsLayout O = ops_layout(Nq, Nk, hd);
+    const K2Smem L = k2_smem_layout(O);
+    const int hdp = O.hdp, NW = O.nw, kbr = O.kb_rows;
+    const int NG = (NW + 3) >> 2;                                   // groups of four windows
+    unsigned char* sK = smem;
+    unsigned char* sV = smem + L.off_v;
+    unsigned char* sP = smem + L.off_p;
+    const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lane_base = 32 * (warp & 3) + 16 * (warp >> 2);
+    const int rr = lane_base + (lane & 15);                         // row of the tile
+    const int part = lane >> 4;                                     // which window pair of each group
+    const bool flush = p.flush;
+    const unsigned char* q_op = p.q_op + (size_t)head * O.q_head_bytes;
+    const unsigned char* k_op = p.k_op + (size_t)head * O.k_head_bytes;
+    const unsigned char* v_op = p.v_op + (size_t)head * O.v_head_bytes;
+    const uint32_t tcols = (uint32_t)k2p_tmem_cols(O);
+
+    if (tid == 0) { mbar_init(&bar_ld, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1); }
+    if (warp == 0) tmem_alloc(&tmem_base_s, tcols);
+    tcgen05_fence_before_sync();
+    __syncthreads();
+    tcgen05_fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t my_tmem = tmem + ((uint32_t)lane_base << 16);
+    const uint32_t idesc_s = umma_idesc_bf16_f32(128, kbr);
+    const uint32_t idesc_o = umma_idesc_bf16_f32(128, hdp);
+    uint32_t ph_ld = 0, ph_s = 0, ph_o = 0;
+
+    if (tid == 0) {                                                 // the head's K and V operands stay resident
+        mbar_expect_tx(&bar_ld, (uint32_t)(O.k_blk_bytes + O.v_blk_bytes));
+        tma_bulk_g2s(sK, k_op, (uint32_t)O.k_blk_bytes, &bar_ld);
+        tma_bulk_g2s(sV, v_op, (uint32_t)O.v_blk_bytes, &bar_ld);
+    }
+    mbar_wait(&bar_ld, ph_ld);
+    ph_ld ^= 1u;
+
+    for (int tile = blockIdx.y; tile < O.q_tiles; tile += gridDim.y) {
+        const int i = tile * K2T + rr;
+        const bool valid = i < Nq;
+        const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
+        const uint32_t* mrow = p.mask + row * NW;
+
+        if (tid == 0) {                                             // Q tile (A operand) -> the P buffer region
+            mbar_expect_tx(&bar_ld, (uint32_t)O.q_tile_bytes);
+            tma_bulk_g2s(sP, q_op + (size_t)tile * O.q_tile_bytes, (uint32_t)O.q_tile_bytes, &bar_ld);
+        }
+        // this lane's windows: 4g + 2 part + j, g < 2, j < 2  ->  mask words mw[2g + j]
+        uint32_t mw[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int w = 4 * (t >> 1) + 2 * part + (t & 1);
+            mw[t] = (valid && w < NW) ? __ldg(mrow + w) : 0u;
+        }
+        mbar_wait(&bar_ld, ph_ld);
+        ph_ld ^= 1u;
+        if (tid == 0) {
+            tcgen05_fence_after_sync();
+            for (int ks = 0; ks < (hdp >> 4); ++ks) {
+                const uint64_t da = umma_smem_desc(smem_u32(sP + (size_t)(2 * ks) * K2T * 16), K2T * 16, 128);
+                const uint64_t db = umma_smem_desc(smem_u32(sK + (size_t)(2 * ks) * kbr * 16), kbr * 16, 128);
+                umma_bf16_ss(tmem, da, db, idesc_s, ks > 0);
+            }
+            umma_commit(&bar_s);
+        }
+        mbar_wait(&bar_s, ph_s);
+        ph_s ^= 1u;
+        tcgen05_fence_after_sync();
+        const int nwin = 2 * NG;                                    // window slots per lane (some may be empty)
+
+        // ---- pass A: row max of bf16?(s) * scale over the kept keys
+        float mb4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        {
+            uint32_t ra[32], rb[32];
+            tmem_ld_16x32bx2_s64_x32(my_tmem, ra);
+#pragma unroll 1
+            for (int t = 0; t < nwin; t += 2) {
+                tmem_ld_wait();
+                tmem_ld_16x32bx2_s64_x32(my_tmem + 128 * (t >> 1) + 32, rb);
+                {
+                    const uint32_t m0 = mw[t & 3];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        float s = __uint_as_float(ra[c]);
+                        if (bf16) s = bf16_half_away(s);
+                        const float tv = __fmul_rn(s, p.scale);
+                        mb4[c & 3] = fmaxf(mb4[c & 3], ((m0 >> c) & 1u) ? tv : -INFINITY);
+                    }
+                }
+                tmem_ld_wait();
+                if (t + 2 < nwin) tmem_ld_16x32bx2_s64_x32(my_tmem + 128 * ((t >> 1) + 1), ra);
+                {
+                    const uint32_t m1 = mw[(t + 1) & 3];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        float s = __uint_as_float(rb[c]);
+                        if (bf16) s = bf16_half_away(s);
+                        const float tv = __fmul_rn(s, p.scale);
+                        mb4[c & 3] = fmaxf(mb4[c & 3], ((m1 >> c) & 1u) ? tv : -INFINITY);
+                    }
+                }
+            }
+        }
+        float m = fmaxf(fmaxf(mb4[0], mb4[1]), fmaxf(mb4[2], mb4[3]));
+        m = fmaxf(m, __shfl_xor_sync(FULL, m, 16));
+        const float m_use = (m == -INFINITY) ? 0.f : m;             // no kept key
+
+        // ---- pass B: E = exp(t - m) on kept keys (0 where pruned), written back over S; row sum
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int t = 0; t < nwin; ++t) {
+            const uint32_t mwt = mw[t & 3];
+            const uint32_t col = 128 * (t >> 1) + 32 * (t & 1);
+            uint32_t r[32];
+            tmem_ld_16x32bx2_s64_x32(my_tmem + col, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                float s = __uint_as_float(r[c]);
+                if (bf16) s = bf16_half_away(s);
+                const float ex = exp_nonpos(__fsub_rn(__fmul_rn(s, p.scale), m_use));
+                const float ev = ((mwt >> c) & 1u) ? ex : 0.f;
+                sum4[c & 3] += ev;
+                r[c] = __float_as_uint(ev);
+            }
+            tmem_st_16x32bx2_s64_x32(my_tmem + col, r);
+        }
+        tmem_st_wait();
+        float l = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        l += __shfl_xor_sync(FULL, l, 16);
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+
+        // ---- pass C: P = E/sum -> A1 -> MXINT8 per window -> bf16 A operand; O += P_w . V_w per group
+        bool first_mma = true;
+        for (int g = 0; g < NG; ++g) {
+            if (g > 0) {                                            // previous group's MMAs have finished reading sP
+                mbar_wait(&bar_o, ph_o);
+                ph_o ^= 1u;
+            }
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+                const int wl = 2 * part + j;                        // window slot within the group
+                uint32_t r[32];
+                tmem_ld_16x32bx2_s64_x32(my_tmem + 128 * g + 32 * j, r);
+                tmem_ld_wait();
+                uint32_t mx4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    uint32_t pb = __float_as_uint(__uint_as_float(r[c]) * inv);
+                    if (bf16) pb = bf16_half_away(pb);
+                    r[c] = pb;
+                    mx4[c & 3] = max(mx4[c & 3], pb);               // p >= 0: bit patterns order like the values
+                }
+                const uint32_t mx = max(max(mx4[0], mx4[1]), max(mx4[2], mx4[3]));
+                const int e = mx_shared_exp(mx);
+                const bool dead = (flush && e <= -127) || mx == 0u;
+                unsigned char* pdst = sP + ((size_t)(wl * 4) * K2T + rr) * 16;
+                if (dead || e >= -120) {
+                    // code = min(127, floor(p * 2^(6-e) + 0.5)) without F2I / I2F (see K1); a dead
+                    // window (no kept key / flushed) runs the same code with scale 0: code 0
+                    const int ec = max(e, -120);
+                    const float s1 = dead ? 0.f : exp2i(6 - ec);
+                    const __nv_bfloat162 w2 = u32_as_bf2(bf16_pow2_bits(ec - 6) * 0x00010001u);
+                    const __nv_bfloat162 nw2 = u32_as_bf2((bf16_pow2_bits(ec + 1) | 0x8000u) * 0x00010001u);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float v0 = fminf(fmaf(__uint_as_float(r[q * 8 + 2 * h]), s1, 0.5f), 127.0f);
+                            const float v1 = fminf(fmaf(__uint_as_float(r[q * 8 + 2 * h + 1]), s1, 0.5f), 127.0f);
+                            const uint32_t v2 = __byte_perm(__float_as_uint(__fadd_rd(v0, 8405760.0f)),
+                                                            __float_as_uint(__fadd_rd(v1, 8405760.0f)), 0x5410);
+                            ow[h] = bf2_as_u32(__hfma2(u32_as_bf2(v2), w2, nw2));
+                        }
+                        *reinterpret_cast<uint4*>(pdst + (size_t)q * K2T * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    }
+                } else {
+                    const float s1 = exp2i(-e), wgt = exp2i(e - 6);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float f[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            const float rq = __uint_as_float(r[q * 8 + t]) * s1 * 64.0f + 0.5f;
+                            f[t] = (float)min(__float2int_rz(rq), 127) * wgt;
+                        }
+                        *reinterpret_cast<uint4*>(pdst + (size_t)q * K2T * 16) =
+                            make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]),
+                                       pack_bf16_trunc(f[4], f[5]), pack_bf16_trunc(f[6], f[7]));
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            tcgen05_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tcgen05_fence_after_sync();
+                for (int wl = 0; wl < 4; ++wl) {
+                    const int w = 4 * g + wl;
+                    if (w >= NW) break;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint64_t da = umma_smem_desc(smem_u32(sP + (size_t)(wl * 4 + 2 * h) * K2T * 16), K2T * 16, 128);
+                        const uint64_t db = umma_smem_desc(smem_u32(sV + (size_t)(w * 4 + 2 * h) * hdp * 16), hdp * 16, 128);
+                        umma_bf16_ss(tmem, da, db, idesc_o, !first_mma);
+                        first_mma = false;
+                    }
+                }
+                umma_commit(&bar_o);
+            }
+        }
+        mbar_wait(&bar_o, ph_o);
+        ph_o ^= 1u;
+        tcgen05_fence_after_sync();
+
+        // ---- O -> A1 -> global: warp w reads TMEM lanes of quarter w & 3, column half w >> 2
+        {
+            const int io = tile * K2T + 32 * (warp & 3) + lane;
+            const bool vo = io < Nq;
+            float* orow = p.out + bb * p.o_sB + hh * p.o_sH + (int64_t)(vo ? io : 0) * p.o_sN;
+            const int half_cols = hdp >> 1;                         // multiple of 8
+            const uint32_t ot = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+            for (int c0 = (warp >> 2) * half_cols; c0 < ((warp >> 2) + 1) * half_cols; c0 += 8) {
+                uint32_t r[8];
+                tmem_ld_32x32b_x8(ot + c0, r);
+                tmem_ld_wait();
+                if (vo) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (c0 + q * 4 < hd) {
+                            float4 o = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                                                   __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+                            if (bf16) {
+                                o.x = bf16_half_away(o.x); o.y = bf16_half_away(o.y);
+                                o.z = bf16_half_away(o.z); o.w = bf16_half_away(o.w);
+                            }
+                            *reinterpret_cast<float4*>(orow + c0 + q * 4) = o;
+                        }
+                    }
+                }
+            }
+        }
+        tcgen05_fence_before_sync();
+        __syncthreads();                        // every lane has read O before TMEM / sP are reused
+        tcgen05_fence_after_sync();
+    }
+    if (warp == 0) tmem_dealloc(tmem, tcols);
+}
+
+// ------------------------------------------------------------------------------------------
 // V -> A1 -> MXINT8 along TOKENS (32-token windows per column) -> bf16 MMA-ready V^T operand.
 // grid (heads, groups of 4 windows); thread <-> (window, column) pairs, consecutive threads on
 // consecutive columns (coalesced loads, conflict-free 16-byte stores).
