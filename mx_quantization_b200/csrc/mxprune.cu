@@ -677,7 +677,7 @@ inline LongWsLayout long_ws_layout(int B, int H, int Nq, int Nk, int hd) {
     size_t o = 0;
     W.q_pp = o;      o += align256(bh * O.q_head_bytes);
     W.k_pp = o;      o += align256(bh * O.k_head_bytes);
-    W.q_ep = o;      o += align256(bh * (size_t)O.q_tiles * KL_T * 4);
+    W.q_ep = o;      o += align256(bh * (size_t)O.q_tiles * KL_TILE * 4);
     W.head_meta = o; o += align256(bh * 32);
     W.flags = o;     o += align256(bh * (size_t)Nq);
     W.total = o;
@@ -705,7 +705,7 @@ static int try_predict_topk_long_tc(const PredParams& p, cudaStream_t st, int* r
         QuantOpsParams qp{};
         qp.x = which ? p.k : p.q;
         qp.H = p.H; qp.N = which ? p.Nk : p.Nq;
-        qp.rows_pad = which ? O.nblk * O.kb_rows : O.q_tiles * KL_T;
+        qp.rows_pad = which ? O.nblk * O.kb_rows : O.q_tiles * KL_TILE;
         qp.hd = p.hd; qp.bf16 = p.bf16; qp.flush = p.flush; qp.which = which; qp.Nq = p.Nq; qp.Nk = p.Nk;
         qp.op = which ? p.k_op : p.q_op;
         qp.pp = w + (which ? W.k_pp : W.q_pp);

@@ -5,10 +5,12 @@
 // digit radix select that RE-SCORES the row in every pass - which is what the tensor core makes
 // cheap: a pass streams the head's predictor operand Kp (bf16 +-2^e, MMA-ready, written once per
 // head by k_quantize_ops) through shared memory in blocks of 128 keys, one tcgen05.mma per block
-// into one of two TMEM buffers, and the 128 row threads read their scores back with tcgen05.ld.
+// into one of two TMEM buffers, and the threads read their scores back with tcgen05.ld.16x32bx2:
+// a warp owns 16 query rows, lanes l and l + 16 share row l and take keys [0,64) / [64,128) of the block.
 //   pass 0..L-1  per-thread histogram (64 bins x 6 bits per level, [bin][thread] in shared memory:
 //                conflict-free, no atomics) of the current digit among keys whose higher digits
-//                equal the prefix found so far; scan from the top bin for the digit of the k-th key
+//                equal the prefix found so far; the two lanes of a row add their columns when they
+//                scan from the top bin for the digit of the k-th key
 //   last pass    emit: keys > T kept, keys == T kept in ascending index until top_k
 // Keys are the exact 15-bit integers of the short kernels (score * 2^(-g-1) + offset, read from the
 // low mantissa bits of one FFMA).  Rows outside that window are flagged and left to the CUDA-core
@@ -20,7 +22,8 @@
 
 namespace mxp {
 
-constexpr int KL_T = 128;             // threads == query rows per tile
+constexpr int KL_T = 256;             // threads per CTA: two lanes per query row
+constexpr int KL_TILE = 128;          // query rows per tile
 constexpr int KL_BINS = 64;
 
 // ------------------------------------------------------------------------------------------
@@ -140,10 +143,13 @@ k_select_long_tc(const LongSelParams p) {
     int* s_nlev = reinterpret_cast<int*>(s_tmem + 1);
 
     const int head = blockIdx.x;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lane_base = 32 * (warp & 3) + 16 * (warp >> 2);
+    const int rr = lane_base + (lane & 15);             // row of the tile
+    const int part = lane >> 4;                         // keys [64 part, 64 part + 64) of every block
     const unsigned char* q_pp = p.q_pp + (size_t)head * O.q_head_bytes;
     const unsigned char* k_pp = p.k_pp + (size_t)head * O.k_head_bytes;
-    const int q_rows_pad = O.q_tiles * KL_T;
+    const int q_rows_pad = O.q_tiles * KL_TILE;
 
     if (tid == 0) {
         mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1);
@@ -155,7 +161,7 @@ k_select_long_tc(const LongSelParams p) {
     __syncthreads();
     tcgen05_fence_after_sync();
     const uint32_t tmem = *s_tmem;
-    const uint32_t my_lane = (uint32_t)(warp * 32) << 16;
+    const uint32_t my_lane = (uint32_t)lane_base << 16;
     const uint32_t idesc = umma_idesc_bf16_f32(128, 128);
     uint32_t ph_k[2] = {0u, 0u}, ph_m[2] = {0u, 0u}, ph_q = 0u;
 
@@ -169,11 +175,14 @@ k_select_long_tc(const LongSelParams p) {
         wide |= spread[b] > K1_MAX_SPREAD;
     }
     const int NW = (Nk + 31) >> 5;
-    const int npad = nblk * 128 - Nk;                   // zero rows of Kp: score exactly 0
+    // zero rows of Kp (score exactly 0) among THIS lane's key columns: only the last block has any
+    const int last0 = (nblk - 1) * 128 + 64 * part;
+    const int my_npad = max(0, min(64, last0 + 64 - Nk));
     unsigned short* my_hist = s_hist + tid;             // bin b at my_hist[b * KL_T]
+    const unsigned short* their_hist = s_hist + (tid ^ 16);
 
     for (int tile = blockIdx.y; tile < O.q_tiles; tile += gridDim.y) {
-        const int i = tile * KL_T + tid;
+        const int i = tile * KL_TILE + rr;
         const bool valid = i < Nq;
         const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
         if (tid == 0) {
@@ -204,7 +213,7 @@ k_select_long_tc(const LongSelParams p) {
             }
         }
         if (M > K1_MAX_M) fast = false;
-        if (valid) p.flags[row] = fast ? 0 : 1;
+        if (valid && part == 0) p.flags[row] = fast ? 0 : 1;
         if (!fast) M = 0;
         const int moff = ((int)M + 1) & ~1;
         const float scl = fast ? exp2i(-g - 1) : 0.f;
@@ -216,7 +225,7 @@ k_select_long_tc(const LongSelParams p) {
         __syncthreads();                                            // *s_nlev = 0 visible
         {
             const int wl = __reduce_max_sync(FULL, fast ? my_lev : 0);
-            if ((tid & 31) == 0) atomicMax(s_nlev, wl);
+            if (lane == 0) atomicMax(s_nlev, wl);
         }
         __syncthreads();
         const int nlev = *s_nlev;
@@ -234,7 +243,7 @@ k_select_long_tc(const LongSelParams p) {
             if (!emit) {
                 for (int b = 0; b < KL_BINS; ++b) my_hist[b * KL_T] = 0;
             }
-            int rem = krem, pos = 0;                                // emit state
+            int rem = krem, pos = 0;                                // emit state (identical in both lanes)
             const uint32_t T = prefix;
             if (tid == 0) {
                 const int pre = min(2, nblk);
@@ -252,7 +261,7 @@ k_select_long_tc(const LongSelParams p) {
                         tcgen05_fence_after_sync();
                         const unsigned char* kb = sK + (size_t)s * O.k_blk_bytes;
                         for (int ks = 0; ks < (O.hdp >> 4); ++ks) {
-                            const uint64_t da = umma_smem_desc(smem_u32(sQ + (size_t)(2 * ks) * KL_T * 16), KL_T * 16, 128);
+                            const uint64_t da = umma_smem_desc(smem_u32(sQ + (size_t)(2 * ks) * KL_TILE * 16), KL_TILE * 16, 128);
                             const uint64_t db = umma_smem_desc(smem_u32(kb + (size_t)(2 * ks) * 128 * 16), 128 * 16, 128);
                             umma_bf16_ss(tmem + (uint32_t)(s * 128), da, db, idesc, ks > 0);
                         }
@@ -270,31 +279,41 @@ k_select_long_tc(const LongSelParams p) {
                                      (uint32_t)O.k_blk_bytes, &bar_k[s]);
                     }
                     const uint32_t tbase = tmem + my_lane + (uint32_t)(s * 128);
+                    if (!emit) {
+                        if (__any_sync(FULL, counting)) {
 #pragma unroll 1
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        uint32_t r[32];
-                        tmem_ld_32x32b_x32(tbase + q4 * 32, r);
-                        tmem_ld_wait();
-                        if (!emit) {
-                            if (counting) {
-                                if (pass == 0) {                    // no prefix yet: every key counts
+                            for (int q2 = 0; q2 < 2; ++q2) {        // this lane's keys 64 part + 32 q2 + c
+                                uint32_t r[32];
+                                tmem_ld_16x32bx2_s64_x32(tbase + q2 * 32, r);
+                                tmem_ld_wait();
+                                if (counting) {
+                                    if (pass == 0) {                // no prefix yet: every key counts
 #pragma unroll
-                                    for (int c = 0; c < 32; ++c) {
-                                        const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd));
-                                        my_hist[((u >> lo) & 63u) * KL_T] += 1;
-                                    }
-                                } else {
+                                        for (int c = 0; c < 32; ++c) {
+                                            const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd));
+                                            my_hist[((u >> lo) & 63u) * KL_T] += 1;
+                                        }
+                                    } else {
 #pragma unroll
-                                    for (int c = 0; c < 32; ++c) {
-                                        const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0xffffu;
-                                        if ((u >> (lo + 6)) == prefix) my_hist[((u >> lo) & 63u) * KL_T] += 1;
+                                        for (int c = 0; c < 32; ++c) {
+                                            const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0xffffu;
+                                            if ((u >> (lo + 6)) == prefix) my_hist[((u >> lo) & 63u) * KL_T] += 1;
+                                        }
                                     }
                                 }
                             }
-                        } else {
-                            // two keys per word (c, c + 16), compared as fp16 bit patterns
-                            const int j0 = j * 128 + q4 * 32;       // first key of this word
-                            const __half2 t2 = u32_as_h2(T * 0x00010001u);
+                        }
+                    } else {
+                        // two words of 32 keys per lane and block, keys (c, c + 16) packed per register and
+                        // compared as fp16 bit patterns; ties are taken in ascending key index: the lower
+                        // lane's 64 keys come first, so the lanes exchange their tie counts per block
+                        const __half2 t2 = u32_as_h2(T * 0x00010001u);
+                        uint32_t gtw[2], eqw[2];
+#pragma unroll
+                        for (int q2 = 0; q2 < 2; ++q2) {
+                            uint32_t r[32];
+                            tmem_ld_16x32bx2_s64_x32(tbase + q2 * 32, r);
+                            tmem_ld_wait();
                             uint32_t gt = 0u, eq = 0u;
 #pragma unroll
                             for (int c = 0; c < 16; ++c) {
@@ -304,23 +323,41 @@ k_select_long_tc(const LongSelParams p) {
                                 gt |= __hgt2_mask(kv, t2) & (0x00010001u << c);
                                 eq |= __heq2_mask(kv, t2) & (0x00010001u << c);
                             }
-                            const int nv = Nk - j0;
+                            const int nv = Nk - (j * 128 + 64 * part + 32 * q2);
                             const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : (1u << nv) - 1u);
-                            gt &= vm;
-                            eq &= vm;
-                            const int cnt = __popc(eq);
-                            uint32_t take = eq;
-                            if (cnt > rem) take = keep_lowest_bits_fast(eq, rem);
-                            rem -= min(cnt, rem);
-                            const uint32_t word = gt | take;
-                            if (valid && fast && (j0 >> 5) < NW) {
-                                p.mask[row * NW + (j0 >> 5)] = word;
-                                if (p.idx) {
-                                    uint32_t w2 = word;
-                                    while (w2) {
-                                        const int bpos = __ffs(w2) - 1;
-                                        w2 &= w2 - 1u;
-                                        p.idx[row * kk + pos++] = j0 + bpos;
+                            gtw[q2] = gt & vm;
+                            eqw[q2] = eq & vm;
+                        }
+                        const int ties_m = __popc(eqw[0]) + __popc(eqw[1]);
+                        const int ties_o = __shfl_xor_sync(FULL, ties_m, 16);
+                        int r_here = part == 0 ? rem : max(rem - ties_o, 0);        // ties still wanted at my first key
+                        rem = max(rem - ties_m - ties_o, 0);
+                        uint32_t word[2];
+#pragma unroll
+                        for (int q2 = 0; q2 < 2; ++q2) {
+                            const int cnt = __popc(eqw[q2]);
+                            uint32_t take = eqw[q2];
+                            if (cnt > r_here) take = keep_lowest_bits_fast(eqw[q2], r_here);
+                            r_here -= min(cnt, r_here);
+                            word[q2] = gtw[q2] | take;
+                        }
+                        const int kept_m = __popc(word[0]) + __popc(word[1]);
+                        const int kept_o = __shfl_xor_sync(FULL, kept_m, 16);
+                        int pos_here = pos + (part == 0 ? 0 : kept_o);
+                        pos += kept_m + kept_o;
+                        if (valid && fast) {
+#pragma unroll
+                            for (int q2 = 0; q2 < 2; ++q2) {
+                                const int j0 = j * 128 + 64 * part + 32 * q2;
+                                if ((j0 >> 5) < NW) {
+                                    p.mask[row * NW + (j0 >> 5)] = word[q2];
+                                    if (p.idx) {
+                                        uint32_t w2 = word[q2];
+                                        while (w2) {
+                                            const int bpos = __ffs(w2) - 1;
+                                            w2 &= w2 - 1u;
+                                            p.idx[row * kk + pos_here++] = j0 + bpos;
+                                        }
                                     }
                                 }
                             }
@@ -330,17 +367,22 @@ k_select_long_tc(const LongSelParams p) {
                 tcgen05_fence_before_sync();
                 __syncthreads();                                    // TMEM buffer of block j is free again
             }
-            if (counting) {
-                // the npad zero rows of Kp all scored key0: discount them
-                if (npad > 0 && (key0 >> (lo + 6)) == prefix) my_hist[((key0 >> lo) & 63u) * KL_T] -= (unsigned short)npad;
-                int cum = 0, bin = KL_BINS - 1;
-                for (; bin > 0; --bin) {
-                    const int h = (int)my_hist[bin * KL_T];
-                    if (cum + h >= krem) break;
-                    cum += h;
+            if (!emit) {
+                // the zero rows of Kp all scored key0: discount them (each lane its own columns)
+                if (counting && my_npad > 0 && (key0 >> (lo + 6)) == prefix)
+                    my_hist[((key0 >> lo) & 63u) * KL_T] -= (unsigned short)my_npad;
+                __syncwarp();                                       // the partner lane's column is complete
+                if (counting) {
+                    int cum = 0, bin = KL_BINS - 1;
+                    for (; bin > 0; --bin) {
+                        const int h = (int)my_hist[bin * KL_T] + (int)their_hist[bin * KL_T];
+                        if (cum + h >= krem) break;
+                        cum += h;
+                    }
+                    krem -= cum;
+                    prefix = (prefix << 6) | (uint32_t)bin;
                 }
-                krem -= cum;
-                prefix = (prefix << 6) | (uint32_t)bin;
+                __syncwarp();                                       // both lanes have scanned before the next zeroing
             }
         }
     }
