@@ -145,6 +145,25 @@ int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_s
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Cross-attention with an additive key bias: PixArt-alpha's MXCrossAttention adds the
+ * text-token mask to BOTH the true and the predicted scores before top-k and softmax
+ * (workloads/PixArt/models/MX_transformer_block.py:794-803, 821-822):
+ *     true_scores += attn_bias ;  pred_scores = ex_q @ ex_k^T + attn_bias
+ * key_bias[b * kb_sB + j] is that bias for key j of batch element b (the reference's (B,1,1,S) mask,
+ * the same for every head and query row; finite values, e.g. (1 - mask) * -10000).  Nq and Nk may
+ * differ (Nk <= 256).  Everything else as mxp_pruned_attention.
+ */
+int mxp_pruned_attention_biased(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                                const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                                const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                                int B, int H, int Nq, int Nk, int hd, int top_k,
+                                float scale, int bfloat_bits, int flush,
+                                float* out, int64_t o_sB, int64_t o_sH, int64_t o_sN,
+                                const float* key_bias, int64_t kb_sB,
+                                uint32_t* mask_out,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Measurement aid: same as mxp_pruned_attention (tcgen05 path), but brackets the three kernels
  * (predict+top-k, V operand prep, exact attention) with CUDA events on `stream`, SYNCHRONISES, and
  * returns their durations in milliseconds in kernel_ms[0..2].  bench.py's roofline uses this.

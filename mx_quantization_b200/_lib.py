@@ -32,6 +32,8 @@ _SIGNATURES = {
     "mxp_pruned_attention_workspace_bytes": (c_size_t, [c_int] * 5),
     "mxp_pruned_attention": (c_int, _VIEW * 3 + [c_int] * 6 + [c_float, c_int, c_int] + _VIEW
                              + [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mxp_pruned_attention_biased": (c_int, _VIEW * 3 + [c_int] * 6 + [c_float, c_int, c_int] + _VIEW
+                                    + [c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mxp_pruned_attention_profile": (c_int, _VIEW * 3 + [c_int] * 6 + [c_float, c_int, c_int] + _VIEW
                                      + [c_void_p, c_void_p, c_size_t, c_void_p, ctypes.POINTER(c_float)]),
 }

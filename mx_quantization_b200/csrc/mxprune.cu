@@ -503,8 +503,10 @@ int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     const K2Smem L = k2_smem_layout(O);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attend_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_attend_pair<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_pair<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_pair<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_pair<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_umma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_umma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -524,9 +526,16 @@ int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     size_t dyn = L.total;
     const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
     if (dyn < floor_bytes) dyn = floor_bytes;
+    if (p.key_bias && !O.single)
+        return fail(MXP_E_UNSUPPORTED, "key_bias: the additive key bias is implemented for Nk <= 256 (cross-attention)");
     if (O.single) {                 // one key block: two lanes per query row, 256 threads
-        if (p.bf16) k_attend_pair<true><<<grid, K2P_T, dyn, st>>>(p);
-        else k_attend_pair<false><<<grid, K2P_T, dyn, st>>>(p);
+        if (p.key_bias) {
+            if (p.bf16) k_attend_pair<true, true><<<grid, K2P_T, dyn, st>>>(p);
+            else k_attend_pair<false, true><<<grid, K2P_T, dyn, st>>>(p);
+        } else {
+            if (p.bf16) k_attend_pair<true, false><<<grid, K2P_T, dyn, st>>>(p);
+            else k_attend_pair<false, false><<<grid, K2P_T, dyn, st>>>(p);
+        }
     } else {                        // key blocks of 128 with online softmax, one thread per row
         if (p.bf16) k_attend_umma<false, true><<<grid, K2T, dyn, st>>>(p);
         else k_attend_umma<false, false><<<grid, K2T, dyn, st>>>(p);
@@ -861,6 +870,8 @@ size_t mxp_predict_topk_workspace_bytes(int B, int H, int Nq, int Nk, int hd) {
 
 static int predict_topk_impl(const PredParams& p, cudaStream_t st) {
     int rc = MXP_OK;
+    if (p.key_bias && p.Nk > K1_MAX_KEYS)
+        return fail(MXP_E_UNSUPPORTED, "key_bias: the additive key bias is implemented for Nk <= 256 (cross-attention)");
     if (try_predict_topk_tc(p, st, &rc) == 0) return rc;
     if (try_predict_topk_long_tc(p, st, &rc) == 0) return rc;
     switch ((p.hd + 31) / 32) {
@@ -966,14 +977,16 @@ size_t mxp_pruned_attention_workspace_bytes(int B, int H, int Nq, int Nk, int hd
     return (ops > codes ? ops : codes) + align256(bh * Nq * nw * 4) + long_ws_layout(B, H, Nq, Nk, hd).total;
 }
 
-int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
-                         const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
-                         const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
-                         int B, int H, int Nq, int Nk, int hd, int top_k, float scale,
-                         int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
-                         int64_t o_sN, uint32_t* mask_out, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+static int pruned_attention_impl(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                                 const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                                 const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                                 int B, int H, int Nq, int Nk, int hd, int top_k, float scale,
+                                 int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
+                                 int64_t o_sN, const float* key_bias, int64_t kb_sB, uint32_t* mask_out,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
+    if (key_bias && (g_attn_path != 0 || ((uintptr_t)key_bias & 3)))
+        return fail(MXP_E_UNSUPPORTED, "key_bias needs the tcgen05 attention path and a 4-byte aligned pointer");
     int rc = check_shape(B, H, Nq, Nk, hd, bfloat_bits);
     if (rc) return rc;
     if ((rc = check_view("q", q, q_sB, q_sH, q_sN, hd))) return rc;
@@ -999,6 +1012,7 @@ int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_s
     pp.B = B; pp.H = H; pp.Nq = Nq; pp.Nk = Nk; pp.hd = hd; pp.top_k = top_k;
     pp.bf16 = bfloat_bits == 16; pp.flush = flush != 0;
     pp.mask = mask; pp.idx = nullptr;
+    pp.key_bias = key_bias; pp.kb_sB = kb_sB;
     pp.long_ws = long_bytes ? w + need - long_bytes : nullptr;
     pp.long_ws_bytes = long_bytes;
     if (tc) {
@@ -1016,6 +1030,7 @@ int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_s
         ap.B = B; ap.H = H; ap.Nq = Nq; ap.Nk = Nk; ap.hd = hd;
         ap.scale = scale; ap.bf16 = bfloat_bits == 16; ap.flush = flush != 0;
         ap.out = out; ap.o_sB = o_sB; ap.o_sH = o_sH; ap.o_sN = o_sN;
+        ap.key_bias = key_bias; ap.kb_sB = kb_sB;
         rc = launch_attend_umma(ap, st);
         prof_mark(3, st);
         return rc;
@@ -1034,6 +1049,31 @@ int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_s
     ap.scale = scale; ap.bf16 = bfloat_bits == 16; ap.flush = flush != 0;
     ap.out = out; ap.o_sB = o_sB; ap.o_sH = o_sH; ap.o_sN = o_sN;
     return attend_core_impl(ap, st);
+}
+
+int mxp_pruned_attention(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                         const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                         const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                         int B, int H, int Nq, int Nk, int hd, int top_k, float scale,
+                         int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
+                         int64_t o_sN, uint32_t* mask_out, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+    return pruned_attention_impl(q, q_sB, q_sH, q_sN, k, k_sB, k_sH, k_sN, v, v_sB, v_sH, v_sN, B, H, Nq, Nk, hd,
+                                 top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, nullptr, 0, mask_out,
+                                 workspace, workspace_bytes, stream);
+}
+
+int mxp_pruned_attention_biased(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                                const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                                const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                                int B, int H, int Nq, int Nk, int hd, int top_k, float scale,
+                                int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
+                                int64_t o_sN, const float* key_bias, int64_t kb_sB, uint32_t* mask_out,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    if (!key_bias) return fail(MXP_E_BADARG, "key_bias: null pointer (use mxp_pruned_attention)");
+    return pruned_attention_impl(q, q_sB, q_sH, q_sN, k, k_sB, k_sH, k_sN, v, v_sB, v_sH, v_sN, B, H, Nq, Nk, hd,
+                                 top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, key_bias, kb_sB, mask_out,
+                                 workspace, workspace_bytes, stream);
 }
 
 int mxp_pruned_attention_profile(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,

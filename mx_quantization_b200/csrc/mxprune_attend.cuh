@@ -43,6 +43,8 @@ struct AttnParams {
     int bf16, flush;
     float* out;
     int64_t o_sB, o_sH, o_sN;
+    const float* key_bias;      // optional additive bias per (batch, key), added to score * scale (fp32)
+    int64_t kb_sB;
 };
 
 // Layout of the MMA-ready operand buffers of one head (all sizes in bytes).
@@ -455,12 +457,13 @@ __host__ __device__ inline int k2p_tmem_cols(const OpsLayout& O) {
     return c;
 }
 
-template <bool BF16>
+template <bool BF16, bool BIAS>
 __global__ void __launch_bounds__(K2P_T, 2)
 k_attend_pair(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar_ld, bar_s, bar_o;
     __shared__ uint32_t tmem_base_s;
+    __shared__ float s_bias[BIAS ? 256 : 1];                        // PixArt cross-attention text mask (:794-803)
     constexpr bool bf16 = BF16;
     const int Nk = p.Nk, Nq = p.Nq, hd = p.hd;
     const OpsLayout O = ops_layout(Nq, Nk, hd);
@@ -482,6 +485,7 @@ k_attend_pair(const AttnParams p) {
     const uint32_t tcols = (uint32_t)k2p_tmem_cols(O);
 
     if (tid == 0) { mbar_init(&bar_ld, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1); }
+    if (BIAS) s_bias[tid] = tid < Nk ? __ldg(p.key_bias + bb * p.kb_sB + tid) : 0.f;
     if (warp == 0) tmem_alloc(&tmem_base_s, tcols);
     tcgen05_fence_before_sync();
     __syncthreads();
@@ -544,11 +548,13 @@ k_attend_pair(const AttnParams p) {
                 tmem_ld_16x32bx2_s64_x32(my_tmem + 128 * (t >> 1) + 32, rb);
                 {
                     const uint32_t m0 = mw[t & 3];
+                    const int kb0 = 128 * (t >> 1) + 64 * part;     // key index of column c
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         float s = __uint_as_float(ra[c]);
                         if (bf16) s = bf16_half_away(s);
-                        const float tv = __fmul_rn(s, p.scale);
+                        float tv = __fmul_rn(s, p.scale);
+                        if (BIAS) tv = __fadd_rn(tv, s_bias[kb0 + c]);
                         mb4[c & 3] = fmaxf(mb4[c & 3], ((m0 >> c) & 1u) ? tv : -INFINITY);
                     }
                 }
@@ -556,11 +562,13 @@ k_attend_pair(const AttnParams p) {
                 if (t + 2 < nwin) tmem_ld_16x32bx2_s64_x32(my_tmem + 128 * ((t >> 1) + 1), ra);
                 {
                     const uint32_t m1 = mw[(t + 1) & 3];
+                    const int kb1 = 128 * (t >> 1) + 32 + 64 * part;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         float s = __uint_as_float(rb[c]);
                         if (bf16) s = bf16_half_away(s);
-                        const float tv = __fmul_rn(s, p.scale);
+                        float tv = __fmul_rn(s, p.scale);
+                        if (BIAS) tv = __fadd_rn(tv, s_bias[kb1 + c]);
                         mb4[c & 3] = fmaxf(mb4[c & 3], ((m1 >> c) & 1u) ? tv : -INFINITY);
                     }
                 }
@@ -583,7 +591,9 @@ k_attend_pair(const AttnParams p) {
             for (int c = 0; c < 32; ++c) {
                 float s = __uint_as_float(r[c]);
                 if (bf16) s = bf16_half_away(s);
-                const float ex = exp_nonpos(__fsub_rn(__fmul_rn(s, p.scale), m_use));
+                float tv = __fmul_rn(s, p.scale);
+                if (BIAS) tv = __fadd_rn(tv, s_bias[col + 64 * part + c]);
+                const float ex = exp_nonpos(__fsub_rn(tv, m_use));
                 const float ev = ((mwt >> c) & 1u) ? ex : 0.f;
                 sum4[c & 3] += ev;
                 r[c] = __float_as_uint(ev);

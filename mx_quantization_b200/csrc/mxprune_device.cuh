@@ -31,6 +31,8 @@ struct PredParams {
     int8_t *q_codes, *q_exps, *k_codes, *k_exps;
     unsigned char *q_op, *k_op;   // MMA-ready bf16 operands for the exact-attention kernel (may be null)
     float* scores;   // dense debug output (k_predict_scores only)
+    const float* key_bias;       // optional additive bias per (batch, key), added to the predicted scores (fp32)
+    int64_t kb_sB;               //   key_bias[b * kb_sB + j]; rows then take the generic fp32 path
     const uint8_t* row_filter;   // k_predict_topk_long only: [heads][Nq], process rows with a non-zero flag (null = all)
     void* long_ws;               // host side: workspace of the long-sequence tensor-core path (may be null)
     size_t long_ws_bytes;

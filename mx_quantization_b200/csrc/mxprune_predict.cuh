@@ -190,7 +190,8 @@ struct GenRow {
 template <int NB>
 __device__ __noinline__ void predict_row_generic(uint32_t* __restrict__ mask_out, int32_t* __restrict__ idx_out,
                                                  int Nk, int kk, int hd, int64_t row, GenRow<NB> gr,
-                                                 const uint32_t* s_krec, const signed char* s_kexp, int nkp) {
+                                                 const uint32_t* s_krec, const signed char* s_kexp, int nkp,
+                                                 const float* kbias = nullptr) {
     constexpr int KPL = K1_MAX_KEYS / 32;
     const int lane = threadIdx.x & 31;
     uint32_t u[KPL];
@@ -208,6 +209,7 @@ __device__ __noinline__ void predict_row_generic(uint32_t* __restrict__ mask_out
                 const float t = exp2i((int)s_kexp[b * nkp + j]) * cnt;
                 s = (b == 0) ? t * exp2i(gr.ep[0]) : fmaf(t, exp2i(gr.ep[b]), s);
             }
+            if (kbias) s = __fadd_rn(s, __ldg(kbias + j));          // pred_scores + attn_bias, fp32
         }
         u[r] = valid ? ordered_key(s) : 0u;
         aor |= u[r];
@@ -362,7 +364,7 @@ k_predict_topk_rows(const PredParams p) {
         int g = 0x7fffffff;
 #pragma unroll
         for (int b = 0; b < NB; ++b) g = min(g, rq.ep[b] + kmin[b]);
-        bool fast = valid && !wide;
+        bool fast = valid && !wide && p.key_bias == nullptr;
         int mq[NB];
         long long M = 0;
 #pragma unroll
@@ -465,7 +467,8 @@ k_predict_topk_rows(const PredParams p) {
                 gr.ep[b] = __shfl_sync(FULL, rq.ep[b], l);
             }
             const int64_t grow = (int64_t)head * Nq + (i0 + (tid & ~31) + l);
-            predict_row_generic<NB>(p.mask, p.idx, Nk, kk, hd, grow, gr, s_krec, s_kexp, nkp);
+            predict_row_generic<NB>(p.mask, p.idx, Nk, kk, hd, grow, gr, s_krec, s_kexp, nkp,
+                                    p.key_bias ? p.key_bias + bb * p.kb_sB : nullptr);
         }
     }
 }

@@ -255,7 +255,7 @@ __device__ __forceinline__ uint32_t keep_lowest_bits_fast(uint32_t x, int m) {
 __device__ __noinline__ void predict_row_generic_tc(uint32_t* __restrict__ mask_out, int32_t* __restrict__ idx_out,
                                                     int Nk, int kk, int hd, int nb, int64_t row, const uint32_t* sq,
                                                     const int* ep, const uint32_t* s_ksign,
-                                                    const signed char* s_kexp) {
+                                                    const signed char* s_kexp, const float* kbias) {
     constexpr int KPL = 8;
     const int lane = threadIdx.x & 31;
     uint32_t u[KPL];
@@ -272,6 +272,7 @@ __device__ __noinline__ void predict_row_generic_tc(uint32_t* __restrict__ mask_
                 const float t = exp2i((int)s_kexp[b * 256 + j]) * cnt;
                 s = (b == 0) ? t * exp2i(ep[0]) : fmaf(t, exp2i(ep[b]), s);
             }
+            if (kbias) s = __fadd_rn(s, __ldg(kbias + j));          // pred_scores + attn_bias, fp32
         }
         u[r] = valid ? ordered_key(s) : 0u;
         aor |= u[r];
@@ -369,6 +370,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     unsigned char* k_op = p.k_op ? p.k_op + (size_t)head * OL.k_head_bytes : nullptr;
     unsigned char* q_op = p.q_op ? p.q_op + (size_t)head * OL.q_head_bytes : nullptr;
     const int kb_rows = OL.kb_rows;
+    const float* kbias = p.key_bias ? p.key_bias + bb * p.kb_sB : nullptr;
 
     // ---- step schedule of this CTA: CR = 64 G rows per step; K steps first, then the Q tiles
     const int CR = K1C_ROWS * G, cr_shift = G == 2 ? 7 : 6;
@@ -557,7 +559,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
 #pragma unroll
         for (int b = 0; b < 4; ++b)
             if (b < nb) g = min(g, epq[b] + kmin[b]);
-        bool fast = valid && !wide && g >= -100 && g <= 80;
+        bool fast = valid && !wide && g >= -100 && g <= 80 && kbias == nullptr;   // biased scores: fp32 path
         long long M = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
@@ -681,7 +683,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                 gep[b] = __shfl_sync(FULL, epq[b], l);
             }
             const int64_t grow = (int64_t)head * Nq + (tile * K1C_TILE + lane_base + l);
-            predict_row_generic_tc(p.mask, p.idx, Nk, kk, hd, nb, grow, gsq, gep, s_ksign, s_kexp);
+            predict_row_generic_tc(p.mask, p.idx, Nk, kk, hd, nb, grow, gsq, gep, s_ksign, s_kexp, kbias);
         }
     }
     tcgen05_fence_before_sync();

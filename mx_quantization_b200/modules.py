@@ -33,11 +33,13 @@ class PrunedAttentionCore(nn.Module):
         self.k = int(k)
         self.scale = scale
 
-    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
+                key_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
         B, H, N, hd = q.shape
         buf = torch.empty((B, N, H, hd), dtype=torch.float32, device=q.device)
         # write straight into (B,N,H,hd): the reference's x.transpose(1,2).reshape(B,N,C) is free
-        ops.pruned_attention(q, k, v, self.mx_specs, self.k, scale=self.scale, out=buf.permute(0, 2, 1, 3))
+        ops.pruned_attention(q, k, v, self.mx_specs, self.k, scale=self.scale, out=buf.permute(0, 2, 1, 3),
+                             key_bias=key_bias)
         return buf.reshape(B, N, H * hd)
 
 
@@ -140,5 +142,28 @@ class MXSelfAttention(nn.Module):
         k = self.to_k(hidden_states).view(B, N, self.num_heads, self.head_dim).transpose(1, 2)
         v = self.to_v(hidden_states).view(B, N, self.num_heads, self.head_dim).transpose(1, 2)
         x = self.to_out(self.core(q, k, v))
+        self.current_timestep += 1
+        return x
+
+
+class MXCrossAttention(MXSelfAttention):
+    """PixArt-alpha cross-attention shim - mirrors workloads/PixArt/models/MX_transformer_block.py:720-859:
+    keys / values come from the text encoder states (S tokens), and the additive attention_mask
+    (B,1,S) is applied to the true and the predicted scores (:794-803, :821-822)."""
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs):
+        if self.core is None:
+            raise RuntimeError("MXCrossAttention.set_config(...) must be called first")
+        if encoder_hidden_states is None:
+            raise ValueError("MXCrossAttention needs encoder_hidden_states")
+        B, N, C = hidden_states.shape
+        S = encoder_hidden_states.shape[1]
+        q = self.to_q(hidden_states).view(B, N, self.num_heads, self.head_dim).transpose(1, 2)
+        k = self.to_k(encoder_hidden_states).reshape(B, S, self.num_heads, self.head_dim).transpose(1, 2)
+        v = self.to_v(encoder_hidden_states).reshape(B, S, self.num_heads, self.head_dim).transpose(1, 2)
+        if attention_mask is not None and attention_mask.dtype == torch.bool:
+            raise NotImplementedError("boolean masks (-inf bias) are not on the path; pass the additive fp32 mask")
+        bias = None if attention_mask is None else attention_mask.to(torch.float32).reshape(B, S)
+        x = self.to_out(self.core(q, k, v, key_bias=bias))
         self.current_timestep += 1
         return x

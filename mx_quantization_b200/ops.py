@@ -193,13 +193,19 @@ def sparse_attention(q_codes, q_exps, k_codes, k_exps, v: torch.Tensor, mask: to
 
 def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs, top_k: int,
                      scale: Optional[float] = None, return_mask: bool = False,
-                     out: Optional[torch.Tensor] = None, _kernel_ms: Optional[list] = None):
+                     out: Optional[torch.Tensor] = None, _kernel_ms: Optional[list] = None,
+                     key_bias: Optional[torch.Tensor] = None):
     """MXINT8 exponent-sign predicted top-k attention: q,k,v (B,H,N,hd) fp32 -> out (B,H,Nq,hd).
 
     Drop-in for lines 101-152 of workloads/deit/scripts/main.py (DiT models.py:168-225, PixArt
     MX_transformer_block.py:647-710) when mx_quant, top_k, approx_flag and pred_mode=="ex_pred".
     ``out`` may be any fp32 (B,H,Nq,hd) *view* with innermost stride 1, e.g. a permuted
     (B,Nq,H,hd) buffer so that the module's transpose(1,2).reshape(B,N,C) is free.
+
+    ``key_bias``: PixArt cross-attention's additive text mask (MX_transformer_block.py:794-803,
+    821-822), any fp32 tensor with B * Nk elements laid out (B, ..., Nk) - e.g. the reference's
+    (B,1,1,S) attention_mask; it is added to the true AND the predicted scores.  Nq may differ
+    from Nk (Nk <= 256 with a bias).
     """
     sp = resolve_specs(mx_specs)
     lib = _lib.load()
@@ -220,7 +226,14 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
         args = (_ptr(q), *_strides(q), _ptr(k), *_strides(k), _ptr(v), *_strides(v),
                 B, H, Nq, Nk, hd, int(top_k), scale, sp.bfloat_bits, int(sp.flush),
                 _ptr(out), *_strides(out), _ptr(mask), _ptr(ws), ws_bytes, _stream())
-        if _kernel_ms is None:
+        if key_bias is not None:
+            if key_bias.dtype != torch.float32 or key_bias.numel() != B * Nk or key_bias.device != q.device:
+                raise ValueError("key_bias must be an fp32 tensor with B*Nk elements, (B, ..., Nk), on q's device")
+            if _kernel_ms is not None:
+                raise ValueError("the per-kernel profile entry takes no key_bias")
+            kb = key_bias.reshape(B, Nk).contiguous()
+            rc = lib.mxp_pruned_attention_biased(*args[:-4], _ptr(kb), Nk, *args[-4:])
+        elif _kernel_ms is None:
             rc = lib.mxp_pruned_attention(*args)
         else:       # measurement aid: per-kernel CUDA-event times (synchronises)
             import ctypes

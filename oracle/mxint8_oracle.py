@@ -307,8 +307,13 @@ def default_scale(hd: int) -> float:
 def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: int,
                      scale: Optional[float] = None, bfloat: int = 32, flush: bool = False,
                      idx: Optional[torch.Tensor] = None, use_torch_topk: bool = False,
-                     integer_scores: bool = False) -> Dict[str, torch.Tensor]:
+                     integer_scores: bool = False,
+                     key_bias: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """The whole path on CPU (q, k, v: fp32 (B,H,N,hd)); returns every intermediate.
+
+    key_bias: additive attention bias broadcastable to (B,1,1,Nk), as PixArt's cross-attention
+    adds to BOTH the true and the predicted scores before top-k
+    (workloads/PixArt/models/MX_transformer_block.py:794-803, 821-822).
 
     idx: use this kept-key set instead of the predictor's (to compare outputs on the same
     set).  use_torch_topk: leave torch.topk in place as the reference does (timing only).
@@ -323,6 +328,8 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
     res: Dict[str, torch.Tensor] = {"q_codes": qc, "q_exps": qe, "k_codes": kc, "k_exps": ke}
     if idx is None:
         pred = (pred_scores_integer if integer_scores else pred_scores_matmul)(qc, qe, kc, ke)
+        if key_bias is not None:
+            pred = pred + key_bias.to(torch.float32)                 # fp32 add, :822
         res["pred_scores"] = pred
         if use_torch_topk:
             idx = torch.topk(pred, top_k, dim=-1, largest=True, sorted=True).indices
@@ -331,6 +338,8 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
     res["idx"] = idx
     qd, kd = dequantize_mxint8(qc, qe), dequantize_mxint8(kc, ke)
     true = _elemwise_out(qd @ kd.transpose(-2, -1), bfloat) * scale
+    if key_bias is not None:
+        true = true + key_bias.to(torch.float32)                     # true_scores += attn_bias, :803
     vals = true.gather(-1, idx)
     res["true_vals"] = vals
     res["out"] = sparse_softmax_pv(vals, idx, v, n_keys, bfloat, flush)

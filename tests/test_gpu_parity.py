@@ -268,3 +268,78 @@ def _long_e2e(mxq, q, k, v, specs, top_k, N, bfloat):
     r = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k, return_idx=True, return_codes=True)
     assert torch.equal(r["idx"].cpu().to(torch.int64), torch.sort(ref["idx"], dim=-1).values)
     assert torch.equal(r["k_codes"].cpu(), ref["k_codes"]) and torch.equal(r["q_exps"].cpu(), ref["q_exps"])
+
+
+# ---- cross-attention (Nq != Nk) with PixArt's additive text mask ----------------------
+
+def _load_cross(name):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    d = {k: torch.from_numpy(z[k]) for k in z.files}
+    B, H, Nq, S, hd, top_k, bfloat, flush = (int(x) for x in z["meta"])
+    return d, dict(B=B, H=H, Nq=Nq, S=S, hd=hd, top_k=top_k, bfloat=bfloat, flush=bool(flush))
+
+
+@pytest.mark.parametrize("pred_path", ["tcgen05", "cuda_core"])
+@pytest.mark.parametrize("name", ["pixart_cross", "pixart_cross_k77", "pixart_cross_all"])
+def test_cross_attention_reference_golden(mxq, name, pred_path):
+    """Outputs of the unmodified reference functions in the order of PixArt's MXCrossAttention.forward
+    (workloads/PixArt/models/MX_transformer_block.py:791-859; tests/golden/make_golden_cross.py)."""
+    d, m = _load_cross(name)
+    specs = mx_specs(m["bfloat"], m["flush"])
+    bias = d["key_bias"].reshape(m["B"], 1, 1, m["S"]).cuda()
+    mxq.set_predict_path(pred_path)
+    try:
+        out, mask = mxq.pruned_attention(d["q"].cuda(), d["k"].cuda(), d["v"].cuda(), specs, m["top_k"],
+                                         scale=1.0 / (m["hd"] ** 0.5), return_mask=True, key_bias=bias)
+    finally:
+        mxq.set_predict_path("tcgen05")
+    got = unpack_mask(mask, m["S"])
+    want = torch.zeros_like(got)
+    want.scatter_(-1, d["idx"], True)
+    assert torch.equal(got, want)
+    ref = {"true_vals": d["true_vals"], "idx": d["idx"], "out": d["out"]}
+    assert_out_close(out.cpu(), ref, d["v"], m["S"], m["bfloat"], OUT_TOL)
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,hd,top_k,bfloat", [
+    (2, 3, 256, 120, 72, 77, 32),      # PixArt cross-attention shape, no mask
+    (1, 2, 100, 197, 64, 30, 16),
+    (1, 1, 300, 64, 64, 16, 32),
+    (1, 2, 64, 1000, 72, 100, 32),     # long key side
+])
+def test_rectangular_attention(mxq, B, H, Nq, Nk, hd, top_k, bfloat):
+    """Nq != Nk through the whole path, against the oracle."""
+    g = torch.Generator().manual_seed(31)
+    q = torch.randn(B, H, Nq, hd, generator=g)
+    k = torch.randn(B, H, Nk, hd, generator=g)
+    v = torch.randn(B, H, Nk, hd, generator=g)
+    specs = mx_specs(bfloat, False)
+    out, mask = mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), specs, top_k, return_mask=True)
+    ref = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, integer_scores=True)
+    want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], Nk), Nk)
+    assert torch.equal(unpack_mask(mask, Nk), want)
+    assert_out_close(out.cpu(), ref, v, Nk, bfloat, OUT_TOL)
+
+
+def test_cross_attention_module_shim(mxq):
+    """MXCrossAttention shim == pruned_attention on its own projections."""
+    from mx_quantization_b200.modules import MXCrossAttention
+    torch.manual_seed(0)
+    dim, heads, B, N, S = 144, 2, 2, 64, 40
+    m = MXCrossAttention(dim, heads).cuda().set_config(mx_quant=True, mx_specs=mx_specs(32, True), top_k=True, k=20,
+                                                       ex_pred=True, pred_mode="ex_pred")
+    x = torch.randn(B, N, dim, device="cuda")
+    enc = torch.randn(B, S, dim, device="cuda")
+    keep = torch.zeros(B, S, device="cuda"); keep[0, :13] = 1; keep[1, :27] = 1
+    amask = ((1 - keep) * -10000.0).reshape(B, 1, S)
+    with torch.no_grad():
+        y = m(x, encoder_hidden_states=enc, attention_mask=amask)
+    with torch.no_grad():
+        q = m.to_q(x).view(B, N, heads, dim // heads).transpose(1, 2)
+        k = m.to_k(enc).view(B, S, heads, dim // heads).transpose(1, 2)
+        v = m.to_v(enc).view(B, S, heads, dim // heads).transpose(1, 2)
+    ref = O.pruned_attention(q.cpu(), k.cpu(), v.cpu(), 20, scale=1.0 / ((dim // heads) ** 0.5), flush=True,
+                             integer_scores=True, key_bias=amask.reshape(B, 1, 1, S).cpu())
+    with torch.no_grad():
+        want = m.to_out(ref["out"].transpose(1, 2).reshape(B, N, dim).cuda())
+    assert float((y - want).abs().max()) <= 1e-3 * float(want.abs().max())

@@ -135,3 +135,31 @@ def test_scatter_script_kat():
     assert float(S.min()) == -184.0 and float(S.max()) == 180.0
     assert int((S == 0).sum()) == 1707
     assert int((S < 0).sum()) == 19064
+
+
+CROSS_CASES = ["pixart_cross", "pixart_cross_k77", "pixart_cross_all"]
+
+
+def load_cross(name):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    d = {k: torch.from_numpy(z[k]) for k in z.files}
+    B, H, Nq, S, hd, top_k, bfloat, flush = (int(x) for x in z["meta"])
+    return d, dict(B=B, H=H, Nq=Nq, S=S, hd=hd, top_k=top_k, bfloat=bfloat, flush=bool(flush))
+
+
+@pytest.mark.parametrize("name", CROSS_CASES)
+def test_cross_attention_with_key_bias(name):
+    """PixArt cross-attention (Nq != Nk, additive text mask on true AND predicted scores,
+    workloads/PixArt/models/MX_transformer_block.py:791-859) - oracle vs the reference's outputs."""
+    d, m = load_cross(name)
+    bias = d["key_bias"].reshape(m["B"], 1, 1, m["S"])
+    r = O.pruned_attention(d["q"], d["k"], d["v"], m["top_k"], scale=1.0 / (m["hd"] ** 0.5),
+                           bfloat=m["bfloat"], flush=m["flush"], key_bias=bias)
+    assert torch.equal(r["pred_scores"], d["pred_scores"])
+    assert torch.equal(r["idx"], d["idx"])
+    assert torch.equal(r["true_vals"], d["true_vals"])
+    assert float((r["out"] - d["out"]).abs().max()) == 0.0
+    # the integer restatement of the scores ranks identically
+    r2 = O.pruned_attention(d["q"], d["k"], d["v"], m["top_k"], scale=1.0 / (m["hd"] ** 0.5),
+                            bfloat=m["bfloat"], flush=m["flush"], key_bias=bias, integer_scores=True)
+    assert torch.equal(r2["idx"], d["idx"])
