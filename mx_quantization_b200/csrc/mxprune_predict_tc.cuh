@@ -531,6 +531,21 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
         if (is_k || qstep != qsteps - 1) continue;
 
         // =============== a full query tile is quantized: score, select, emit
+        if (kk >= Nk) {
+            // dense attention (the reference's top_k=False blocks, e.g. DeiT block 11 / DiT block 27:
+            // workloads/deit/scripts/main.py:282-296): every key is kept, nothing to score or select
+            const int i = tile * K1C_TILE + rr;
+            if (i < Nq) {
+                const int64_t row = (int64_t)head * Nq + i;
+                for (int w = part; w < NW; w += 2) {
+                    const int nv = Nk - 32 * w;
+                    p.mask[row * NW + w] = nv >= 32 ? 0xffffffffu : (1u << nv) - 1u;
+                }
+                if (p.idx && part == 0)
+                    for (int j = 0; j < Nk; ++j) p.idx[row * kk + j] = j;
+            }
+            continue;
+        }
         if (tid == 0) {
             tcgen05_fence_after_sync();
             for (int ks = 0; ks < (L.hdp >> 4); ++ks) {

@@ -11,8 +11,9 @@ maintainer can swap the body of ``forward`` (INTEGRATION.md shows the patch).  T
 projections stay whatever the host model uses (``mx.Linear`` in the reference - outside the hot
 path); here they are plain ``nn.Linear`` unless the caller passes its own.
 
-Only mx_quant && top_k && approx/ex_pred && pred_mode == "ex_pred" is implemented; every other
-combination raises (no silent fallback, per the north star).
+Implemented: mx_quant && top_k && approx/ex_pred && pred_mode == "ex_pred" (the pruned path) and
+mx_quant && !top_k (dense MXINT8 attention, what the reference runs in the last block of each
+model - same kernels with every key kept).  Every other combination raises (no silent fallback).
 """
 from typing import Optional
 
@@ -38,12 +39,16 @@ class PrunedAttentionCore(nn.Module):
         B, H, N, hd = q.shape
         buf = torch.empty((B, N, H, hd), dtype=torch.float32, device=q.device)
         # write straight into (B,N,H,hd): the reference's x.transpose(1,2).reshape(B,N,C) is free
-        ops.pruned_attention(q, k, v, self.mx_specs, self.k, scale=self.scale, out=buf.permute(0, 2, 1, 3),
+        # k <= 0: dense MXINT8 attention (the reference's top_k=False blocks) = every key kept
+        top_k = self.k if self.k > 0 else k.shape[2]
+        ops.pruned_attention(q, k, v, self.mx_specs, top_k, scale=self.scale, out=buf.permute(0, 2, 1, 3),
                              key_bias=key_bias)
         return buf.reshape(B, N, H * hd)
 
 
 def _require_hot_path(mx_quant, top_k, approx, pred_mode, where):
+    if mx_quant and not top_k:
+        return          # dense MXINT8 attention (deit main.py:282-296: the last block runs top_k=False)
     if not (mx_quant and top_k and approx and pred_mode == "ex_pred"):
         raise NotImplementedError(
             f"{where}: only mx_quant=True, top_k=True, approx/ex_pred=True, pred_mode='ex_pred' is on the "
@@ -66,7 +71,7 @@ class QuantizedAttention(nn.Module):
         self.proj_drop = getattr(orig_attn, "proj_drop", nn.Identity())
         self.block_idx = block_idx
         self.current_timestep = 0
-        self.core = PrunedAttentionCore(mx_specs, k, scale=self.scale)
+        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale)
 
     def forward(self, x):
         B, N, C = x.shape
@@ -98,7 +103,7 @@ class Attention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.block_idx = block_idx
         self.current_timestep = 0
-        self.core = PrunedAttentionCore(mx_specs, k, scale=self.scale)
+        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale)
 
     def forward(self, x):
         B, N, C = x.shape
@@ -131,7 +136,7 @@ class MXSelfAttention(nn.Module):
             raise NotImplementedError("anal / exclude_timesteps (dense steps) are out of scope")
         self.block_idx = block_idx
         # reference: scale_factor = 1 / math.sqrt(q.size(-1)) applied as an fp32 scalar (:647-653)
-        self.core = PrunedAttentionCore(mx_specs, k, scale=1.0 / (self.head_dim ** 0.5))
+        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=1.0 / (self.head_dim ** 0.5))
         return self
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs):

@@ -343,3 +343,22 @@ def test_cross_attention_module_shim(mxq):
     with torch.no_grad():
         want = m.to_out(ref["out"].transpose(1, 2).reshape(B, N, dim).cuda())
     assert float((y - want).abs().max()) <= 1e-3 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("B,H,N,hd,bfloat", [(2, 3, 197, 64, 32), (1, 2, 256, 72, 16), (1, 1, 50, 96, 32)])
+def test_dense_attention_top_k_false(mxq, B, H, N, hd, bfloat):
+    """The reference's top_k=False blocks (last block of each model, deit main.py:282-296): dense MXINT8
+    attention == every key kept.  Checked against the oracle and through the DeiT shim."""
+    q, k, v = make_qkv(B, H, N, hd, seed=9, kind="randn")
+    specs = mx_specs(bfloat, False)
+    out, mask = mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), specs, N, return_mask=True)
+    assert bool(unpack_mask(mask, N).all())
+    ref = O.pruned_attention(q, k, v, N, bfloat=bfloat, integer_scores=True)
+    assert_out_close(out.cpu(), ref, v, N, bfloat, OUT_TOL)
+    r = mxq.predict_topk(q.cuda(), k.cuda(), specs, N, return_idx=True)
+    assert torch.equal(r["idx"].cpu().to(torch.int64), torch.arange(N).expand(B, H, N, N))
+
+    from mx_quantization_b200.modules import PrunedAttentionCore
+    core = PrunedAttentionCore(specs, 0)           # k = 0 <=> top_k=False
+    y = core(q.cuda(), k.cuda(), v.cuda())
+    assert torch.equal(y, out.permute(0, 2, 1, 3).reshape(B, N, H * hd))
