@@ -556,7 +556,9 @@ k_attend_pair(const AttnParams p) {
                         float tv = __fmul_rn(s, p.scale);
                         if (BIAS) tv = __fadd_rn(tv, s_bias[kb0 + c]);
                         mb4[c & 3] = fmaxf(mb4[c & 3], ((m0 >> c) & 1u) ? tv : -INFINITY);
+                        ra[c] = __float_as_uint(tv);
                     }
+                    tmem_st_16x32bx2_s64_x32(my_tmem + 128 * (t >> 1), ra);     // pass B reads t, not s
                 }
                 tmem_ld_wait();
                 if (t + 2 < nwin) tmem_ld_16x32bx2_s64_x32(my_tmem + 128 * ((t >> 1) + 1), ra);
@@ -570,10 +572,13 @@ k_attend_pair(const AttnParams p) {
                         float tv = __fmul_rn(s, p.scale);
                         if (BIAS) tv = __fadd_rn(tv, s_bias[kb1 + c]);
                         mb4[c & 3] = fmaxf(mb4[c & 3], ((m1 >> c) & 1u) ? tv : -INFINITY);
+                        rb[c] = __float_as_uint(tv);
                     }
+                    tmem_st_16x32bx2_s64_x32(my_tmem + 128 * (t >> 1) + 32, rb);
                 }
             }
         }
+        tmem_st_wait();
         float m = fmaxf(fmaxf(mb4[0], mb4[1]), fmaxf(mb4[2], mb4[3]));
         m = fmaxf(m, __shfl_xor_sync(FULL, m, 16));
         const float m_use = (m == -INFINITY) ? 0.f : m;             // no kept key
@@ -589,10 +594,7 @@ k_attend_pair(const AttnParams p) {
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                float s = __uint_as_float(r[c]);
-                if (bf16) s = bf16_half_away(s);
-                float tv = __fmul_rn(s, p.scale);
-                if (BIAS) tv = __fadd_rn(tv, s_bias[col + 64 * part + c]);
+                const float tv = __uint_as_float(r[c]);             // bf16?(s) * scale (+ bias), from pass A
                 const float ex = exp_nonpos(__fsub_rn(tv, m_use));
                 const float ev = ((mwt >> c) & 1u) ? ex : 0.f;
                 sum4[c & 3] += ev;
