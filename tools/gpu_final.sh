@@ -24,6 +24,6 @@ python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/pla
 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 120 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches_$TAG.log 2>&1
 python tools/prof_layer.py deit_base_c2 3 > gpurun_out/plain_full_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"k_predict_topk_tc|k_attend_umma|k_prep_v" -s 3 -c 3 \
+ncu --set full --clock-control none --import-source on -k regex:"k_predict_topk_tc|k_attend_pair|k_attend_umma|k_prep_v" -s 3 -c 3 \
     -o gpurun_out/prof_full_$TAG python tools/prof_layer.py deit_base_c2 3 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_full_$TAG.log
