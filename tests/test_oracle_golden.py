@@ -163,3 +163,23 @@ def test_cross_attention_with_key_bias(name):
     r2 = O.pruned_attention(d["q"], d["k"], d["v"], m["top_k"], scale=1.0 / (m["hd"] ** 0.5),
                             bfloat=m["bfloat"], flush=m["flush"], key_bias=bias, integer_scores=True)
     assert torch.equal(r2["idx"], d["idx"])
+
+
+def test_coverage_rate_matches_reference_analysis():
+    """coverage rate from the kept-key bitmask == funcs/analysis.py:56-110 total_chosen_k
+    (values in tests/golden/analysis_coverage.json were produced by the reference function)."""
+    import json
+    from mx_quantization_b200.analysis import coverage_rate, topk_overlap
+    here = os.path.dirname(os.path.abspath(__file__))
+    want = json.load(open(os.path.join(here, "golden", "analysis_coverage.json")))
+    for name, cov in want.items():
+        z = np.load(os.path.join(here, "golden", name + ".npz"))
+        idx = torch.from_numpy(z["idx"].astype(np.int64))
+        n_keys = int(z["meta"][2])
+        words = O.idx_to_mask_words(idx, n_keys)
+        mask = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+        assert abs(coverage_rate(mask) - cov) < 1e-12
+        assert bool((topk_overlap(mask, idx) == 1.0).all())
+        other = torch.from_numpy(z["topk_idx_torch"].astype(np.int64))
+        ov = topk_overlap(mask, other)                  # torch.topk picks other members among ties
+        assert float(ov.min()) >= 0.0 and float(ov.max()) <= 1.0
