@@ -762,15 +762,38 @@ k_prep_v(const VPrepParams p) {
         }
         const int e = mx_shared_exp(mx);
         const bool dead = p.flush && e <= -127;
-        const float wgt = exp2i(e - 6);
+        if (mx != 0u && !dead && e >= -120 && e <= 126) {
+            // codes without F2I / I2F (same arithmetic as the K1 quantizer): FFMA, clamp, FADD.RM against
+            // 2^23 + 0x4300 -> bf16 pattern of 128 + c in the low half; (128 + c) * w - 128 * w = c * w
+            const float s1 = exp2i(6 - e);
+            const __nv_bfloat162 w2 = u32_as_bf2(bf16_pow2_bits(e - 6) * 0x00010001u);
+            const __nv_bfloat162 nw2 = u32_as_bf2((bf16_pow2_bits(e + 1) | 0x8000u) * 0x00010001u);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float f[8];
+            for (int q = 0; q < 4; ++q) {
+                uint32_t ow[4];
 #pragma unroll
-            for (int tt = 0; tt < 8; ++tt) f[tt] = (float)mx_code(xb[q * 8 + tt], e, dead) * wgt;
-            *reinterpret_cast<uint4*>(dst + v_op_offset(O, w * 4 + q, d)) =
-                make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]), pack_bf16_trunc(f[4], f[5]),
-                           pack_bf16_trunc(f[6], f[7]));
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t x0 = xb[q * 8 + 2 * h], x1 = xb[q * 8 + 2 * h + 1];
+                    const float v0 = fminf(fmaf(fabsf(__uint_as_float(x0)), s1, 0.5f), 127.0f);
+                    const float v1 = fminf(fmaf(fabsf(__uint_as_float(x1)), s1, 0.5f), 127.0f);
+                    const uint32_t v2 = __byte_perm(__float_as_uint(__fadd_rd(v0, 8405760.0f)),
+                                                    __float_as_uint(__fadd_rd(v1, 8405760.0f)), 0x5410);
+                    const uint32_t sx = __byte_perm(x0, x1, 0x7632) & 0x80008000u;
+                    ow[h] = bf2_as_u32(__hfma2(u32_as_bf2(v2), w2, nw2)) ^ sx;
+                }
+                *reinterpret_cast<uint4*>(dst + v_op_offset(O, w * 4 + q, d)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+        } else {
+            const float wgt = exp2i(e - 6);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float f[8];
+#pragma unroll
+                for (int tt = 0; tt < 8; ++tt) f[tt] = (float)mx_code(xb[q * 8 + tt], e, dead) * wgt;
+                *reinterpret_cast<uint4*>(dst + v_op_offset(O, w * 4 + q, d)) =
+                    make_uint4(pack_bf16_trunc(f[0], f[1]), pack_bf16_trunc(f[2], f[3]), pack_bf16_trunc(f[4], f[5]),
+                               pack_bf16_trunc(f[6], f[7]));
+            }
         }
     }
 }
