@@ -164,6 +164,27 @@ int mxp_pruned_attention_biased(const float* q, int64_t q_sB, int64_t q_sH, int6
                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * MX Linear (the step either side of the attention core): the forward of the
+ * reference's mx.Linear (microxscaling/mx/linear.py:20-103) for MXINT8 activations and weights,
+ *     y = A1( A1( MXq(A1(x)) . MXq(A1(W))^T ) + A1(bias) )
+ * both operands MX-quantized along in_features in blocks of 32 (quantize_mx_op, axes=[-1]),
+ * A1 = quantize_elemwise_op (bf16 half-away rounding for bfloat 16, identity for 32).
+ *   x     fp32 (M, K) rows with stride ldx      W   fp32 (N, K) rows with stride ldw
+ *   out   fp32 (M, N) rows with stride ldo      bias fp32 (N) or NULL
+ * The weight is quantized once into the GEMM's operand order (mxp_mx_linear_prepare_weight ->
+ * w_op, mxp_mx_linear_weight_bytes bytes); mxp_mx_linear quantizes the activations into the
+ * workspace and runs the bf16 x bf16 -> fp32 GEMM on the tensor cores (the MXINT8 values are exact
+ * in bf16).  K must be a multiple of 64, N a multiple of 4.
+ */
+size_t mxp_mx_linear_weight_bytes(int N, int K);
+size_t mxp_mx_linear_workspace_bytes(int M, int N, int K);
+int mxp_mx_linear_prepare_weight(const float* w, int64_t ldw, int N, int K, int bfloat_bits, int flush,
+                                 void* w_op, void* stream);
+int mxp_mx_linear(const float* x, int64_t ldx, int M, int K, const void* w_op, int N, const float* bias,
+                  int bfloat_bits, int flush, float* out, int64_t ldo,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Measurement aid: same as mxp_pruned_attention (tcgen05 path), but brackets the three kernels
  * (predict+top-k, V operand prep, exact attention) with CUDA events on `stream`, SYNCHRONISES, and
  * returns their durations in milliseconds in kernel_ms[0..2].  bench.py's roofline uses this.

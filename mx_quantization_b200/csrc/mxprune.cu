@@ -11,6 +11,7 @@
 #include "mxprune_attend.cuh"
 #include "mxprune_predict_tc.cuh"
 #include "mxprune_predict_long_tc.cuh"
+#include "mxprune_linear.cuh"
 
 using namespace mxp;
 
@@ -1074,6 +1075,80 @@ int mxp_pruned_attention_biased(const float* q, int64_t q_sB, int64_t q_sH, int6
     return pruned_attention_impl(q, q_sB, q_sH, q_sN, k, k_sB, k_sH, k_sN, v, v_sB, v_sH, v_sN, B, H, Nq, Nk, hd,
                                  top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, key_bias, kb_sB, mask_out,
                                  workspace, workspace_bytes, stream);
+}
+
+// ---- MX Linear ---------------------------------------------------------------------
+static int check_linear(int M, int N, int K, int bfloat_bits) {
+    if (M <= 0 || N <= 0 || K <= 0) return fail(MXP_E_BADARG, "empty shape M=%d N=%d K=%d", M, N, K);
+    if (K % GL_BK) return fail(MXP_E_UNSUPPORTED, "in_features %d: need a multiple of %d", K, GL_BK);
+    if (N & 3) return fail(MXP_E_UNSUPPORTED, "out_features %d: need a multiple of 4", N);
+    if (bfloat_bits != 16 && bfloat_bits != 32) return fail(MXP_E_UNSUPPORTED, "bfloat=%d: only 16 or 32 are on the path", bfloat_bits);
+    return MXP_OK;
+}
+static int launch_quantize_gemm_operand(const float* x, int64_t ld, int rows, int K, int rows_tile, int bf16, int flush,
+                                        void* op, cudaStream_t st) {
+    const int rows_pad = (rows + rows_tile - 1) / rows_tile * rows_tile;
+    const int64_t ntask = (int64_t)rows_pad * (K / 32);
+    int64_t blocks = (ntask + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_quantize_gemm_operand<<<(unsigned)blocks, 256, 0, st>>>(x, ld, rows, rows_pad, K, rows_tile, bf16, flush, (unsigned char*)op);
+    return check_launch("k_quantize_gemm_operand");
+}
+
+size_t mxp_mx_linear_weight_bytes(int N, int K) {
+    return (size_t)((N + GL_BN - 1) / GL_BN) * GL_BN * (size_t)K * 2;
+}
+size_t mxp_mx_linear_workspace_bytes(int M, int N, int K) {
+    return align256((size_t)((M + GL_BM - 1) / GL_BM) * GL_BM * (size_t)K * 2) + align256((size_t)N * 4);
+}
+
+int mxp_mx_linear_prepare_weight(const float* w, int64_t ldw, int N, int K, int bfloat_bits, int flush, void* w_op,
+                                 void* stream) {
+    g_launches = 0;
+    int rc = check_linear(1, N, K, bfloat_bits);
+    if (rc) return rc;
+    if (!w || !w_op || ((uintptr_t)w & 15) || ((uintptr_t)w_op & 15) || (ldw & 3) || ldw < K)
+        return fail(MXP_E_BADARG, "weight: null / misaligned pointer or row stride");
+    return launch_quantize_gemm_operand(w, ldw, N, K, GL_BN, bfloat_bits == 16, flush != 0, w_op, (cudaStream_t)stream);
+}
+
+int mxp_mx_linear(const float* x, int64_t ldx, int M, int K, const void* w_op, int N, const float* bias,
+                  int bfloat_bits, int flush, float* out, int64_t ldo, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+    g_launches = 0;
+    int rc = check_linear(M, N, K, bfloat_bits);
+    if (rc) return rc;
+    if (!x || !w_op || !out || ((uintptr_t)x & 15) || ((uintptr_t)w_op & 15) || ((uintptr_t)out & 15) || (ldx & 3) ||
+        (ldo & 3) || ldx < K || ldo < N)
+        return fail(MXP_E_BADARG, "x / w_op / out: null or misaligned pointer, or bad row stride");
+    const size_t need = mxp_mx_linear_workspace_bytes(M, N, K);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
+        return fail(MXP_E_BADARG, "workspace: need %zu bytes, 256-byte aligned", need);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* a_op = (unsigned char*)workspace;
+    float* rbias = (float*)(a_op + align256((size_t)((M + GL_BM - 1) / GL_BM) * GL_BM * (size_t)K * 2));
+    if ((rc = launch_quantize_gemm_operand(x, ldx, M, K, GL_BM, bfloat_bits == 16, flush != 0, a_op, st))) return rc;
+    if (bias) {
+        k_round_bias<<<(N + 255) / 256, 256, 0, st>>>(bias, rbias, N, bfloat_bits == 16);
+        if ((rc = check_launch("k_round_bias"))) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_mx_linear_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    LinearParams lp{};
+    lp.a_op = a_op; lp.w_op = (const unsigned char*)w_op; lp.bias = bias ? rbias : nullptr;
+    lp.out = out; lp.ldo = ldo; lp.M = M; lp.N = N; lp.K = K; lp.bf16 = bfloat_bits == 16; lp.stages = 2;
+    const GemmOpLayout L = gemm_op_layout(K);
+    // two CTAs per SM: 2 x 256 TMEM columns; the shared-memory request keeps a third one out
+    size_t dyn = lp.stages * (L.a_stage + L.b_stage) + 2048;
+    const size_t floor_bytes = (size_t)232448 / 3 + 1024;
+    if (dyn < floor_bytes) dyn = floor_bytes;
+    dim3 grid((unsigned)((M + GL_BM - 1) / GL_BM), (unsigned)((N + GL_BN - 1) / GL_BN));
+    k_mx_linear_umma<<<grid, GL_T, dyn, st>>>(lp);
+    return check_launch("k_mx_linear_umma");
 }
 
 int mxp_pruned_attention_profile(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,

@@ -115,7 +115,8 @@ struct BlockQ {
 };
 
 // xv: the block's 32 fp32 bit patterns (elements >= nd are zero).  A1 + A2 + operand formation.
-template <bool CODES>
+// PRED = false skips the predictor operand and the sign word (callers that only need c * 2^(e-6)).
+template <bool CODES, bool PRED = true>
 __device__ __forceinline__ void quantize_block_thread(uint32_t (&xv)[32], int nd, bool bf16, bool flush, BlockQ& r) {
     if (bf16) {
 #pragma unroll
@@ -165,10 +166,14 @@ __device__ __forceinline__ void quantize_block_thread(uint32_t (&xv)[32], int nd
                 const uint32_t v2 = __byte_perm(fl[2 * p], fl[2 * p + 1], 0x5410);
                 const uint32_t sx = __byte_perm(xv[8 * c + 2 * p], xv[8 * c + 2 * p + 1], 0x7632) & 0x80008000u;
                 const uint32_t rr = bf2_as_u32(__hfma2(u32_as_bf2(v2), w2, nw2)) ^ sx;
-                const uint32_t m = __hlt2_mask(u32_as_bf2(rr), zero2);      // -0 is not < 0: zero codes count as +
                 ow[p] = rr;
-                pw[p] = (m & 0x80008000u) | e2;
-                sw |= m & (0x00010001u << (4 * c + p));
+                if (PRED) {
+                    const uint32_t m = __hlt2_mask(u32_as_bf2(rr), zero2);  // -0 is not < 0: zero codes count as +
+                    pw[p] = (m & 0x80008000u) | e2;
+                    sw |= m & (0x00010001u << (4 * c + p));
+                } else {
+                    pw[p] = 0u;
+                }
             }
             r.op[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             r.pp[c] = make_uint4(pw[0], pw[1], pw[2], pw[3]);

@@ -172,3 +172,26 @@ class MXCrossAttention(MXSelfAttention):
         x = self.to_out(self.core(q, k, v, key_bias=bias))
         self.current_timestep += 1
         return x
+
+
+class MxLinear(nn.Linear):
+    """Drop-in for the reference's mx.Linear (microxscaling/mx/linear.py:227-320) on the MXINT8
+    configuration of the workloads: same constructor (in_features, out_features, bias, mx_specs),
+    forward = ops.mx_linear.  The MX-quantized weight operand is cached and rebuilt when the weight
+    tensor changes (inference: once)."""
+
+    def __init__(self, in_features, out_features, bias=True, mx_specs=None, name=None):
+        super().__init__(in_features, out_features, bias)
+        resolve_specs(mx_specs)
+        self.mx_specs = mx_specs
+        self.name = name
+        self._w_op = None
+        self._w_key = None
+
+    def forward(self, inputs):
+        key = (self.weight.data_ptr(), self.weight._version, str(self.weight.device))
+        if self._w_op is None or self._w_key != key:
+            self._w_op = ops.mx_linear_prepare_weight(self.weight.detach(), self.mx_specs)
+            self._w_key = key
+        b = None if self.bias is None else self.bias.detach()
+        return ops.mx_linear(inputs, self._w_op, b, self.mx_specs, out_features=self.out_features)

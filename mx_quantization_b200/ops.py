@@ -242,3 +242,53 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
             _kernel_ms[:] = [float(x) for x in ms]
     _lib.check(rc, "mxp_pruned_attention")
     return (out, mask) if return_mask else out
+
+
+# ---- MX Linear -------------------------------------------------------------------
+def mx_linear_prepare_weight(weight: torch.Tensor, mx_specs) -> torch.Tensor:
+    """MX-quantize an (out_features, in_features) fp32 weight once into the GEMM's operand order."""
+    sp = resolve_specs(mx_specs)
+    lib = _lib.load()
+    if weight.dim() != 2 or weight.dtype != torch.float32 or not weight.is_cuda:
+        raise ValueError("weight must be a CUDA fp32 (out_features, in_features) tensor")
+    w = weight if weight.stride(1) == 1 else weight.contiguous()
+    N, K = w.shape
+    with torch.cuda.device(w.device):
+        w_op = torch.empty((lib.mxp_mx_linear_weight_bytes(N, K),), dtype=torch.uint8, device=w.device)
+        rc = lib.mxp_mx_linear_prepare_weight(_ptr(w), w.stride(0), N, K, sp.bfloat_bits, int(sp.flush),
+                                              _ptr(w_op), _stream())
+    _lib.check(rc, "mxp_mx_linear_prepare_weight")
+    return w_op
+
+
+def mx_linear(x: torch.Tensor, weight, bias: Optional[torch.Tensor], mx_specs,
+              out_features: Optional[int] = None) -> torch.Tensor:
+    """Forward of the reference's mx.Linear (microxscaling/mx/linear.py:20-103) for MXINT8:
+    y = A1(A1(MXq(A1(x)) @ MXq(A1(W))^T) + A1(bias)).  ``weight`` is either the fp32 (N,K) tensor or
+    the operand returned by mx_linear_prepare_weight (then pass out_features)."""
+    sp = resolve_specs(mx_specs)
+    lib = _lib.load()
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise ValueError("x must be a CUDA fp32 tensor")
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    if weight.dtype == torch.uint8:
+        if out_features is None:
+            raise ValueError("out_features is required with a prepared weight operand")
+        w_op, N = weight, int(out_features)
+    else:
+        N = weight.shape[0]
+        w_op = mx_linear_prepare_weight(weight, mx_specs)
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError("bias must be a contiguous fp32 tensor with out_features elements")
+    with torch.cuda.device(x.device):
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        ws_bytes = lib.mxp_mx_linear_workspace_bytes(M, N, K)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+        rc = lib.mxp_mx_linear(_ptr(x2), x2.stride(0), M, K, _ptr(w_op), N, _ptr(bias), sp.bfloat_bits,
+                               int(sp.flush), _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream())
+    _lib.check(rc, "mxp_mx_linear")
+    return out.reshape(*x.shape[:-1], N)

@@ -344,3 +344,18 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
     res["true_vals"] = vals
     res["out"] = sparse_softmax_pv(vals, idx, v, n_keys, bfloat, flush)
     return res
+
+
+def mx_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              bfloat: int = 32, flush: bool = False) -> torch.Tensor:
+    """Forward of the reference's mx.Linear for MXINT8 activations and weights
+    (microxscaling/mx/linear.py:20-103): element-wise A1 on input / weight / bias (:29-47), MX
+    quantization of both along in_features (:57-72, axes=[-1]), fp32 F.linear (:83), A1 on the
+    output (:85-87), + bias and A1 again (:89-93)."""
+    x, weight = x.to(torch.float32), weight.to(torch.float32)
+    qx = fake_quant_mxint8(x, axis=-1, bfloat=bfloat, flush_subnorms=flush)
+    qw = fake_quant_mxint8(weight, axis=-1, bfloat=bfloat, flush_subnorms=flush)
+    out = _elemwise_out(torch.nn.functional.linear(qx, qw), bfloat)
+    if bias is not None:
+        out = _elemwise_out(out + _elemwise_out(bias.to(torch.float32), bfloat), bfloat)
+    return out

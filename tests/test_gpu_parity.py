@@ -362,3 +362,55 @@ def test_dense_attention_top_k_false(mxq, B, H, N, hd, bfloat):
     core = PrunedAttentionCore(specs, 0)           # k = 0 <=> top_k=False
     y = core(q.cuda(), k.cuda(), v.cuda())
     assert torch.equal(y, out.permute(0, 2, 1, 3).reshape(B, N, H * hd))
+
+
+# ---- MX Linear (mx.Linear forward, MXINT8 activations and weights) ----------------------
+
+def _check_linear(y, ref, bfloat):
+    err = (y - ref).abs()
+    scale = float(ref.abs().max())
+    if bfloat == 32:
+        # exact products, fp32 accumulation in a different order from the reference's BLAS
+        assert float(err.max()) <= 2e-5 * scale, float(err.max()) / scale
+    else:
+        # the two bf16 roundings of the output flip where the fp32 sums straddle a rounding tie
+        assert float(err.max()) <= 2.0 ** -7 * scale
+        assert float((err > 0).float().mean()) <= 0.02
+
+
+@pytest.mark.parametrize("name", ["mx_linear_qkv", "mx_linear_bf16", "mx_linear_nobias"])
+def test_mx_linear_reference_golden(mxq, name):
+    """Outputs of the unmodified reference mx.Linear forward (tests/golden/make_golden_linear.py)."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    M, K, N, has_bias, bfloat, flush = (int(v) for v in z["meta"])
+    x, w = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["w"]).cuda()
+    b = torch.from_numpy(z["b"]).cuda() if has_bias else None
+    y = mxq.mx_linear(x, w, b, mx_specs(bfloat, bool(flush)))
+    _check_linear(y.cpu(), torch.from_numpy(z["y"]), bfloat)
+
+
+@pytest.mark.parametrize("M,K,N,bias,bfloat", [
+    (300, 768, 2304, True, 32),        # DeiT-base qkv projection
+    (257, 1152, 1152, True, 16),       # DiT / PixArt output projection, bfloat 16
+    (64, 64, 4, False, 32),
+    (1000, 3072, 768, True, 32),       # DeiT-base MLP fc2
+])
+def test_mx_linear_vs_oracle(mxq, M, K, N, bias, bfloat):
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn(2, M // 2 if M % 2 == 0 else M, K, generator=g)[: 2 if M % 2 == 0 else 1]
+    x = x * torch.exp(0.5 * torch.randn(*x.shape[:-1], 1, generator=g))
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    b = torch.randn(N, generator=g) * 0.1 if bias else None
+    specs = mx_specs(bfloat, False)
+    from mx_quantization_b200.modules import MxLinear
+    lin = MxLinear(K, N, bias=bias, mx_specs=specs).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(w)
+        if bias:
+            lin.bias.copy_(b)
+        y = lin(x.cuda())
+        y2 = lin(x.cuda())                                   # cached weight operand
+    assert torch.equal(y, y2)
+    ref = O.mx_linear(x, w, b, bfloat=bfloat)
+    assert y.shape == ref.shape
+    _check_linear(y.cpu(), ref, bfloat)

@@ -183,3 +183,25 @@ def test_coverage_rate_matches_reference_analysis():
         other = torch.from_numpy(z["topk_idx_torch"].astype(np.int64))
         ov = topk_overlap(mask, other)                  # torch.topk picks other members among ties
         assert float(ov.min()) >= 0.0 and float(ov.max()) <= 1.0
+
+
+LINEAR_CASES = ["mx_linear_qkv", "mx_linear_bf16", "mx_linear_nobias"]
+
+
+def load_linear(name):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    M, K, N, has_bias, bfloat, flush = (int(v) for v in z["meta"])
+    d = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    return d, dict(M=M, K=K, N=N, has_bias=bool(has_bias), bfloat=bfloat, flush=bool(flush))
+
+
+@pytest.mark.parametrize("name", LINEAR_CASES)
+def test_mx_linear_oracle_matches_reference(name):
+    """oracle restatement of mx.Linear's forward vs outputs of the reference
+    (tests/golden/make_golden_linear.py).  Same BLAS, same thread count -> bit-equal."""
+    d, m = load_linear(name)
+    torch.set_num_threads(1)
+    y = O.mx_linear(d["x"], d["w"], d.get("b"), bfloat=m["bfloat"], flush=m["flush"])
+    assert float((y - d["y"]).abs().max()) <= 1e-6 * float(d["y"].abs().max())
+    if m["bfloat"] == 32:
+        assert torch.equal(y, d["y"])
