@@ -1140,14 +1140,19 @@ int mxp_mx_linear(const float* x, int64_t ldx, int M, int K, const void* w_op, i
     }
     LinearParams lp{};
     lp.a_op = a_op; lp.w_op = (const unsigned char*)w_op; lp.bias = bias ? rbias : nullptr;
-    lp.out = out; lp.ldo = ldo; lp.M = M; lp.N = N; lp.K = K; lp.bf16 = bfloat_bits == 16; lp.stages = 2;
+    lp.out = out; lp.ldo = ldo; lp.M = M; lp.N = N; lp.K = K; lp.bf16 = bfloat_bits == 16; lp.stages = 4;
     const GemmOpLayout L = gemm_op_layout(K);
-    // two CTAs per SM: 2 x 256 TMEM columns; the shared-memory request keeps a third one out
-    size_t dyn = lp.stages * (L.a_stage + L.b_stage) + 2048;
-    const size_t floor_bytes = (size_t)232448 / 3 + 1024;
-    if (dyn < floor_bytes) dyn = floor_bytes;
-    dim3 grid((unsigned)((M + GL_BM - 1) / GL_BM), (unsigned)((N + GL_BN - 1) / GL_BN));
-    k_mx_linear_umma<<<grid, GL_T, dyn, st>>>(lp);
+    // persistent: one CTA per SM (4 stages of 48 KiB, 512 TMEM columns for the double-buffered accumulator)
+    const size_t dyn = lp.stages * (L.a_stage + L.b_stage) + 4096;
+    const int ntiles = ((M + GL_BM - 1) / GL_BM) * ((N + GL_BN - 1) / GL_BN);
+    int sms = 148;
+    {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            sms = n;
+    }
+    k_mx_linear_umma<<<(unsigned)(ntiles < sms ? ntiles : sms), GL_T, dyn, st>>>(lp);
     return check_launch("k_mx_linear_umma");
 }
 

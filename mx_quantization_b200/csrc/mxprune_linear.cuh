@@ -78,28 +78,38 @@ __global__ void k_round_bias(const float* __restrict__ b, float* __restrict__ o,
     if (i < N) o[i] = bf16 ? bf16_half_away(b[i]) : b[i];
 }
 
-__global__ void __launch_bounds__(GL_T, 2)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epilogue_barrier() {               // the 128 epilogue threads
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// Persistent: one CTA per SM walks the output tiles (feature tile fastest, so the CTAs that share an
+// activation tile run together and the weight operand stays L2-resident).  The accumulator is
+// double-buffered in TMEM (2 x 256 columns): the epilogue of tile i overlaps the main loop of tile i+1.
+__global__ void __launch_bounds__(GL_T, 1)
 k_mx_linear_umma(const LinearParams p) {
     extern __shared__ __align__(1024) unsigned char smem_gl[];
     const GemmOpLayout L = gemm_op_layout(p.K);
     const int stages = p.stages;
     const size_t stage_bytes = L.a_stage + L.b_stage;
-    float* s_bias = reinterpret_cast<float*>(smem_gl + stages * stage_bytes);                 // [256]
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_gl + stages * stage_bytes + 1024);   // [stages]
-    uint64_t* bar_empty = bar_full + 8;                                                        // [stages]
-    uint64_t* bar_acc = bar_empty + 8;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
+    float* s_bias = reinterpret_cast<float*>(smem_gl + stages * stage_bytes);                 // [2][256]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_gl + stages * stage_bytes + 2048);   // [8]
+    uint64_t* bar_empty = bar_full + 8;                                                        // [8]
+    uint64_t* bar_acc_full = bar_empty + 8;                                                    // [2]
+    uint64_t* bar_acc_empty = bar_acc_full + 2;                                                // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
-    const int n0 = tile_n * GL_BN;
+    const int tiles_n = (p.N + GL_BN - 1) / GL_BN, tiles_m = (p.M + GL_BM - 1) / GL_BM;
+    const int ntiles = tiles_n * tiles_m;
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-        mbar_init(bar_acc, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], 1); }
     }
-    if (warp == 1) tmem_alloc(s_tmem, 256u);
-    for (int j = tid; j < GL_BN; j += GL_T) s_bias[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+    if (warp == 1) tmem_alloc(s_tmem, 512u);
     tcgen05_fence_before_sync();
     __syncthreads();
     tcgen05_fence_after_sync();
@@ -108,75 +118,98 @@ k_mx_linear_umma(const LinearParams p) {
     if (warp == 0) {
         // ---------------- TMA producer
         if (lane == 0) {
-            const unsigned char* a_src = p.a_op + (size_t)tile_m * L.ksteps * L.a_stage;
-            const unsigned char* b_src = p.w_op + (size_t)tile_n * L.ksteps * L.b_stage;
-            for (int ks = 0; ks < L.ksteps; ++ks) {
-                const int s = ks % stages;
-                if (ks >= stages) mbar_wait(&bar_empty[s], (uint32_t)(((ks / stages) - 1) & 1));
-                unsigned char* dst = smem_gl + (size_t)s * stage_bytes;
-                mbar_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
-                tma_bulk_g2s(dst, a_src + (size_t)ks * L.a_stage, (uint32_t)L.a_stage, &bar_full[s]);
-                tma_bulk_g2s(dst + L.a_stage, b_src + (size_t)ks * L.b_stage, (uint32_t)L.b_stage, &bar_full[s]);
+            int it = 0;                                             // running stage counter across tiles
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int tile_m = t / tiles_n, tile_n = t - tile_m * tiles_n;
+                const unsigned char* a_src = p.a_op + (size_t)tile_m * L.ksteps * L.a_stage;
+                const unsigned char* b_src = p.w_op + (size_t)tile_n * L.ksteps * L.b_stage;
+                for (int ks = 0; ks < L.ksteps; ++ks, ++it) {
+                    const int s = it % stages;
+                    mbar_wait(&bar_empty[s], (uint32_t)(((it / stages) & 1) ^ 1));      // first lap passes at once
+                    unsigned char* dst = smem_gl + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
+                    tma_bulk_g2s(dst, a_src + (size_t)ks * L.a_stage, (uint32_t)L.a_stage, &bar_full[s]);
+                    tma_bulk_g2s(dst + L.a_stage, b_src + (size_t)ks * L.b_stage, (uint32_t)L.b_stage, &bar_full[s]);
+                }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16_f32(GL_BM, GL_BN);
-            for (int ks = 0; ks < L.ksteps; ++ks) {
-                const int s = ks % stages;
-                mbar_wait(&bar_full[s], (uint32_t)((ks / stages) & 1));
+            int it = 0, i = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+                const int buf = i & 1;
+                mbar_wait(&bar_acc_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));         // epilogue has drained this buffer
                 tcgen05_fence_after_sync();
-                const unsigned char* sa = smem_gl + (size_t)s * stage_bytes;
-                const unsigned char* sb = sa + L.a_stage;
+                const uint32_t acc = tmem + (uint32_t)(buf * GL_BN);
+                for (int ks = 0; ks < L.ksteps; ++ks, ++it) {
+                    const int s = it % stages;
+                    mbar_wait(&bar_full[s], (uint32_t)((it / stages) & 1));
+                    tcgen05_fence_after_sync();
+                    const unsigned char* sa = smem_gl + (size_t)s * stage_bytes;
+                    const unsigned char* sb = sa + L.a_stage;
 #pragma unroll
-                for (int k4 = 0; k4 < GL_BK / 16; ++k4) {
-                    const uint64_t da = umma_smem_desc(smem_u32(sa + (size_t)(2 * k4) * GL_BM * 16), GL_BM * 16, 128);
-                    const uint64_t db = umma_smem_desc(smem_u32(sb + (size_t)(2 * k4) * GL_BN * 16), GL_BN * 16, 128);
-                    umma_bf16_ss(tmem, da, db, idesc, ks > 0 || k4 > 0);
+                    for (int k4 = 0; k4 < GL_BK / 16; ++k4) {
+                        const uint64_t da = umma_smem_desc(smem_u32(sa + (size_t)(2 * k4) * GL_BM * 16), GL_BM * 16, 128);
+                        const uint64_t db = umma_smem_desc(smem_u32(sb + (size_t)(2 * k4) * GL_BN * 16), GL_BN * 16, 128);
+                        umma_bf16_ss(acc, da, db, idesc, ks > 0 || k4 > 0);
+                    }
+                    umma_commit(&bar_empty[s]);                     // stage free once these MMAs have read it
                 }
-                umma_commit(&bar_empty[s]);                         // stage free once these MMAs have read it
+                umma_commit(&bar_acc_full[buf]);                    // accumulator of this tile complete
             }
-            umma_commit(bar_acc);                                   // accumulator complete
         }
     } else {
         // ---------------- epilogue: warps 2..5 -> TMEM lane quarter (warp & 3), thread = output row
         const int q = warp & 3;
-        const int row = tile_m * GL_BM + q * 32 + lane;
-        mbar_wait(bar_acc, 0u);
-        tcgen05_fence_after_sync();
-        const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16);
-        float* orow = p.out + (int64_t)row * p.ldo + n0;
+        const int et = tid - 64;                                    // 0..127
         const bool bf16 = p.bf16 != 0;
+        int i = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+            const int tile_m = t / tiles_n, tile_n = t - tile_m * tiles_n;
+            const int n0 = tile_n * GL_BN, buf = i & 1;
+            float* sb = s_bias + buf * GL_BN;
+            for (int j = et; j < GL_BN; j += 128) sb[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+            epilogue_barrier();
+            mbar_wait(&bar_acc_full[buf], (uint32_t)((i >> 1) & 1));
+            tcgen05_fence_after_sync();
+            const int row = tile_m * GL_BM + q * 32 + lane;
+            const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GL_BN);
+            float* orow = p.out + (int64_t)row * p.ldo + n0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < GL_BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t0 + c0, r);
-            tmem_ld_wait();
-            if (row < p.M) {
+            for (int c0 = 0; c0 < GL_BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t0 + c0, r);
+                tmem_ld_wait();
+                if (row < p.M) {
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    if (n0 + c0 + 4 * v < p.N) {                    // N is a multiple of 4 (checked on the host)
-                        float o[4];
+                    for (int v = 0; v < 8; ++v) {
+                        if (n0 + c0 + 4 * v < p.N) {                // N is a multiple of 4 (checked on the host)
+                            float o[4];
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            float y = __uint_as_float(r[4 * v + t]);
-                            if (bf16) y = bf16_half_away(y);        // A1 on the matmul output   linear.py:89-91
-                            if (p.bias) {
-                                y = __fadd_rn(y, s_bias[c0 + 4 * v + t]);
-                                if (bf16) y = bf16_half_away(y);    // A1 after the bias add      linear.py:93-97
+                            for (int u = 0; u < 4; ++u) {
+                                float y = __uint_as_float(r[4 * v + u]);
+                                if (bf16) y = bf16_half_away(y);    // A1 on the matmul output   linear.py:85-87
+                                if (p.bias) {
+                                    y = __fadd_rn(y, sb[c0 + 4 * v + u]);
+                                    if (bf16) y = bf16_half_away(y);        // A1 after the bias add   linear.py:89-93
+                                }
+                                o[u] = y;
                             }
-                            o[t] = y;
+                            *reinterpret_cast<float4*>(orow + c0 + 4 * v) = make_float4(o[0], o[1], o[2], o[3]);
                         }
-                        *reinterpret_cast<float4*>(orow + c0 + 4 * v) = make_float4(o[0], o[1], o[2], o[3]);
                     }
                 }
             }
+            tcgen05_fence_before_sync();
+            epilogue_barrier();                                     // every epilogue thread has read its lanes
+            if (et == 0) mbar_arrive(&bar_acc_empty[buf]);
         }
     }
     tcgen05_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 256u);
+    if (warp == 1) tmem_dealloc(tmem, 512u);
 }
 
 }  // namespace mxp
