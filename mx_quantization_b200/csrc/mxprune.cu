@@ -1143,7 +1143,7 @@ int mxp_mx_linear(const float* x, int64_t ldx, int M, int K, const void* w_op, i
     lp.out = out; lp.ldo = ldo; lp.M = M; lp.N = N; lp.K = K; lp.bf16 = bfloat_bits == 16; lp.stages = 4;
     const GemmOpLayout L = gemm_op_layout(K);
     // persistent: one CTA per SM (4 stages of 48 KiB, 512 TMEM columns for the double-buffered accumulator)
-    const size_t dyn = lp.stages * (L.a_stage + L.b_stage) + 4096;
+    const size_t dyn = lp.stages * (L.a_stage + L.b_stage) + 2048 + 4 * 32 * 36 * 4 + 1024;
     const int ntiles = ((M + GL_BM - 1) / GL_BM) * ((N + GL_BN - 1) / GL_BN);
     int sms = 148;
     {

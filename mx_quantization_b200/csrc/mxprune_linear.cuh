@@ -95,7 +95,8 @@ k_mx_linear_umma(const LinearParams p) {
     const int stages = p.stages;
     const size_t stage_bytes = L.a_stage + L.b_stage;
     float* s_bias = reinterpret_cast<float*>(smem_gl + stages * stage_bytes);                 // [2][256]
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_gl + stages * stage_bytes + 2048);   // [8]
+    float* s_tr = s_bias + 2 * GL_BN;                                                          // [4 warps][32][36]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_gl + stages * stage_bytes + 2048 + 4 * 32 * 36 * 4);   // [8]
     uint64_t* bar_empty = bar_full + 8;                                                        // [8]
     uint64_t* bar_acc_full = bar_empty + 8;                                                    // [2]
     uint64_t* bar_acc_empty = bar_acc_full + 2;                                                // [2]
@@ -174,33 +175,36 @@ k_mx_linear_umma(const LinearParams p) {
             epilogue_barrier();
             mbar_wait(&bar_acc_full[buf], (uint32_t)((i >> 1) & 1));
             tcgen05_fence_after_sync();
-            const int row = tile_m * GL_BM + q * 32 + lane;
             const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GL_BN);
-            float* orow = p.out + (int64_t)row * p.ldo + n0;
+            // Coalesced stores: each warp transposes its 32 rows x 32 columns through shared memory
+            // (row pitch 36 words: conflict-free 128-bit writes and reads), so that 8 lanes write 128
+            // contiguous bytes of one output row instead of 32 lanes writing 16 bytes of 32 rows.
+            float* tr = s_tr + (warp - 2) * (32 * 36);
+            const int lr = lane >> 3, lc = (lane & 7) * 4;          // this lane's row (mod 4) and column group
+            const int row_base = tile_m * GL_BM + q * 32;
 #pragma unroll 1
             for (int c0 = 0; c0 < GL_BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(t0 + c0, r);
                 tmem_ld_wait();
-                if (row < p.M) {
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        if (n0 + c0 + 4 * v < p.N) {                // N is a multiple of 4 (checked on the host)
-                            float o[4];
+                for (int v = 0; v < 8; ++v)
+                    *reinterpret_cast<uint4*>(tr + lane * 36 + 4 * v) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+                __syncwarp();
+                const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + lc);
+                const bool col_ok = n0 + c0 + lc < p.N;             // N is a multiple of 4 (checked on the host)
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                float y = __uint_as_float(r[4 * v + u]);
-                                if (bf16) y = bf16_half_away(y);    // A1 on the matmul output   linear.py:85-87
-                                if (p.bias) {
-                                    y = __fadd_rn(y, sb[c0 + 4 * v + u]);
-                                    if (bf16) y = bf16_half_away(y);        // A1 after the bias add   linear.py:89-93
-                                }
-                                o[u] = y;
-                            }
-                            *reinterpret_cast<float4*>(orow + c0 + 4 * v) = make_float4(o[0], o[1], o[2], o[3]);
-                        }
+                for (int i8 = 0; i8 < 8; ++i8) {
+                    const int rl = lr + 4 * i8, row = row_base + rl;
+                    float4 y = *reinterpret_cast<const float4*>(tr + rl * 36 + lc);
+                    if (bf16) { y.x = bf16_half_away(y.x); y.y = bf16_half_away(y.y); y.z = bf16_half_away(y.z); y.w = bf16_half_away(y.w); }   // A1, linear.py:85-87
+                    if (p.bias) {
+                        y.x = __fadd_rn(y.x, b4.x); y.y = __fadd_rn(y.y, b4.y); y.z = __fadd_rn(y.z, b4.z); y.w = __fadd_rn(y.w, b4.w);
+                        if (bf16) { y.x = bf16_half_away(y.x); y.y = bf16_half_away(y.y); y.z = bf16_half_away(y.z); y.w = bf16_half_away(y.w); }   // :89-93
                     }
+                    if (row < p.M && col_ok) *reinterpret_cast<float4*>(p.out + (int64_t)row * p.ldo + n0 + c0 + lc) = y;
                 }
+                __syncwarp();
             }
             tcgen05_fence_before_sync();
             epilogue_barrier();                                     // every epilogue thread has read its lanes
