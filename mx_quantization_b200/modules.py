@@ -56,6 +56,19 @@ def _require_hot_path(mx_quant, top_k, approx, pred_mode, where):
             "dense / related-work predictor modes are out of scope (SURVEY.md 8f3) and there is no fallback")
 
 
+def to_mx_linear(lin: nn.Linear, mx_specs) -> "MxLinear":
+    """nn.Linear -> MxLinear sharing the parameters (what apply_quantization_to_deit /
+    MXBasicTransformerBlock.set_config do with mx.Linear: deit main.py:231-318,
+    MX_transformer_block.py:344-362)."""
+    if isinstance(lin, MxLinear):
+        return lin
+    m = MxLinear(lin.in_features, lin.out_features, bias=lin.bias is not None, mx_specs=mx_specs)
+    m.weight = lin.weight
+    if lin.bias is not None:
+        m.bias = lin.bias
+    return m
+
+
 class QuantizedAttention(nn.Module):
     """DeiT shim - constructor mirrors workloads/deit/scripts/main.py:42."""
 
@@ -67,7 +80,8 @@ class QuantizedAttention(nn.Module):
             raise NotImplementedError("--anal analysis dumps are out of scope (SURVEY.md 8f4)")
         self.num_heads = orig_attn.num_heads
         self.scale = orig_attn.scale
-        self.qkv, self.proj = orig_attn.qkv, orig_attn.proj
+        # the reference swaps the projections for mx.Linear as well (main.py:262-281)
+        self.qkv, self.proj = to_mx_linear(orig_attn.qkv, mx_specs), to_mx_linear(orig_attn.proj, mx_specs)
         self.proj_drop = getattr(orig_attn, "proj_drop", nn.Identity())
         self.block_idx = block_idx
         self.current_timestep = 0
@@ -96,10 +110,10 @@ class Attention(nn.Module):
             raise NotImplementedError("anal / exclude_timesteps (dense steps) are out of scope")
         self.num_heads, self.head_dim = num_heads, dim // num_heads
         self.scale = self.head_dim ** -0.5
-        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.qkv = MxLinear(dim, dim * 3, bias=qkv_bias, mx_specs=mx_specs)        # models.py:129 (mx Linear)
         self.q_norm = norm_layer(self.head_dim) if qk_norm else nn.Identity()
         self.k_norm = norm_layer(self.head_dim) if qk_norm else nn.Identity()
-        self.proj = nn.Linear(dim, dim, bias=proj_bias)
+        self.proj = MxLinear(dim, dim, bias=proj_bias, mx_specs=mx_specs)
         self.proj_drop = nn.Dropout(proj_drop)
         self.block_idx = block_idx
         self.current_timestep = 0
@@ -135,6 +149,9 @@ class MXSelfAttention(nn.Module):
         if anal or exclude_timesteps:
             raise NotImplementedError("anal / exclude_timesteps (dense steps) are out of scope")
         self.block_idx = block_idx
+        # the block's set_config swaps nn.Linear -> mx.Linear (MX_transformer_block.py:344-362)
+        self.to_q, self.to_k, self.to_v = (to_mx_linear(m, mx_specs) for m in (self.to_q, self.to_k, self.to_v))
+        self.to_out[0] = to_mx_linear(self.to_out[0], mx_specs)
         # reference: scale_factor = 1 / math.sqrt(q.size(-1)) applied as an fp32 scalar (:647-653)
         self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=1.0 / (self.head_dim ** 0.5))
         return self

@@ -325,7 +325,7 @@ def test_cross_attention_module_shim(mxq):
     """MXCrossAttention shim == pruned_attention on its own projections."""
     from mx_quantization_b200.modules import MXCrossAttention
     torch.manual_seed(0)
-    dim, heads, B, N, S = 144, 2, 2, 64, 40
+    dim, heads, B, N, S = 128, 2, 2, 64, 40
     m = MXCrossAttention(dim, heads).cuda().set_config(mx_quant=True, mx_specs=mx_specs(32, True), top_k=True, k=20,
                                                        ex_pred=True, pred_mode="ex_pred")
     x = torch.randn(B, N, dim, device="cuda")
@@ -338,11 +338,13 @@ def test_cross_attention_module_shim(mxq):
         q = m.to_q(x).view(B, N, heads, dim // heads).transpose(1, 2)
         k = m.to_k(enc).view(B, S, heads, dim // heads).transpose(1, 2)
         v = m.to_v(enc).view(B, S, heads, dim // heads).transpose(1, 2)
+    from mx_quantization_b200.modules import MxLinear
+    assert isinstance(m.to_q, MxLinear) and isinstance(m.to_out[0], MxLinear)      # set_config swapped the projections
     ref = O.pruned_attention(q.cpu(), k.cpu(), v.cpu(), 20, scale=1.0 / ((dim // heads) ** 0.5), flush=True,
                              integer_scores=True, key_bias=amask.reshape(B, 1, 1, S).cpu())
     with torch.no_grad():
         want = m.to_out(ref["out"].transpose(1, 2).reshape(B, N, dim).cuda())
-    assert float((y - want).abs().max()) <= 1e-3 * float(want.abs().max())
+    assert float((y - want).abs().max()) <= 2e-3 * float(want.abs().max())
 
 
 @pytest.mark.parametrize("B,H,N,hd,bfloat", [(2, 3, 197, 64, 32), (1, 2, 256, 72, 16), (1, 1, 50, 96, 32)])
