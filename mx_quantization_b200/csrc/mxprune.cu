@@ -646,10 +646,11 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
     const int nc = p.Nk <= 32 ? 1 : p.Nk <= 64 ? 2 : p.Nk <= 128 ? 4 : p.Nk <= 224 ? 7 : 8;
     const int nb = (p.hd + 31) / 32;
     int G = nb <= 2 ? 2 : 1;
-    if (k1c_smem_layout(p.hd, nc, 2, G).total > per_cta2) G = 1;
+    const bool biased = p.key_bias != nullptr;
+    if (k1c_smem_layout(p.hd, nc, 2, G, biased).total > per_cta2) G = 1;
     int ring = K1C_MAXR;
-    while (ring > 2 && k1c_smem_layout(p.hd, nc, ring, G).total > per_cta2) --ring;
-    K1cSmem L = k1c_smem_layout(p.hd, nc, ring, G);
+    while (ring > 2 && k1c_smem_layout(p.hd, nc, ring, G, biased).total > per_cta2) --ring;
+    K1cSmem L = k1c_smem_layout(p.hd, nc, ring, G, biased);
     if (L.total > per_cta1) return 1;
     const int heads = p.B * p.H;
     const int tiles = (p.Nq + K1C_TILE - 1) / K1C_TILE;

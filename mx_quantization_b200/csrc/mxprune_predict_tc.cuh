@@ -55,12 +55,13 @@ struct K1cSmem {
 // nc = number of 32-key chunks (the kernel's NC): the MMA covers 32 * nc key columns, rows past Nk
 // of the predictor operand are zero so that padding keys score exactly 0.
 // G = TMA boxes (of 64 rows) per ring slot == per quantize step.
-__host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring, int G) {
+// biased: two extra K columns carry the additive key bias through the MMA (see the kernel).
+__host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring, int G, bool biased = false) {
     K1cSmem L;
     L.nfull = hd >> 5;
     L.tail = hd & 31;
     L.nb = (hd + 31) >> 5;
-    L.hdp = (hd + 15) & ~15;
+    L.hdp = (hd + (biased ? 2 : 0) + 15) & ~15;
     L.n_mma = 32 * nc;
     int c = 32;
     while (c < 64 * ((nc + 1) / 2)) c <<= 1;              // both lane halves read (nc + 1) / 2 chunks
@@ -344,10 +345,14 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     constexpr int NMMA = 32 * NC;
     constexpr int NCH = (NC + 1) / 2;                               // key chunks per thread
     const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
-    const K1cSmem L = k1c_smem_layout(hd, NC, ring, G);
+    const bool biased = p.key_bias != nullptr;
+    const K1cSmem L = k1c_smem_layout(hd, NC, ring, G, biased);
     const int nfull = L.nfull, tail = L.tail, nb = L.nb;
-    const int kch = L.hdp >> 3;                                     // 16-byte chunks per operand row
-    const int tail_chunks = kch - 4 * nfull;                        // operand chunks the partial block owns
+    const int kch = L.hdp >> 3;                                     // 16-byte chunks per predictor-operand row
+    // operand chunks the partial block owns: in the HBM exact operand (its zero padding included) and in
+    // the shared-memory predictor operand (with a bias, the chunks past the data belong to the bias columns)
+    const int tail_chunks_hbm = (((hd + 15) & ~15) >> 3) - 4 * nfull;
+    const int tail_chunks = biased ? (tail + 7) >> 3 : kch - 4 * nfull;
     unsigned char* s_kop = smem + L.off_kop;
     unsigned char* s_qop = smem + L.off_qop;
     uint32_t* s_ksign = reinterpret_cast<uint32_t*>(smem + L.off_ksign);
@@ -359,6 +364,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_kmax + 4);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_misc + 64);   // [K1C_MAXR]
     uint64_t* bar_mma = bar_full + K1C_MAXR;
+    int* s_bmeta = reinterpret_cast<int*>(bar_mma + 1);            // [3] bias: min 2-adic exponent, max |bias| bits, inexact flag
 
     const int head = blockIdx.x, bb = head / p.H, hh = head - bb * p.H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -413,6 +419,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
         if (tail) { prefetch_tmap(&maps.k_tail); prefetch_tmap(&maps.q_tail); }
     }
     if (tid < 4) { s_kmin[tid] = 0x7fffffff; s_kmax[tid] = -0x7fffffff; }
+    if (tid == 4) { s_bmeta[0] = 0x7fffffff; s_bmeta[1] = 0; s_bmeta[2] = 0; }
     if (warp == 0) tmem_alloc(s_tmem, (uint32_t)L.tmem_cols);
     tcgen05_fence_before_sync();
     __syncthreads();
@@ -474,7 +481,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
             }
             BlockQ r;
             quantize_block_thread<CODES>(xv, full ? 32 : tail, bf16, flush, r);
-            const int nchunk = full ? 4 : tail_chunks;
+            const int nchunk = full ? 4 : tail_chunks, nchunk_hbm = full ? 4 : tail_chunks_hbm;
             if (is_k) {
                 if (row < NMMA) {
                     unsigned char* dst = s_kop + ((4 * b) * NMMA + row) * 16;
@@ -495,7 +502,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                     unsigned char* dst = k_op + ((size_t)(4 * b) * kb_rows + row) * 16;
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch)
-                        if (ch < nchunk) *reinterpret_cast<uint4*>(dst + (size_t)ch * kb_rows * 16) = r.op[ch];
+                        if (ch < nchunk_hbm) *reinterpret_cast<uint4*>(dst + (size_t)ch * kb_rows * 16) = r.op[ch];
                 }
                 if (CODES && write_k && in_range) {
                     const int64_t krow = (int64_t)head * Nk + row;
@@ -517,7 +524,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                     unsigned char* gdst = q_op + (size_t)tile * OL.q_tile_bytes + ((size_t)(4 * b) * K1C_TILE + rt) * 16;
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch)
-                        if (ch < nchunk) *reinterpret_cast<uint4*>(gdst + ch * (K1C_TILE * 16)) = r.op[ch];
+                        if (ch < nchunk_hbm) *reinterpret_cast<uint4*>(gdst + ch * (K1C_TILE * 16)) = r.op[ch];
                 }
                 if (CODES && write_q && in_range) {
                     const int64_t qrow = (int64_t)head * Nq + row;
@@ -526,6 +533,46 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
 #pragma unroll
                     for (int v = 0; v < 8; ++v)
                         if (4 * v < (full ? 32 : tail)) dst2[v] = r.cw[v];
+                }
+            }
+        }
+        if (biased) {
+            // The additive key bias rides through the MMA: two extra K columns hold bias_j split into
+            // two bf16 terms (exact when the bias has <= 16 significant bits) on the key side and 1.0 on
+            // the query side, so the accumulator is pred + bias_j - exact whenever both are multiples of
+            // 2^(g+1) inside the integer window, which is when fl32(pred + bias) is exact as well.
+            const int cb = hd >> 3;                                 // first chunk past the data
+            for (int t = tid; t < CR; t += K1C_T) {
+                const int row = row0 + t;
+                if (is_k) {
+                    uint32_t w0 = 0u;
+                    int ex = 0x7fffffff;
+                    uint32_t mag = 0u, inexact = 0u;
+                    if (row < nrows) {
+                        const float bj = __ldg(kbias + row);
+                        const uint32_t bits = __float_as_uint(bj);
+                        const uint32_t hi = bits & 0xffff0000u;
+                        const uint32_t lo = __float_as_uint(bj - __uint_as_float(hi));     // exact
+                        w0 = (hi >> 16) | (lo & 0xffff0000u);
+                        inexact = (lo & 0xffffu) ? 1u : 0u;
+                        mag = bits & 0x7fffffffu;
+                        if (mag) ex = (int)(mag >> 23) - 150 + (__ffs((int)((mag & 0x7fffffu) | 0x800000u)) - 1);
+                        if ((mag != 0u && (mag >> 23) == 0u) || (mag >> 23) == 255u) inexact = 1u;   // subnormal / inf / nan: fp32 path
+                    }
+                    if (row < NMMA) {
+                        *reinterpret_cast<uint4*>(s_kop + ((size_t)cb * NMMA + row) * 16) = make_uint4(w0, 0u, 0u, 0u);
+                        for (int ch = cb + 1; ch < kch; ++ch)
+                            *reinterpret_cast<uint4*>(s_kop + ((size_t)ch * NMMA + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    ex = __reduce_min_sync(FULL, ex);
+                    mag = __reduce_max_sync(FULL, mag);
+                    inexact = __reduce_or_sync(FULL, inexact);
+                    if (lane == 0) { atomicMin(&s_bmeta[0], ex); atomicMax(&s_bmeta[1], (int)mag); atomicOr(&s_bmeta[2], (int)inexact); }
+                } else {
+                    const int rt = qstep * CR + t;
+                    *reinterpret_cast<uint4*>(s_qop + ((size_t)cb * K1C_TILE + rt) * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+                    for (int ch = cb + 1; ch < kch; ++ch)
+                        *reinterpret_cast<uint4*>(s_qop + ((size_t)ch * K1C_TILE + rt) * 16) = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
         }
@@ -579,8 +626,15 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
 #pragma unroll
         for (int b = 0; b < 4; ++b)
             if (b < nb) g = min(g, epq[b] + kmin[b]);
-        bool fast = valid && !wide && g >= -100 && g <= 80 && kbias == nullptr;   // biased scores: fp32 path
+        bool fast = valid && !wide && g >= -100 && g <= 80;
         long long M = 0;
+        if (biased) {
+            // integer keys carry the bias when every bias_j is an even multiple of 2^g (then pred + bias
+            // is exact in fp32, as the reference adds it); its magnitude widens the key window
+            if (s_bmeta[2] != 0 || g + 1 > s_bmeta[0]) fast = false;
+            const float bm = __uint_as_float((uint32_t)s_bmeta[1]) * (fast ? exp2i(-g) : 0.f);
+            if (bm > 40000.f) fast = false; else M = (long long)bm;
+        }
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             if (b < nb) {

@@ -416,3 +416,29 @@ def test_mx_linear_vs_oracle(mxq, M, K, N, bias, bfloat):
     ref = O.mx_linear(x, w, b, bfloat=bfloat)
     assert y.shape == ref.shape
     _check_linear(y.cpu(), ref, bfloat)
+
+
+@pytest.mark.parametrize("bias_kind", ["mask_-10000", "arbitrary_fp32", "dyadic_small", "half_masked_-1e4_hd64"])
+def test_key_bias_variants(mxq, bias_kind):
+    """Additive key bias: the integer-key fast path (bias carried through the MMA, exact) and the fp32
+    fallback (bias with more than 16 significant bits / not a multiple of the row's 2^(g+1)) must both
+    reproduce the oracle's sets."""
+    B, H, Nq, S, hd, top_k = 2, 2, 96, 120, (64 if "hd64" in bias_kind else 72), 50
+    g = torch.Generator().manual_seed(77)
+    q = torch.randn(B, H, Nq, hd, generator=g)
+    k = torch.randn(B, H, S, hd, generator=g)
+    v = torch.randn(B, H, S, hd, generator=g)
+    if bias_kind.startswith("mask") or bias_kind.startswith("half"):
+        keep = torch.zeros(B, S); keep[0, :31] = 1; keep[1, :60] = 1
+        bias = (1 - keep) * -10000.0
+    elif bias_kind == "arbitrary_fp32":
+        bias = torch.randn(B, S, generator=g) * 3.0
+    else:
+        bias = torch.randint(-8, 9, (B, S), generator=g).float() * 0.5
+    specs = mx_specs(32, True)
+    out, mask = mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), specs, top_k, return_mask=True,
+                                     key_bias=bias.reshape(B, 1, 1, S).cuda())
+    ref = O.pruned_attention(q, k, v, top_k, flush=True, integer_scores=True, key_bias=bias.reshape(B, 1, 1, S))
+    want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], S), S)
+    assert torch.equal(unpack_mask(mask, S), want)
+    assert_out_close(out.cpu(), ref, v, S, 32, OUT_TOL)
