@@ -618,17 +618,17 @@ static bool make_view_maps(const View& v, int B, int H, int N, int hd, CUtensorM
     return true;
 }
 
-template <int NC, bool CODES>
+template <int NC, bool CODES, bool BIASED>
 static int launch_predict_topk_tc_one(const PredParams& p, const K1cMaps& maps, const K1cSmem& L, size_t dyn,
                                       dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_tc<NC, CODES>,
+        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_tc<NC, CODES, BIASED>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    k_predict_topk_tc<NC, CODES><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
+    k_predict_topk_tc<NC, CODES, BIASED><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
     return check_launch("k_predict_topk_tc");
 }
 
@@ -664,9 +664,11 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
     const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
     if (dyn < floor_bytes) dyn = floor_bytes;
     const bool codes = p.q_codes != nullptr || p.k_codes != nullptr;
+    if (biased && codes) return 1;          // codes + bias: the CUDA-core kernel handles it
 #define MXP_TC(NC_)                                                                                     \
-    *rc_out = codes ? launch_predict_topk_tc_one<NC_, true>(p, maps, L, dyn, grid, st)                  \
-                    : launch_predict_topk_tc_one<NC_, false>(p, maps, L, dyn, grid, st)
+    *rc_out = biased ? launch_predict_topk_tc_one<NC_, false, true>(p, maps, L, dyn, grid, st)          \
+            : codes  ? launch_predict_topk_tc_one<NC_, true, false>(p, maps, L, dyn, grid, st)          \
+                     : launch_predict_topk_tc_one<NC_, false, false>(p, maps, L, dyn, grid, st)
     switch (nc) {
         case 1: MXP_TC(1); break;
         case 2: MXP_TC(2); break;

@@ -337,7 +337,9 @@ __device__ __forceinline__ void tmem_ld_16x32bx2_x16(uint32_t taddr, uint32_t (&
 }
 
 // NC = number of 32-key TMEM chunks a row's keys occupy (Nk <= 32 * NC); the MMA's N is 32 * NC.
-template <int NC, bool CODES>
+// BIASED: an additive key bias (cross-attention text mask) is present; compiled separately so that the
+// unbiased kernel carries none of its code.
+template <int NC, bool CODES, bool BIASED>
 __global__ void __launch_bounds__(K1C_T, 2)
 k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring, const int G) {
     extern __shared__ __align__(1024) unsigned char smem_k1c[];     // 1024-byte aligned: SWIZZLE_128B boxes
@@ -345,7 +347,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     constexpr int NMMA = 32 * NC;
     constexpr int NCH = (NC + 1) / 2;                               // key chunks per thread
     const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
-    const bool biased = p.key_bias != nullptr;
+    constexpr bool biased = BIASED;
     const K1cSmem L = k1c_smem_layout(hd, NC, ring, G, biased);
     const int nfull = L.nfull, tail = L.tail, nb = L.nb;
     const int kch = L.hdp >> 3;                                     // 16-byte chunks per predictor-operand row
@@ -381,7 +383,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     unsigned char* k_op = p.k_op ? p.k_op + (size_t)head * OL.k_head_bytes : nullptr;
     unsigned char* q_op = p.q_op ? p.q_op + (size_t)head * OL.q_head_bytes : nullptr;
     const int kb_rows = OL.kb_rows;
-    const float* kbias = p.key_bias ? p.key_bias + bb * p.kb_sB : nullptr;
+    const float* kbias = biased ? p.key_bias + bb * p.kb_sB : nullptr;
 
     // ---- step schedule of this CTA: CR = 64 G rows per step; K steps first, then the Q tiles
     const int CR = K1C_ROWS * G, cr_shift = G == 2 ? 7 : 6;
