@@ -103,6 +103,11 @@ def out_error_budget(ref, v, n_keys, bfloat=32, out_tol=1e-3, rel_window=1e-6):
     vrow = torch.nn.functional.pad(vrow, (0, pad)).reshape(*vrow.shape[:-1], nw, 32).unsqueeze(-3)
     extra = (risky.double() * (2 * step) * vrow.double()).sum(dim=(-1, -2))     # (B,H,Nq)
     base = out_tol * float(out_ref.abs().max())
+    if bfloat == 16:
+        # the output itself is rounded to bf16 (A1, matmul.py:89-91): an fp32 sum within an ulp of a
+        # rounding tie lands on either neighbour depending on the summation order - one bf16 ulp of
+        # the row's largest output
+        extra = extra + 2.0 ** -8 * out_ref.abs().amax(-1).double()
     return base + extra.float()
 
 
