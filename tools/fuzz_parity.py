@@ -66,7 +66,8 @@ def main():
                 from tests.helpers import out_error_budget
                 err = (out.cpu() - ref["out"]).abs().amax(-1)
                 budget = out_error_budget(ref, v, Nk, bfloat, 1e-3)
-                assert float((err > budget).float().mean()) <= 0.01, "more than 1% of rows outside the budget"
+                nbad = int((err > budget).sum())
+                assert nbad <= max(2, int(0.01 * err.numel())), "more than 1% of rows (and more than 2) outside the budget"
                 assert float(err.max()) <= 0.05 * float(ref["out"].abs().max()), "error above 5% of max|ref|"
             print(tag, "ok")
         except Exception as e:      # noqa: BLE001
