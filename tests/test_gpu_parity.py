@@ -442,3 +442,34 @@ def test_key_bias_variants(mxq, bias_kind):
     want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], S), S)
     assert torch.equal(unpack_mask(mask, S), want)
     assert_out_close(out.cpu(), ref, v, S, 32, OUT_TOL)
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,hd,top_k,bfloat,flush", [
+    (1, 1, 1, 1, 32, 1, 32, False),        # single query, single key
+    (1, 2, 5, 3, 40, 2, 32, True),
+    (2, 1, 17, 256, 48, 1, 32, False),     # k = 1
+    (1, 3, 130, 33, 80, 33, 32, False),    # k = Nk (dense), two tiles
+    (1, 1, 257, 129, 104, 64, 32, True),   # three tiles, NC = 7 path with Nk = 129
+    (1, 2, 64, 225, 128, 100, 32, False),  # NC = 8 with padding columns, head_dim 128
+    (2, 2, 300, 257, 64, 77, 32, False),   # just past the single-key-block limit
+    (1, 1, 40, 300, 36, 30, 32, False),    # head_dim % 8 != 0 -> CUDA-core predictor; Nk > 256 unsupported for attention
+])
+def test_odd_shapes(mxq, B, H, Nq, Nk, hd, top_k, bfloat, flush):
+    """Corner shapes found useful by tools/fuzz_parity.py (which runs ~1000 random ones)."""
+    g = torch.Generator().manual_seed(123)
+    q = torch.randn(B, H, Nq, hd, generator=g)
+    k = torch.randn(B, H, Nk, hd, generator=g)
+    v = torch.randn(B, H, Nk, hd, generator=g)
+    specs = mx_specs(bfloat, flush)
+    ref = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, flush=flush, integer_scores=True)
+    want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], Nk), Nk)
+    r = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k, return_idx=True)
+    assert torch.equal(unpack_mask(r["mask"], Nk), want)
+    assert torch.equal(r["idx"].cpu().to(torch.int64), torch.sort(ref["idx"], dim=-1).values)
+    if hd % 8 == 0:
+        out, mask = mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), specs, top_k, return_mask=True)
+        assert torch.equal(mask, r["mask"])
+        assert_out_close(out.cpu(), ref, v, Nk, bfloat, OUT_TOL)
+    else:
+        with pytest.raises(ValueError):             # unsupported combination: loud, no fallback
+            mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), specs, top_k)
