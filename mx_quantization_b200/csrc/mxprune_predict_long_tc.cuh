@@ -178,8 +178,12 @@ k_select_long_tc(const LongSelParams p) {
     // zero rows of Kp (score exactly 0) among THIS lane's key columns: only the last block has any
     const int last0 = (nblk - 1) * 128 + 64 * part;
     const int my_npad = max(0, min(64, last0 + 64 - Nk));
-    unsigned short* my_hist = s_hist + tid;             // bin b at my_hist[b * KL_T]
-    const unsigned short* their_hist = s_hist + (tid ^ 16);
+    // u16 counters, bin b of a thread at [b * KL_T + slot]: the 32 lanes of a warp sit in 32 different
+    // 32-bit words (banks) - two warps interleave the half-words - so the per-key read-modify-writes of
+    // a warp never conflict, whatever bins its lanes hit
+    const int hslot = (warp >> 1) * 64 + 2 * lane + (warp & 1);
+    unsigned short* my_hist = s_hist + hslot;           // bin b at my_hist[b * KL_T]
+    const unsigned short* their_hist = s_hist + ((warp >> 1) * 64 + 2 * (lane ^ 16) + (warp & 1));
 
     for (int tile = blockIdx.y; tile < O.q_tiles; tile += gridDim.y) {
         const int i = tile * KL_TILE + rr;
@@ -218,9 +222,12 @@ k_select_long_tc(const LongSelParams p) {
         const int moff = ((int)M + 1) & ~1;
         const float scl = fast ? exp2i(-g - 1) : 0.f;
         // keys carry the fp16 bias of the short kernel (two keys per word compare with one HSET2)
-        const uint32_t key0 = (uint32_t)((moff >> 1) + 1) + K1_KEY_BIAS;    // key of a score of exactly 0
+        // histogram passes rank on the plain key u = S/2 + moff/2 + 1 (fewest digits); the emit pass adds
+        // the fp16 bias of the short kernel so that two keys per word compare with one HSET2
+        const uint32_t key0 = (uint32_t)((moff >> 1) + 1);          // key of a score of exactly 0
         const float cadd = 8388608.0f + (float)key0;
-        const int wtot = 32 - __clz(moff + 1 + (int)K1_KEY_BIAS);   // key width in bits
+        const float cadd_e = cadd + (float)K1_KEY_BIAS;
+        const int wtot = 32 - __clz(moff + 1);                      // key width in bits
         const int my_lev = (wtot + 5) / 6;
         __syncthreads();                                            // *s_nlev = 0 visible
         {
@@ -244,7 +251,7 @@ k_select_long_tc(const LongSelParams p) {
                 for (int b = 0; b < KL_BINS; ++b) my_hist[b * KL_T] = 0;
             }
             int rem = krem, pos = 0;                                // emit state (identical in both lanes)
-            const uint32_t T = prefix;
+            const uint32_t T = prefix + K1_KEY_BIAS;                // emit compares biased keys
             if (tid == 0) {
                 const int pre = min(2, nblk);
                 for (int b = 0; b < pre; ++b) {
@@ -317,8 +324,8 @@ k_select_long_tc(const LongSelParams p) {
                             uint32_t gt = 0u, eq = 0u;
 #pragma unroll
                             for (int c = 0; c < 16; ++c) {
-                                const uint32_t fl = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd));
-                                const uint32_t fh = __float_as_uint(fmaf(__uint_as_float(r[c + 16]), scl, cadd));
+                                const uint32_t fl = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd_e));
+                                const uint32_t fh = __float_as_uint(fmaf(__uint_as_float(r[c + 16]), scl, cadd_e));
                                 const __half2 kv = u32_as_h2(__byte_perm(fl, fh, 0x5410));
                                 gt |= __hgt2_mask(kv, t2) & (0x00010001u << c);
                                 eq |= __heq2_mask(kv, t2) & (0x00010001u << c);
