@@ -473,3 +473,26 @@ def test_odd_shapes(mxq, B, H, Nq, Nk, hd, top_k, bfloat, flush):
     else:
         with pytest.raises(ValueError):             # unsupported combination: loud, no fallback
             mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), specs, top_k)
+
+
+def test_cuda_graph_capture_and_replay(mxq):
+    """The library allocates nothing, never synchronises and enqueues on the caller's stream, so a
+    whole call (three kernels, tensor maps baked into the launch parameters) captures into a CUDA
+    graph; replaying it on new input values in the same buffers gives the eager result."""
+    B, H, N, hd, top_k = 2, 3, 197, 64, 30
+    specs = mx_specs(32, False)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    buf = torch.randn(B, N, 3, H, hd, device="cuda", generator=g)
+    qkv = buf.permute(2, 0, 3, 1, 4)
+    out = torch.empty(B, N, H, hd, device="cuda")
+    mxq.pruned_attention(qkv[0], qkv[1], qkv[2], specs, top_k, out=out.permute(0, 2, 1, 3))      # warm-up (attributes set)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        mxq.pruned_attention(qkv[0], qkv[1], qkv[2], specs, top_k, out=out.permute(0, 2, 1, 3))
+    buf.copy_(torch.randn(B, N, 3, H, hd, device="cuda", generator=g))                              # new activations
+    graph.replay()
+    torch.cuda.synchronize()
+    got = out.clone()
+    want = mxq.pruned_attention(qkv[0], qkv[1], qkv[2], specs, top_k).permute(0, 2, 1, 3)
+    assert torch.equal(got, want.contiguous())
