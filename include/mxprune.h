@@ -164,6 +164,36 @@ int mxp_pruned_attention_biased(const float* q, int64_t q_sB, int64_t q_sH, int6
                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The reference's other sources of the top-k ranking, behind the same call:
+ *   MXP_PRED_EXP_SIGN   pred_mode == "ex_pred"     both sides +-2^e                 (== mxp_pruned_attention)
+ *   MXP_PRED_PARTIAL_Q  pred_mode == "partial_Q"   Q = MXINT8 value, K = +-2^e      funcs/exponent_based_prediction.py:300-318
+ *   MXP_PRED_PARTIAL_K  pred_mode == "partial_K"   Q = +-2^e, K = MXINT8 value      funcs/exponent_based_prediction.py:274-298
+ *   MXP_PRED_EXACT      approx_flag == False       top-k of the true scores mx.matmul(q, k^T) * scale
+ *                                                   workloads/deit/scripts/main.py:101-102,130
+ * (callers: main.py:107-123, DiT models.py:178-194).  Modes 1-3 need Nk <= 256 and head_dim a multiple
+ * of 8, >= 32 (MXP_E_UNSUPPORTED otherwise); `scale` ranks the exact mode and scales the attention in
+ * every mode.  mxp_predict_topk_mode is the selection alone (mask / idx as mxp_predict_topk).
+ */
+#define MXP_PRED_EXP_SIGN  0
+#define MXP_PRED_PARTIAL_Q 1
+#define MXP_PRED_PARTIAL_K 2
+#define MXP_PRED_EXACT     3
+int mxp_pruned_attention_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                              const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                              const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                              int B, int H, int Nq, int Nk, int hd, int top_k, int pred_mode,
+                              float scale, int bfloat_bits, int flush,
+                              float* out, int64_t o_sB, int64_t o_sH, int64_t o_sN,
+                              uint32_t* mask_out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int mxp_predict_topk_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                          const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                          int B, int H, int Nq, int Nk, int hd, int top_k, int pred_mode,
+                          float scale, int bfloat_bits, int flush,
+                          uint32_t* mask, int32_t* idx,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * MX Linear (the step either side of the attention core): the forward of the
  * reference's mx.Linear (microxscaling/mx/linear.py:20-103) for MXINT8 activations and weights,
  *     y = A1( A1( MXq(A1(x)) . MXq(A1(W))^T ) + A1(bias) )

@@ -6,7 +6,7 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(CSRC, "libmxprune.so")
-SOURCES = ["mxprune.cu", "mxprune_device.cuh", "mxprune_predict.cuh", "mxprune_attend.cuh", "mxprune_umma.cuh"]
+SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
 
 
 def _stale() -> bool:

@@ -11,6 +11,7 @@
 #include "mxprune_attend.cuh"
 #include "mxprune_predict_tc.cuh"
 #include "mxprune_predict_long_tc.cuh"
+#include "mxprune_predict_wide.cuh"
 #include "mxprune_linear.cuh"
 
 using namespace mxp;
@@ -680,6 +681,60 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
     return 0;
 }
 
+// ---- K1-wide: partial_Q / partial_K / exact-score top-k, Nk <= 256, tensor-core domain only
+template <int NC>
+static int launch_predict_topk_wide_one(const PredParams& p, const K1cMaps& maps, const K1cSmem& L, size_t dyn,
+                                        dim3 grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_wide<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024);
+        if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    k_predict_topk_wide<NC><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
+    return check_launch("k_predict_topk_wide");
+}
+
+static int predict_topk_wide(const PredParams& p, cudaStream_t st) {
+    if (p.Nk > 256 || p.hd < 32 || (p.hd & 7))
+        return fail(MXP_E_UNSUPPORTED, "pred_mode %d needs Nk <= 256 and head_dim a multiple of 8, >= 32 (got Nk=%d hd=%d)",
+                    p.pred_mode, p.Nk, p.hd);
+    if (p.key_bias || p.q_codes || p.k_codes)
+        return fail(MXP_E_UNSUPPORTED, "pred_mode %d: key_bias and code outputs are implemented for the exponent-sign predictor only",
+                    p.pred_mode);
+    K1cMaps maps;
+    if (!make_view_maps(p.q, p.B, p.H, p.Nq, p.hd, &maps.q_main, &maps.q_tail) ||
+        !make_view_maps(p.k, p.B, p.H, p.Nk, p.hd, &maps.k_main, &maps.k_tail))
+        return fail(MXP_E_UNSUPPORTED, "pred_mode %d: the q/k views cannot be described by a TMA tensor map", p.pred_mode);
+    const size_t per_cta2 = 232448 / 2 - 1024, per_cta1 = 232448 - 1024;
+    const int nc = p.Nk <= 32 ? 1 : p.Nk <= 64 ? 2 : p.Nk <= 128 ? 4 : p.Nk <= 224 ? 7 : 8;
+    const int nb = (p.hd + 31) / 32;
+    int G = nb <= 2 ? 2 : 1;
+    if (k1c_smem_layout(p.hd, nc, 2, G, false).total > per_cta2) G = 1;
+    int ring = K1C_MAXR;
+    while (ring > 2 && k1c_smem_layout(p.hd, nc, ring, G, false).total > per_cta2) --ring;
+    K1cSmem L = k1c_smem_layout(p.hd, nc, ring, G, false);
+    if (L.total > per_cta1) return fail(MXP_E_UNSUPPORTED, "pred_mode %d: shape needs %zu bytes of shared memory", p.pred_mode, L.total);
+    const int heads = p.B * p.H;
+    const int tiles = (p.Nq + K1C_TILE - 1) / K1C_TILE;
+    int splits = (148 * 2 + heads - 1) / heads;
+    if (splits > tiles) splits = tiles;
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)heads, (unsigned)splits);
+    const int max_ctas = 512 / L.tmem_cols;
+    size_t dyn = L.total;
+    const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
+    if (dyn < floor_bytes) dyn = floor_bytes;
+    switch (nc) {
+        case 1: return launch_predict_topk_wide_one<1>(p, maps, L, dyn, grid, st);
+        case 2: return launch_predict_topk_wide_one<2>(p, maps, L, dyn, grid, st);
+        case 4: return launch_predict_topk_wide_one<4>(p, maps, L, dyn, grid, st);
+        case 7: return launch_predict_topk_wide_one<7>(p, maps, L, dyn, grid, st);
+        default: return launch_predict_topk_wide_one<8>(p, maps, L, dyn, grid, st);
+    }
+}
+
 // ---- K1-long-TC (Nk > 256): operand pre-pass + tensor-core radix select + CUDA-core clean-up ----
 struct LongWsLayout { size_t q_pp, k_pp, q_ep, head_meta, flags, total; };
 inline LongWsLayout long_ws_layout(int B, int H, int Nq, int Nk, int hd) {
@@ -876,6 +931,8 @@ static int predict_topk_impl(const PredParams& p, cudaStream_t st) {
     int rc = MXP_OK;
     if (p.key_bias && p.Nk > K1_MAX_KEYS)
         return fail(MXP_E_UNSUPPORTED, "key_bias: the additive key bias is implemented for Nk <= 256 (cross-attention)");
+    if (p.pred_mode < 0 || p.pred_mode > 3) return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 3]", p.pred_mode);
+    if (p.pred_mode != 0) return predict_topk_wide(p, st);
     if (try_predict_topk_tc(p, st, &rc) == 0) return rc;
     if (try_predict_topk_long_tc(p, st, &rc) == 0) return rc;
     switch ((p.hd + 31) / 32) {
@@ -987,8 +1044,10 @@ static int pruned_attention_impl(const float* q, int64_t q_sB, int64_t q_sH, int
                                  int B, int H, int Nq, int Nk, int hd, int top_k, float scale,
                                  int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
                                  int64_t o_sN, const float* key_bias, int64_t kb_sB, uint32_t* mask_out,
-                                 void* workspace, size_t workspace_bytes, void* stream) {
+                                 void* workspace, size_t workspace_bytes, void* stream, int pred_mode = 0) {
     g_launches = 0;
+    if (pred_mode != 0 && g_attn_path != 0)
+        return fail(MXP_E_UNSUPPORTED, "pred_mode %d needs the tcgen05 attention path", pred_mode);
     if (key_bias && (g_attn_path != 0 || ((uintptr_t)key_bias & 3)))
         return fail(MXP_E_UNSUPPORTED, "key_bias needs the tcgen05 attention path and a 4-byte aligned pointer");
     int rc = check_shape(B, H, Nq, Nk, hd, bfloat_bits);
@@ -1017,6 +1076,7 @@ static int pruned_attention_impl(const float* q, int64_t q_sB, int64_t q_sH, int
     pp.bf16 = bfloat_bits == 16; pp.flush = flush != 0;
     pp.mask = mask; pp.idx = nullptr;
     pp.key_bias = key_bias; pp.kb_sB = kb_sB;
+    pp.pred_mode = pred_mode; pp.score_scale = scale;
     pp.long_ws = long_bytes ? w + need - long_bytes : nullptr;
     pp.long_ws_bytes = long_bytes;
     if (tc) {
@@ -1078,6 +1138,45 @@ int mxp_pruned_attention_biased(const float* q, int64_t q_sB, int64_t q_sH, int6
     return pruned_attention_impl(q, q_sB, q_sH, q_sN, k, k_sB, k_sH, k_sN, v, v_sB, v_sH, v_sN, B, H, Nq, Nk, hd,
                                  top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, key_bias, kb_sB, mask_out,
                                  workspace, workspace_bytes, stream);
+}
+
+int mxp_pruned_attention_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                              const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                              const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                              int B, int H, int Nq, int Nk, int hd, int top_k, int pred_mode, float scale,
+                              int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
+                              int64_t o_sN, uint32_t* mask_out, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+    if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_EXACT)
+        return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 3]", pred_mode);
+    return pruned_attention_impl(q, q_sB, q_sH, q_sN, k, k_sB, k_sH, k_sN, v, v_sB, v_sH, v_sN, B, H, Nq, Nk, hd,
+                                 top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, nullptr, 0, mask_out,
+                                 workspace, workspace_bytes, stream, pred_mode);
+}
+
+int mxp_predict_topk_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                          const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                          int B, int H, int Nq, int Nk, int hd, int top_k, int pred_mode, float scale,
+                          int bfloat_bits, int flush, uint32_t* mask, int32_t* idx,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    int rc = check_shape(B, H, Nq, Nk, hd, bfloat_bits);
+    if (rc) return rc;
+    if ((rc = check_view("q", q, q_sB, q_sH, q_sN, hd))) return rc;
+    if ((rc = check_view("k", k, k_sB, k_sH, k_sN, hd))) return rc;
+    if (!mask) return fail(MXP_E_BADARG, "mask: null pointer");
+    if (top_k < 1 || top_k > Nk) return fail(MXP_E_BADARG, "top_k=%d outside [1, Nk=%d]", top_k, Nk);
+    if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_EXACT)
+        return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 3]", pred_mode);
+    PredParams p{};
+    p.q = View{q, q_sB, q_sH, q_sN};
+    p.k = View{k, k_sB, k_sH, k_sN};
+    p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk; p.hd = hd; p.top_k = top_k;
+    p.bf16 = bfloat_bits == 16; p.flush = flush != 0;
+    p.mask = mask; p.idx = idx;
+    p.pred_mode = pred_mode; p.score_scale = scale;
+    p.long_ws = workspace; p.long_ws_bytes = workspace_bytes;
+    return predict_topk_impl(p, (cudaStream_t)stream);
 }
 
 // ---- MX Linear ---------------------------------------------------------------------

@@ -1,0 +1,338 @@
+// K1-wide: the reference's OTHER top-k score sources for Nk <= 256, on the same
+// staging / quantizer / tensor-core skeleton as K1-TC (mxprune_predict_tc.cuh):
+//
+//   pred_mode 1  partial_Q   Q = MXINT8 value c * 2^(e-6), K = +-2^e
+//                            funcs/exponent_based_prediction.py:300-318, workloads/deit/scripts/main.py:111-112
+//   pred_mode 2  partial_K   Q = +-2^e, K = MXINT8 value        funcs/exponent_based_prediction.py:274-298, main.py:113-114
+//   pred_mode 3  exact       top-k of the TRUE scores, mx.matmul(q, k^T) * scale - the reference's
+//                            `top_k and not approx_flag` branch  main.py:101-102,130
+//
+// Both operand kinds are exact in bf16 and come out of the same per-block quantizer
+// (quantize_block_thread: r.op = c * 2^(e-6), r.pp = +-2^e), so a mode only chooses which of the two
+// goes into the MMA's A and B operands.  The accumulator is the reference's fp32 matmul result bit for
+// bit while one (query, key) pair's terms fit the tensor core's exact window (tools/umma_exact_test.cu:
+// 22 bits; beyond it the reference's own BLAS summation order decides and parity is unpinned).
+//
+// These scores are not small integers (7 more bits per MXINT8 operand than the +-2^e predictor), so
+// the selection works on the full 32-bit ORDERED fp32 key: three digit levels (14 + 14 + 4 bits),
+// each re-reads the score tile from TMEM, maps this row's keys to a digit relative to the prefix
+// chosen so far (below prefix -> 0, above -> max) and runs K1-TC's register bisection (HSET2/HADD2 on
+// fp16 bit patterns, two lanes per query row).  32 counting passes instead of ~10: these are the
+// reference's comparison modes, not the headline path.  Ties: ascending key index, as everywhere.
+#pragma once
+#include "mxprune_predict_tc.cuh"
+
+namespace mxp {
+
+constexpr int PRED_EX = 0, PRED_PARTIAL_Q = 1, PRED_PARTIAL_K = 2, PRED_TRUE = 3;
+
+template <int NC>
+__global__ void __launch_bounds__(K1C_T, 2)
+k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring, const int G) {
+    extern __shared__ __align__(1024) unsigned char smem_k1w[];
+    unsigned char* const smem = smem_k1w;
+    constexpr int NMMA = 32 * NC;
+    constexpr int NCH = (NC + 1) / 2;                               // key chunks per thread
+    const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
+    const int mode = p.pred_mode;
+    const bool q_exact = mode == PRED_PARTIAL_Q || mode == PRED_TRUE;
+    const bool k_exact = mode == PRED_PARTIAL_K || mode == PRED_TRUE;
+    const bool true_mode = mode == PRED_TRUE;
+    const K1cSmem L = k1c_smem_layout(hd, NC, ring, G, false);
+    const int nfull = L.nfull, tail = L.tail, nb = L.nb;
+    const int kch = L.hdp >> 3;
+    const int tail_chunks_hbm = (((hd + 15) & ~15) >> 3) - 4 * nfull;
+    const int tail_chunks = kch - 4 * nfull;
+    unsigned char* s_kop = smem + L.off_kop;
+    unsigned char* s_qop = smem + L.off_qop;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.off_misc + 32);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_misc + 64);   // [K1C_MAXR]
+    uint64_t* bar_mma = bar_full + K1C_MAXR;
+
+    const int head = blockIdx.x, bb = head / p.H, hh = head - bb * p.H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lane_base = 32 * (warp & 3) + 16 * (warp >> 2);
+    const int rr = lane_base + (lane & 15);
+    const int part = lane >> 4;
+    const bool bf16 = p.bf16, flush = p.flush;
+    const bool write_kop = p.k_op != nullptr && blockIdx.y == 0;
+    const OpsLayout OL = ops_layout(Nq, Nk, hd);
+    unsigned char* k_op = p.k_op ? p.k_op + (size_t)head * OL.k_head_bytes : nullptr;
+    unsigned char* q_op = p.q_op ? p.q_op + (size_t)head * OL.q_head_bytes : nullptr;
+    const int kb_rows = OL.kb_rows;
+    const float sscale = p.score_scale;
+
+    const int CR = K1C_ROWS * G, cr_shift = G == 2 ? 7 : 6;
+    const int nks = (NMMA + CR - 1) / CR;
+    const int qsteps = K1C_TILE / CR;
+    const int tiles = (Nq + K1C_TILE - 1) / K1C_TILE;
+    const int my_tiles = (tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int nsteps = nks + qsteps * my_tiles;
+    const uint32_t box_main = (uint32_t)L.box_main, box_tail = (uint32_t)L.box_tail;
+    const uint32_t slot_tx = (uint32_t)G * (box_main + box_tail);
+    const uint32_t slot_bytes = (uint32_t)L.slot_bytes;
+    const uint32_t tail_base = (uint32_t)G * box_main;
+
+    auto issue = [&](int c, int slot_i) {                           // one thread
+        unsigned char* slot = smem + (size_t)slot_i * slot_bytes;
+        uint64_t* bar = &bar_full[slot_i];
+        const bool is_k = c < nks;
+        int row0;
+        if (is_k) row0 = c * CR;
+        else {
+            const int qc = c - nks;
+            row0 = ((int)blockIdx.y + (qc / qsteps) * (int)gridDim.y) * K1C_TILE + (qc % qsteps) * CR;
+        }
+        mbar_expect_tx(bar, slot_tx);
+        for (int g = 0; g < G; ++g) {
+            if (nfull) tma_load_5d(slot + g * box_main, is_k ? &maps.k_main : &maps.q_main, 0, row0 + g * K1C_ROWS, 0, hh, bb, bar);
+            if (tail) tma_load_4d(slot + tail_base + g * box_tail, is_k ? &maps.k_tail : &maps.q_tail, 0, row0 + g * K1C_ROWS, hh, bb, bar);
+        }
+    };
+
+    if (tid == 0) {
+        for (int r = 0; r < ring; ++r) mbar_init(&bar_full[r], 1);
+        mbar_init(bar_mma, 1);
+        prefetch_tmap(&maps.k_main); prefetch_tmap(&maps.q_main);
+        if (tail) { prefetch_tmap(&maps.k_tail); prefetch_tmap(&maps.q_tail); }
+    }
+    if (warp == 0) tmem_alloc(s_tmem, (uint32_t)L.tmem_cols);
+    tcgen05_fence_before_sync();
+    __syncthreads();
+    tcgen05_fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t my_tmem = tmem + ((uint32_t)lane_base << 16);
+    if (tid == 0) {
+        const int pre = min(ring, nsteps);
+        for (int c = 0; c < pre; ++c) issue(c, c);
+    }
+    const uint32_t idesc = umma_idesc_bf16_f32(128, NMMA);
+    const int NW = (Nk + 31) >> 5;
+    uint32_t ph_mma = 0;
+    int slot_i = 0;
+    uint32_t slot_par = 0;
+    int tile = (int)blockIdx.y - (int)gridDim.y;
+    int qstep = qsteps - 1;
+
+    for (int c = 0; c < nsteps; ++c) {
+        const bool is_k = c < nks;
+        if (!is_k) {
+            if (++qstep == qsteps) { qstep = 0; tile += (int)gridDim.y; }
+        }
+        const int row0 = is_k ? c * CR : tile * K1C_TILE + qstep * CR;
+        const int nrows = is_k ? Nk : Nq;
+        const unsigned char* slot = smem + (size_t)slot_i * slot_bytes;
+        mbar_wait(&bar_full[slot_i], slot_par);
+
+        // -------- quantize the step's rows (one thread per MX block), as K1-TC; the MMA operand of a
+        // side is the exact value or the +-2^e predictor value according to the mode
+        const int ntask = CR * nb;
+        for (int t = tid; t < ntask; t += K1C_T) {
+            const int b = t >> cr_shift, rl = t & (CR - 1);
+            const int g = rl >> 6, rl6 = rl & 63;
+            const int row = row0 + rl;
+            const bool in_range = row < nrows;
+            const bool full = b < nfull;
+            uint32_t xv[32];
+            if (full) {
+                const unsigned char* src = slot + g * box_main + (b * 64 + rl6) * 128;
+                const int sw7 = (rl6 & 7) << 4;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(src + ((s << 4) ^ sw7));
+                    xv[4 * s] = v.x; xv[4 * s + 1] = v.y; xv[4 * s + 2] = v.z; xv[4 * s + 3] = v.w;
+                }
+            } else {
+                const unsigned char* src = slot + tail_base + g * box_tail + rl6 * tail * 4;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (4 * s < tail) v = *reinterpret_cast<const uint4*>(src + (s << 4));
+                    xv[4 * s] = v.x; xv[4 * s + 1] = v.y; xv[4 * s + 2] = v.z; xv[4 * s + 3] = v.w;
+                }
+            }
+            BlockQ r;
+            quantize_block_thread<false>(xv, full ? 32 : tail, bf16, flush, r);
+            const int nchunk = full ? 4 : tail_chunks, nchunk_hbm = full ? 4 : tail_chunks_hbm;
+            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+            if (is_k) {
+                if (row < NMMA) {
+                    unsigned char* dst = s_kop + ((4 * b) * NMMA + row) * 16;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        if (ch < nchunk)
+                            *reinterpret_cast<uint4*>(dst + ch * (NMMA * 16)) =
+                                !in_range ? zero4 : k_exact ? r.op[ch] : r.pp[ch];
+                }
+                if (write_kop && row < kb_rows) {
+                    unsigned char* dst = k_op + ((size_t)(4 * b) * kb_rows + row) * 16;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        if (ch < nchunk_hbm) *reinterpret_cast<uint4*>(dst + (size_t)ch * kb_rows * 16) = r.op[ch];
+                }
+            } else {
+                const int rt = qstep * CR + rl;
+                unsigned char* dst = s_qop + ((4 * b) * K1C_TILE + rt) * 16;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    if (ch < nchunk) *reinterpret_cast<uint4*>(dst + ch * (K1C_TILE * 16)) = q_exact ? r.op[ch] : r.pp[ch];
+                if (q_op) {
+                    unsigned char* gdst = q_op + (size_t)tile * OL.q_tile_bytes + ((size_t)(4 * b) * K1C_TILE + rt) * 16;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        if (ch < nchunk_hbm) *reinterpret_cast<uint4*>(gdst + ch * (K1C_TILE * 16)) = r.op[ch];
+                }
+            }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0 && c + ring < nsteps) issue(c + ring, slot_i);
+        if (++slot_i == ring) { slot_i = 0; slot_par ^= 1u; }
+        if (is_k || qstep != qsteps - 1) continue;
+
+        // =============== a full query tile is quantized: score, select, emit
+        const int i = tile * K1C_TILE + rr;
+        const bool valid = i < Nq;
+        const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
+        if (kk >= Nk) {                                             // every key kept
+            if (valid) {
+                for (int w = part; w < NW; w += 2) {
+                    const int nv = Nk - 32 * w;
+                    p.mask[row * NW + w] = nv >= 32 ? 0xffffffffu : (1u << nv) - 1u;
+                }
+                if (p.idx && part == 0)
+                    for (int j = 0; j < Nk; ++j) p.idx[row * kk + j] = j;
+            }
+            continue;
+        }
+        if (tid == 0) {
+            tcgen05_fence_after_sync();
+            for (int ks = 0; ks < (L.hdp >> 4); ++ks) {
+                const uint64_t da = umma_smem_desc(smem_u32(s_qop + (size_t)(2 * ks) * K1C_TILE * 16), K1C_TILE * 16, 128);
+                const uint64_t db = umma_smem_desc(smem_u32(s_kop + (size_t)(2 * ks) * NMMA * 16), NMMA * 16, 128);
+                umma_bf16_ss(tmem, da, db, idesc, ks > 0);
+            }
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1u;
+        tcgen05_fence_after_sync();
+        if (!__any_sync(FULL, valid)) continue;                     // a warp of rows past Nq has nothing to select
+
+        // ordered 32-bit key of an accumulator value: the exact mode ranks A1(s) * scale as the
+        // reference does (matmul.py:89-91 then main.py:102); -0 is canonicalised by ordered_key
+        auto key_of = [&](uint32_t raw) -> uint32_t {
+            float s = __uint_as_float(raw);
+            if (true_mode) {
+                if (bf16) s = bf16_half_away(s);
+                s = __fmul_rn(s, sscale);
+            }
+            return ordered_key(s);
+        };
+        const int col0 = part * NCH * 32;                           // this thread's first key column
+
+        // ---- select: three digit levels over the ordered key, most significant first
+        uint32_t P = 0u;                                            // digits chosen so far
+#pragma unroll 1
+        for (int level = 0; level < 3; ++level) {
+            const int D = level == 2 ? 4 : 14;
+            const int shift = level == 0 ? 18 : level == 1 ? 4 : 0;
+            const uint32_t dmask = (1u << D) - 1u;
+            const uint32_t above = dmask + 2u;                      // digit code of a key above the prefix
+            uint32_t kw[NCH * 16];
+#pragma unroll
+            for (int w = 0; w < NCH; ++w) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r[16];
+                    tmem_ld_16x32bx2_x16<NCH * 32>(my_tmem + w * 32 + h * 16, r);
+                    tmem_ld_wait();
+                    const int nv = Nk - (col0 + w * 32 + h * 16);   // valid columns among these 16
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const uint32_t u = key_of(r[t]);
+                        const uint32_t hi = level == 0 ? 0u : (u >> shift) >> D;
+                        uint32_t v = ((u >> shift) & dmask) + 1u;
+                        v = hi > P ? above : v;
+                        v = (hi < P || t >= nv) ? 0u : v;
+                        const uint32_t f = v + K1_KEY_BIAS;
+                        if (h == 0) kw[16 * w + t] = f;
+                        else kw[16 * w + t] = __byte_perm(kw[16 * w + t], f, 0x5410);
+                    }
+                }
+            }
+            uint32_t tsel = 0u;
+#pragma unroll 1
+            for (int bit = D - 1; bit >= 0; --bit) {
+                const uint32_t cand = tsel | (1u << bit);
+                const int mine = count_ge_regs<NCH * 16>(kw, cand + 1u + K1_KEY_BIAS);
+                const int theirs = __shfl_xor_sync(FULL, mine, 16);
+                if (mine + theirs >= kk) tsel = cand;
+            }
+            P = (P << D) | tsel;
+        }
+        const uint32_t T = P;                                       // ordered key of the top_k-th largest score
+
+        // ---- emit: keys > T kept, keys == T kept in ascending key index until top_k
+        uint32_t gtw[NCH], eqw[NCH];
+        int ngt_m = 0, neq_m = 0;
+#pragma unroll
+        for (int w = 0; w < NCH; ++w) {
+            uint32_t gt = 0u, eq = 0u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t r[16];
+                tmem_ld_16x32bx2_x16<NCH * 32>(my_tmem + w * 32 + h * 16, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const uint32_t u = key_of(r[t]);
+                    gt |= u > T ? 1u << (16 * h + t) : 0u;
+                    eq |= u == T ? 1u << (16 * h + t) : 0u;
+                }
+            }
+            const int nv = Nk - (col0 + w * 32);
+            const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : (1u << nv) - 1u);
+            gtw[w] = gt & vm;
+            eqw[w] = eq & vm;
+            ngt_m += __popc(gtw[w]);
+            neq_m += __popc(eqw[w]);
+        }
+        // the tile's scores are consumed: TMEM and the Q-side shared memory may be reused
+        tcgen05_fence_before_sync();
+        {
+            const int ngt_o = __shfl_xor_sync(FULL, ngt_m, 16);
+            const int neq_o = __shfl_xor_sync(FULL, neq_m, 16);
+            const int rem_all = kk - (ngt_m + ngt_o);               // ties to keep in the whole row
+            const int ties0 = part == 0 ? neq_m : neq_o;
+            const int ngt0 = part == 0 ? ngt_m : ngt_o;
+            int rem = part == 0 ? rem_all : rem_all - min(rem_all, ties0);
+            int pos = part == 0 ? 0 : ngt0 + min(rem_all, ties0);
+#pragma unroll
+            for (int w = 0; w < NCH; ++w) {
+                const int gw = part * NCH + w;
+                const int cnt = __popc(eqw[w]);
+                uint32_t take = eqw[w];
+                if (cnt > rem) take = keep_lowest_bits_fast(eqw[w], rem);
+                rem -= min(cnt, rem);
+                const uint32_t word = gtw[w] | take;
+                if (valid && gw < NW) {
+                    p.mask[row * NW + gw] = word;
+                    if (p.idx) {
+                        uint32_t w2 = word;
+                        while (w2) {
+                            const int bpos = __ffs(w2) - 1;
+                            w2 &= w2 - 1u;
+                            p.idx[row * kk + pos++] = gw * 32 + bpos;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)L.tmem_cols);
+}
+
+}  // namespace mxp

@@ -11,9 +11,11 @@ maintainer can swap the body of ``forward`` (INTEGRATION.md shows the patch).  T
 projections stay whatever the host model uses (``mx.Linear`` in the reference - outside the hot
 path); here they are plain ``nn.Linear`` unless the caller passes its own.
 
-Implemented: mx_quant && top_k && approx/ex_pred && pred_mode == "ex_pred" (the pruned path) and
+Implemented: mx_quant && top_k && approx/ex_pred with pred_mode "ex_pred" (the pruned hot path),
+"partial_Q" or "partial_K"; mx_quant && top_k && !approx (top-k of the true scores); and
 mx_quant && !top_k (dense MXINT8 attention, what the reference runs in the last block of each
-model - same kernels with every key kept).  Every other combination raises (no silent fallback).
+model - same kernels with every key kept).  Every other combination (two_step_leading_ones, MXINT4,
+ELSA, mx_quant=False) raises - no silent fallback.
 """
 from typing import Optional
 
@@ -27,12 +29,13 @@ from .specs import resolve_specs
 class PrunedAttentionCore(nn.Module):
     """q, k, v (B,H,N,hd) fp32 views -> x (B,N,H*hd), ready for the output projection."""
 
-    def __init__(self, mx_specs, k: int, scale: Optional[float] = None):
+    def __init__(self, mx_specs, k: int, scale: Optional[float] = None, pred_mode: str = "ex_pred"):
         super().__init__()
         resolve_specs(mx_specs)
         self.mx_specs = mx_specs
         self.k = int(k)
         self.scale = scale
+        self.pred_mode = pred_mode
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
                 key_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -42,18 +45,26 @@ class PrunedAttentionCore(nn.Module):
         # k <= 0: dense MXINT8 attention (the reference's top_k=False blocks) = every key kept
         top_k = self.k if self.k > 0 else k.shape[2]
         ops.pruned_attention(q, k, v, self.mx_specs, top_k, scale=self.scale, out=buf.permute(0, 2, 1, 3),
-                             key_bias=key_bias)
+                             key_bias=key_bias, pred_mode=self.pred_mode)
         return buf.reshape(B, N, H * hd)
 
 
-def _require_hot_path(mx_quant, top_k, approx, pred_mode, where):
+def _require_hot_path(mx_quant, top_k, approx, pred_mode, where) -> str:
+    """Validate the reference's flag combination; returns the ops.PRED_MODES key that ranks the keys
+    (workloads/deit/scripts/main.py:104-131: approx_flag picks the predictor, else top-k of the true scores)."""
     if mx_quant and not top_k:
-        return          # dense MXINT8 attention (deit main.py:282-296: the last block runs top_k=False)
-    if not (mx_quant and top_k and approx and pred_mode == "ex_pred"):
+        return "ex_pred"    # dense MXINT8 attention (deit main.py:282-296: the last block runs top_k=False)
+    if not mx_quant:
+        raise NotImplementedError(f"{where}: mx_quant=False (the fp32 attention of the host model) is not on the "
+                                  "B200 path and there is no fallback")
+    if not approx:
+        return "exact"
+    if pred_mode not in ("ex_pred", "partial_Q", "partial_K"):
         raise NotImplementedError(
-            f"{where}: only mx_quant=True, top_k=True, approx/ex_pred=True, pred_mode='ex_pred' is on the "
-            f"B200 hot path (got mx_quant={mx_quant}, top_k={top_k}, approx={approx}, pred_mode={pred_mode!r}); "
-            "dense / related-work predictor modes are out of scope (SURVEY.md 8f3) and there is no fallback")
+            f"{where}: pred_mode={pred_mode!r} is not built (built: 'ex_pred', 'partial_Q', 'partial_K', and "
+            "approx=False); two_step_leading_ones / MXINT4 / ELSA are related-work predictors outside the path "
+            "(SURVEY.md 8f3) and there is no fallback")
+    return pred_mode
 
 
 def to_mx_linear(lin: nn.Linear, mx_specs) -> "MxLinear":
@@ -75,7 +86,7 @@ class QuantizedAttention(nn.Module):
     def __init__(self, orig_attn, mx_quant=False, mx_specs=None, top_k=True, k=20, approx_flag=True,
                  pred_mode="ex_pred", anal=False, file_name_dict=None, block_idx=None, orthogonal_matrix=None):
         super().__init__()
-        _require_hot_path(mx_quant, top_k, approx_flag, pred_mode, "QuantizedAttention")
+        mode = _require_hot_path(mx_quant, top_k, approx_flag, pred_mode, "QuantizedAttention")
         if anal:
             raise NotImplementedError("--anal analysis dumps are out of scope (SURVEY.md 8f4)")
         self.num_heads = orig_attn.num_heads
@@ -85,7 +96,7 @@ class QuantizedAttention(nn.Module):
         self.proj_drop = getattr(orig_attn, "proj_drop", nn.Identity())
         self.block_idx = block_idx
         self.current_timestep = 0
-        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale)
+        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale, pred_mode=mode)
 
     def forward(self, x):
         B, N, C = x.shape
@@ -105,7 +116,7 @@ class Attention(nn.Module):
                  exclude_timesteps=None, orthogonal_matrix=None):
         super().__init__()
         assert dim % num_heads == 0, 'dim should be divisible by num_heads'
-        _require_hot_path(mx_quant, top_k, ex_pred, pred_mode, "Attention")
+        mode = _require_hot_path(mx_quant, top_k, ex_pred, pred_mode, "Attention")
         if anal or exclude_timesteps:
             raise NotImplementedError("anal / exclude_timesteps (dense steps) are out of scope")
         self.num_heads, self.head_dim = num_heads, dim // num_heads
@@ -117,7 +128,7 @@ class Attention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.block_idx = block_idx
         self.current_timestep = 0
-        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale)
+        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale, pred_mode=mode)
 
     def forward(self, x):
         B, N, C = x.shape
@@ -145,7 +156,7 @@ class MXSelfAttention(nn.Module):
 
     def set_config(self, mx_quant=False, mx_specs=None, top_k=False, k=20, ex_pred=False, exclude_timesteps=None,
                    pred_mode="ex_pred", block_idx=None, anal=False, file_name_dict=None, orthogonal_matrix=None):
-        _require_hot_path(mx_quant, top_k, ex_pred, pred_mode, "MXSelfAttention.set_config")
+        mode = _require_hot_path(mx_quant, top_k, ex_pred, pred_mode, "MXSelfAttention.set_config")
         if anal or exclude_timesteps:
             raise NotImplementedError("anal / exclude_timesteps (dense steps) are out of scope")
         self.block_idx = block_idx
@@ -153,7 +164,8 @@ class MXSelfAttention(nn.Module):
         self.to_q, self.to_k, self.to_v = (to_mx_linear(m, mx_specs) for m in (self.to_q, self.to_k, self.to_v))
         self.to_out[0] = to_mx_linear(self.to_out[0], mx_specs)
         # reference: scale_factor = 1 / math.sqrt(q.size(-1)) applied as an fp32 scalar (:647-653)
-        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=1.0 / (self.head_dim ** 0.5))
+        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=1.0 / (self.head_dim ** 0.5),
+                                        pred_mode=mode)
         return self
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs):

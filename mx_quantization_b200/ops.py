@@ -108,6 +108,19 @@ def exp_sign_approx(x: torch.Tensor, mx_specs) -> torch.Tensor:
     return out
 
 
+# The reference's sources of the top-k ranking (workloads/deit/scripts/main.py:105-131): pred_mode strings as
+# the reference spells them, plus "exact" for its `top_k and not approx_flag` branch (top-k of the true scores).
+PRED_MODES = {"ex_pred": 0, "partial_Q": 1, "partial_K": 2, "exact": 3}
+
+
+def _pred_mode_code(pred_mode: str) -> int:
+    if pred_mode not in PRED_MODES:
+        raise NotImplementedError(
+            f"pred_mode={pred_mode!r}: built modes are {sorted(PRED_MODES)}; two_step_leading_ones (EXION), MXINT4 "
+            "(Sanger) and ELSA are not built (SURVEY.md 8f3) and there is no fallback")
+    return PRED_MODES[pred_mode]
+
+
 def _qk_shapes(q, k):
     B, H, Nq, hd = q.shape
     if k.shape[0] != B or k.shape[1] != H or k.shape[3] != hd:
@@ -131,11 +144,16 @@ def predict_scores(q: torch.Tensor, k: torch.Tensor, mx_specs) -> torch.Tensor:
 
 
 def predict_topk(q: torch.Tensor, k: torch.Tensor, mx_specs, top_k: int, return_idx: bool = False,
-                 return_codes: bool = False):
-    """Fused quantize + exp-sign predictor + per-row top-k.
+                 return_codes: bool = False, pred_mode: str = "ex_pred", scale: Optional[float] = None):
+    """Fused quantize + predictor + per-row top-k.
 
     Returns a dict: mask int32 (B,H,Nq,ceil(Nk/32)) [bit j%32 of word j//32 = key j kept],
-    optionally idx int32 (B,H,Nq,top_k) ascending key order, and q/k codes+exps."""
+    optionally idx int32 (B,H,Nq,top_k) ascending key order, and q/k codes+exps.
+    pred_mode: "ex_pred" (exponent-sign, default), "partial_Q", "partial_K" or "exact" (top-k of the true
+    scores * scale) - see PRED_MODES."""
+    mode = _pred_mode_code(pred_mode)
+    if mode != 0:
+        return _predict_topk_mode(q, k, mx_specs, top_k, mode, scale, return_idx, return_codes)
     sp = resolve_specs(mx_specs)
     lib = _lib.load()
     q, k = _view4(q, "q"), _view4(k, "k")
@@ -160,6 +178,27 @@ def predict_topk(q: torch.Tensor, k: torch.Tensor, mx_specs, top_k: int, return_
                                   _ptr(res.get("k_codes")), _ptr(res.get("k_exps")),
                                   _ptr(ws), ws_bytes, _stream())
     _lib.check(rc, "mxp_predict_topk")
+    return res
+
+
+def _predict_topk_mode(q, k, mx_specs, top_k, mode, scale, return_idx, return_codes):
+    if return_codes:
+        raise ValueError("return_codes is available with pred_mode='ex_pred' only")
+    sp = resolve_specs(mx_specs)
+    lib = _lib.load()
+    q, k = _view4(q, "q"), _view4(k, "k")
+    dev = _same_device(q, k)
+    B, H, Nq, Nk, hd = _qk_shapes(q, k)
+    scale = float(hd) ** -0.5 if scale is None else float(scale)
+    res = {}
+    with torch.cuda.device(dev):
+        res["mask"] = torch.empty((B, H, Nq, (Nk + 31) // 32), dtype=torch.int32, device=dev)
+        if return_idx:
+            res["idx"] = torch.empty((B, H, Nq, int(top_k)), dtype=torch.int32, device=dev)
+        rc = lib.mxp_predict_topk_mode(_ptr(q), *_strides(q), _ptr(k), *_strides(k), B, H, Nq, Nk, hd, int(top_k),
+                                       mode, scale, sp.bfloat_bits, int(sp.flush), _ptr(res["mask"]),
+                                       _ptr(res.get("idx")), _ptr(None), 0, _stream())
+    _lib.check(rc, "mxp_predict_topk_mode")
     return res
 
 
@@ -194,8 +233,12 @@ def sparse_attention(q_codes, q_exps, k_codes, k_exps, v: torch.Tensor, mask: to
 def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs, top_k: int,
                      scale: Optional[float] = None, return_mask: bool = False,
                      out: Optional[torch.Tensor] = None, _kernel_ms: Optional[list] = None,
-                     key_bias: Optional[torch.Tensor] = None):
+                     key_bias: Optional[torch.Tensor] = None, pred_mode: str = "ex_pred"):
     """MXINT8 exponent-sign predicted top-k attention: q,k,v (B,H,N,hd) fp32 -> out (B,H,Nq,hd).
+
+    ``pred_mode``: what ranks the keys - "ex_pred" (default), "partial_Q", "partial_K" (the reference's
+    pred_mode values, workloads/deit/scripts/main.py:109-114) or "exact" (its approx_flag=False branch:
+    top-k of the true scores, main.py:130).  Everything after the selection is the same.
 
     Drop-in for lines 101-152 of workloads/deit/scripts/main.py (DiT models.py:168-225, PixArt
     MX_transformer_block.py:647-710) when mx_quant, top_k, approx_flag and pred_mode=="ex_pred".
@@ -215,6 +258,9 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
     if tuple(v.shape) != (B, H, Nk, hd):
         raise ValueError(f"v {tuple(v.shape)} must be (B,H,Nk,head_dim) = {(B, H, Nk, hd)}")
     scale = float(hd) ** -0.5 if scale is None else float(scale)
+    mode = _pred_mode_code(pred_mode)
+    if mode != 0 and (key_bias is not None or _kernel_ms is not None):
+        raise ValueError("key_bias / the per-kernel profile entry are available with pred_mode='ex_pred' only")
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((B, H, Nq, hd), dtype=torch.float32, device=dev)
@@ -226,7 +272,9 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
         args = (_ptr(q), *_strides(q), _ptr(k), *_strides(k), _ptr(v), *_strides(v),
                 B, H, Nq, Nk, hd, int(top_k), scale, sp.bfloat_bits, int(sp.flush),
                 _ptr(out), *_strides(out), _ptr(mask), _ptr(ws), ws_bytes, _stream())
-        if key_bias is not None:
+        if mode != 0:
+            rc = lib.mxp_pruned_attention_mode(*args[:18], mode, *args[18:])
+        elif key_bias is not None:
             if key_bias.dtype != torch.float32 or key_bias.numel() != B * Nk or key_bias.device != q.device:
                 raise ValueError("key_bias must be an fp32 tensor with B*Nk elements, (B, ..., Nk), on q's device")
             if _kernel_ms is not None:

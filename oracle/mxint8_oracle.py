@@ -17,6 +17,8 @@ It restates, stage by stage, what d9bjo0522/mx_quantization computes on this pat
   A6  top-k                        workloads/deit/scripts/main.py:123  (canonical rule below)
   A7  true scores (mx.matmul)      microxscaling/mx/matmul.py:32-100, main.py:101-102,124
   A8  softmax / scatter / P.V      workloads/deit/scripts/main.py:147-152
+  f3  other rankings               partial_Q / partial_K (funcs/exponent_based_prediction.py:274-318,
+                                   main.py:111-114) and top-k of the true scores (main.py:130)
 
 Parity pinning: ``tests/golden/make_golden.py`` runs the *unmodified reference* (imported
 from /root/reference in the authoring container) on seeded inputs and commits its outputs
@@ -245,6 +247,20 @@ def pred_scores_matmul(qc, qe, kc, ke, block: int = BLOCK) -> torch.Tensor:
     return aq @ ak.transpose(-2, -1)
 
 
+def pred_scores_mode(qc, qe, kc, ke, pred_mode: str = "ex_pred", block: int = BLOCK) -> torch.Tensor:
+    """`pred_scores = ex_quant_q @ ex_quant_k^T` (workloads/deit/scripts/main.py:118) for the predictor
+    variants that reuse the MXINT8 codes:
+      ex_pred    both sides +-2^e                             funcs/exponent_based_prediction.py:44-94
+      partial_Q  Q = MXINT8 value c * 2^(e-6), K = +-2^e      funcs/exponent_based_prediction.py:300-318
+      partial_K  Q = +-2^e, K = MXINT8 value                  funcs/exponent_based_prediction.py:274-298
+    fp32 matmul, as the reference computes it."""
+    if pred_mode not in ("ex_pred", "partial_Q", "partial_K"):
+        raise ValueError(f"pred_mode {pred_mode!r}")
+    aq = dequantize_mxint8(qc, qe, block) if pred_mode == "partial_Q" else exponent_based_sign(qc, qe, block)
+    ak = dequantize_mxint8(kc, ke, block) if pred_mode == "partial_K" else exponent_based_sign(kc, ke, block)
+    return aq @ ak.transpose(-2, -1)
+
+
 # --------------------------------------------------------------------------------------
 # A6: canonical top-k
 # --------------------------------------------------------------------------------------
@@ -308,7 +324,8 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
                      scale: Optional[float] = None, bfloat: int = 32, flush: bool = False,
                      idx: Optional[torch.Tensor] = None, use_torch_topk: bool = False,
                      integer_scores: bool = False,
-                     key_bias: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                     key_bias: Optional[torch.Tensor] = None,
+                     pred_mode: str = "ex_pred") -> Dict[str, torch.Tensor]:
     """The whole path on CPU (q, k, v: fp32 (B,H,N,hd)); returns every intermediate.
 
     key_bias: additive attention bias broadcastable to (B,1,1,Nk), as PixArt's cross-attention
@@ -319,6 +336,8 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
     set).  use_torch_topk: leave torch.topk in place as the reference does (timing only).
     integer_scores: rank on pred_scores_integer (block-exact sums; what the CUDA kernel
     computes) instead of the fp32 matmul - identical wherever pred_window_ok holds.
+    pred_mode: "ex_pred" | "partial_Q" | "partial_K" (pred_scores_mode) or "exact" - the reference's
+    approx_flag=False branch, `torch.topk(true_scores, k)` (main.py:130).
     """
     q, k, v = (t.to(torch.float32) for t in (q, k, v))
     n_keys = k.shape[-2]
@@ -326,9 +345,18 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
     qc, qe = quantize_mxint8(q, BLOCK, bfloat, flush)
     kc, ke = quantize_mxint8(k, BLOCK, bfloat, flush)
     res: Dict[str, torch.Tensor] = {"q_codes": qc, "q_exps": qe, "k_codes": kc, "k_exps": ke}
+    qd, kd = dequantize_mxint8(qc, qe), dequantize_mxint8(kc, ke)
+    true = _elemwise_out(qd @ kd.transpose(-2, -1), bfloat) * scale
+    if key_bias is not None:
+        true = true + key_bias.to(torch.float32)                     # true_scores += attn_bias, :803
     if idx is None:
-        pred = (pred_scores_integer if integer_scores else pred_scores_matmul)(qc, qe, kc, ke)
-        if key_bias is not None:
+        if pred_mode == "exact":
+            pred = true
+        elif pred_mode != "ex_pred":
+            pred = pred_scores_mode(qc, qe, kc, ke, pred_mode)
+        else:
+            pred = (pred_scores_integer if integer_scores else pred_scores_matmul)(qc, qe, kc, ke)
+        if key_bias is not None and pred_mode != "exact":
             pred = pred + key_bias.to(torch.float32)                 # fp32 add, :822
         res["pred_scores"] = pred
         if use_torch_topk:
@@ -336,10 +364,6 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
         else:
             idx = canonical_topk(pred, top_k)
     res["idx"] = idx
-    qd, kd = dequantize_mxint8(qc, qe), dequantize_mxint8(kc, ke)
-    true = _elemwise_out(qd @ kd.transpose(-2, -1), bfloat) * scale
-    if key_bias is not None:
-        true = true + key_bias.to(torch.float32)                     # true_scores += attn_bias, :803
     vals = true.gather(-1, idx)
     res["true_vals"] = vals
     res["out"] = sparse_softmax_pv(vals, idx, v, n_keys, bfloat, flush)

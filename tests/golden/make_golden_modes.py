@@ -1,0 +1,76 @@
+"""Generate tests/golden/modes_*.npz: the reference's OTHER top-k rankings run with the
+UNMODIFIED reference functions on seeded inputs.
+
+    python tests/golden/make_golden_modes.py          (authoring container only: needs /root/reference)
+
+  partial_Q / partial_K   funcs.exponent_approximation(...).partial_Q() / .partial_K()
+                          (funcs/exponent_based_prediction.py:274-318) then `ex_q @ ex_k^T`
+                          (workloads/deit/scripts/main.py:111-118)
+  exact                   the `top_k and not approx_flag` branch: top-k of
+                          mx.matmul(q, k^T) * scale  (main.py:101-102,130)
+followed by the same gather / softmax / scatter_ / mx.matmul(attn, v) as every mode (main.py:124,147-152).
+As in make_golden.py, torch.topk is replaced by the first k of a stable descending sort (canonical tie
+rule) and the raw torch.topk indices are stored beside it.
+"""
+import os
+
+import numpy as np
+import torch
+
+from make_golden import HERE, exponent_approximation, make_inputs, mx_matmul, mx_specs
+
+MODES = ("partial_Q", "partial_K", "exact")
+
+CASES = [
+    # name,              B  H  N    hd  k   bfloat flush  kind     seed
+    ("modes_deit",       1, 2, 48,  64, 12, 32, False, "randn",  21),
+    ("modes_dit_bf16",   1, 2, 40,  72, 10, 16, False, "randn",  22),
+    ("modes_pixart",     1, 2, 33,  72,  9, 32, True,  "edges",  23),
+    ("modes_deit_197",   1, 1, 197, 64, 30, 32, False, "randn",  24),
+]
+
+
+def reference_mode(q, k, v, top_k, scale, specs, mode):
+    out = {}
+    true_scores = mx_matmul(q, k.transpose(-2, -1), mx_specs=specs, mode_config='aa')
+    true_scores = true_scores * scale
+    if mode == "exact":
+        rank = true_scores
+    else:
+        obj = exponent_approximation(Q=q, K=k, mx_specs=specs)
+        ex_q, ex_k = obj.partial_Q() if mode == "partial_Q" else obj.partial_K()
+        rank = ex_q @ ex_k.transpose(-2, -1)
+    out["rank_scores"] = rank
+    out["topk_idx_torch"] = torch.topk(rank, top_k, dim=-1, largest=True, sorted=True).indices
+    idx = torch.sort(rank, dim=-1, descending=True, stable=True).indices[..., :top_k].contiguous()
+    out["idx"] = idx
+    vals = true_scores.gather(dim=-1, index=idx)
+    attn = torch.zeros_like(true_scores)
+    attn.scatter_(-1, idx, torch.softmax(vals, dim=-1).to(attn.dtype))
+    out["out"] = mx_matmul(attn, v, mx_specs=specs, mode_config='aa')
+    return out
+
+
+def main():
+    torch.set_num_threads(1)
+    for name, B, H, N, hd, top_k, bfloat, flush, kind, seed in CASES:
+        specs = mx_specs(bfloat, flush)
+        q, k, v = make_inputs(B, H, N, hd, seed, kind)
+        arrays = {"q": q.numpy(), "k": k.numpy(), "v": v.numpy()}
+        for mode in MODES:
+            ref = reference_mode(q, k, v, top_k, hd ** -0.5, specs, mode)
+            for key, val in ref.items():
+                a = val.numpy()
+                if "idx" in key:
+                    a = a.astype(np.int16)
+                if key == "rank_scores" and N > 64:
+                    continue                      # keep the big fixture small
+                arrays[f"{mode}.{key}"] = a
+        arrays["meta"] = np.array([B, H, N, hd, top_k, bfloat, int(flush)], dtype=np.int64)
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **arrays)
+        print(f"{name}: wrote {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

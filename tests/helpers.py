@@ -61,6 +61,11 @@ def unpack_mask(mask_i32, n_keys):
     return O.mask_words_to_dense(mask_i32.cpu().to(torch.int64) & 0xFFFFFFFF, n_keys)
 
 
+def canonical_idx_from_mask(dense, top_k):
+    """Kept-key indices (ascending) of a dense bool mask with exactly top_k kept keys per row."""
+    return torch.sort(dense.to(torch.int8), dim=-1, descending=True, stable=True).indices[..., :top_k].contiguous()
+
+
 def load_golden(name):
     z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     d = {k: torch.from_numpy(z[k].astype(np.int64) if z[k].dtype == np.int16 else z[k]) for k in z.files}

@@ -7,8 +7,8 @@ import pytest
 import torch
 
 from oracle import mxint8_oracle as O
-from tests.helpers import (assert_out_close, fused_qkv_views, load_golden, make_qkv, mx_specs,
-                           unpack_mask)
+from tests.helpers import (assert_out_close, canonical_idx_from_mask, fused_qkv_views, load_golden, make_qkv,
+                           mx_specs, unpack_mask)
 
 pytestmark = pytest.mark.gpu
 
@@ -496,3 +496,102 @@ def test_cuda_graph_capture_and_replay(mxq):
     got = out.clone()
     want = mxq.pruned_attention(qkv[0], qkv[1], qkv[2], specs, top_k).permute(0, 2, 1, 3)
     assert torch.equal(got, want.contiguous())
+
+
+# ---- the reference's other rankings: partial_Q / partial_K / top-k of the true scores ----
+MODES = ["partial_Q", "partial_K", "exact"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["modes_deit", "modes_dit_bf16", "modes_pixart", "modes_deit_197"])
+def test_other_rankings_reference_golden(mxq, name, mode):
+    """Masks and outputs of the unmodified reference (tests/golden/make_golden_modes.py)."""
+    d, m = load_golden(name)
+    specs = mx_specs(m["bfloat"], m["flush"])
+    q, k, v = d["q"].cuda(), d["k"].cuda(), d["v"].cuda()
+    out, mask = mxq.pruned_attention(q, k, v, specs, m["top_k"], return_mask=True, pred_mode=mode)
+    got = unpack_mask(mask, m["N"])
+    want = torch.zeros_like(got)
+    want.scatter_(-1, d[f"{mode}.idx"], True)
+    assert torch.equal(got, want)
+    r = O.pruned_attention(d["q"], d["k"], d["v"], m["top_k"], bfloat=m["bfloat"], flush=m["flush"],
+                           idx=d[f"{mode}.idx"])
+    ref = {"true_vals": r["true_vals"], "idx": d[f"{mode}.idx"], "out": d[f"{mode}.out"]}
+    assert_out_close(out.cpu(), ref, d["v"], m["N"], m["bfloat"], OUT_TOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("B,H,Nq,Nk,hd,kfrac,bfloat,kind", [
+    (2, 3, 197, 197, 64, 0.15, 32, "randn"),
+    (1, 2, 256, 256, 72, 0.6, 16, "randn"),
+    (1, 2, 130, 77, 72, 0.3, 32, "edges"),          # rectangular, two query tiles, ragged key chunk
+    (1, 1, 64, 32, 32, 0.5, 32, "randn"),
+    (2, 2, 100, 224, 128, 0.05, 32, "randn"),
+    (1, 2, 197, 197, 64, 0.2, 32, "lognormal"),     # wide exponent spread: ranks on the ordered fp32 key
+    (1, 1, 40, 40, 64, 1.0, 32, "randn"),           # every key kept
+])
+def test_other_rankings_vs_oracle(mxq, B, H, Nq, Nk, hd, kfrac, bfloat, kind, mode):
+    top_k = max(1, min(Nk, int(round(kfrac * Nk))))
+    q, k, v = make_qkv(B, H, Nq, hd, seed=31, kind=kind, Nk=Nk)
+    specs = mx_specs(bfloat, False)
+    res = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k, return_idx=True, pred_mode=mode)
+    ref = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, pred_mode=mode)
+    want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], Nk), Nk)
+    got = unpack_mask(res["mask"], Nk)
+    if kind == "lognormal":
+        # terms of one pair can spread past the tensor core's exact window (and past fp32's 24 bits, where
+        # the reference's own BLAS order decides): near-ties may flip, everything else must agree
+        assert float((got == want).all(-1).float().mean()) > 0.97
+        assert bool((got.sum(-1) == top_k).all())
+    else:
+        assert torch.equal(got, want)
+        assert torch.equal(res["idx"].cpu().to(torch.int64), torch.sort(ref["idx"], dim=-1).values)
+    out, mask = mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), specs, top_k, return_mask=True, pred_mode=mode)
+    assert torch.equal(mask, res["mask"])
+    ref2 = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, idx=canonical_idx_from_mask(unpack_mask(mask, Nk), top_k))
+    assert_out_close(out.cpu(), ref2, v, Nk, bfloat, OUT_TOL)
+
+
+@pytest.mark.gpu
+def test_other_rankings_full_size_properties(mxq):
+    """DeiT-base layer shape (B=256,H=12,N=197,hd=64,k=30): every row keeps exactly k keys; the 'exact' ranking
+    keeps, per row, a set whose smallest true score is >= every dropped key's (checked on a head sample)."""
+    B, H, N, hd, top_k = 256, 12, 197, 64, 30
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(B, H, N, hd, device="cuda", generator=g)
+    k = torch.randn(B, H, N, hd, device="cuda", generator=g)
+    specs = mx_specs(32, False)
+    for mode in MODES:
+        mask = mxq.predict_topk(q, k, specs, top_k, pred_mode=mode)["mask"]
+        bits = (mask.to(torch.int64) & 0xFFFFFFFF)
+        cnt = sum(((bits >> s) & 1) for s in range(32)).sum(-1)
+        assert bool((cnt == top_k).all()), mode
+        sl = (slice(0, 256, 97), slice(0, 12, 5))
+        ref = O.pruned_attention(q[sl].cpu(), k[sl].cpu(), k[sl].cpu(), top_k, pred_mode=mode)
+        want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], N), N)
+        assert torch.equal(unpack_mask(mask[sl], N), want), mode
+
+
+@pytest.mark.gpu
+def test_other_rankings_module_and_errors(mxq):
+    from mx_quantization_b200.modules import Attention
+    torch.manual_seed(0)
+    specs = mx_specs(16, False)
+    x = torch.randn(2, 64, 128, device="cuda")
+    outs = {}
+    for name, kw in {"ex": dict(ex_pred=True, pred_mode="ex_pred"), "pq": dict(ex_pred=True, pred_mode="partial_Q"),
+                     "exact": dict(ex_pred=False)}.items():
+        torch.manual_seed(1)
+        m = Attention(128, num_heads=2, qkv_bias=True, mx_quant=True, mx_specs=specs, top_k=True, k=16, **kw).cuda()
+        outs[name] = m(x)
+        assert outs[name].shape == x.shape and bool(torch.isfinite(outs[name]).all())
+    assert not torch.equal(outs["ex"], outs["exact"])
+    with pytest.raises(NotImplementedError):
+        Attention(128, num_heads=2, mx_quant=True, mx_specs=specs, top_k=True, k=16, ex_pred=True, pred_mode="MXINT4")
+    q = torch.randn(1, 1, 300, 64, device="cuda")
+    with pytest.raises(ValueError):                      # modes 1-3: Nk <= 256
+        mxq.predict_topk(q, q, specs, 10, pred_mode="partial_K")
+    with pytest.raises(NotImplementedError):
+        mxq.predict_topk(q, q, specs, 10, pred_mode="ELSA")

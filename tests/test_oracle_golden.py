@@ -137,6 +137,28 @@ def test_scatter_script_kat():
     assert int((S < 0).sum()) == 19064
 
 
+MODE_CASES = ["modes_deit", "modes_dit_bf16", "modes_pixart", "modes_deit_197"]
+
+
+@pytest.mark.parametrize("mode", ["partial_Q", "partial_K", "exact"])
+@pytest.mark.parametrize("name", MODE_CASES)
+def test_other_rankings_against_reference(golden_dir, name, mode):
+    """partial_Q / partial_K (funcs/exponent_based_prediction.py:274-318) and the approx_flag=False branch
+    (workloads/deit/scripts/main.py:130), outputs of the unmodified reference
+    (tests/golden/make_golden_modes.py)."""
+    d, m = load(golden_dir, name)
+    r = O.pruned_attention(d["q"], d["k"], d["v"], m["top_k"], bfloat=m["bfloat"], flush=m["flush"], pred_mode=mode)
+    if f"{mode}.rank_scores" in d:
+        assert torch.equal(r["pred_scores"], d[f"{mode}.rank_scores"])
+    assert torch.equal(r["idx"], d[f"{mode}.idx"])
+    # raw torch.topk (tie order unspecified) keeps the same strictly-greater set
+    pred = r["pred_scores"]
+    kth = pred.gather(-1, d[f"{mode}.idx"][..., -1:])
+    assert torch.equal(kth, pred.gather(-1, d[f"{mode}.topk_idx_torch"][..., -1:]))
+    ref_out = d[f"{mode}.out"]
+    assert float((r["out"] - ref_out).abs().max()) <= 1e-3 * float(ref_out.abs().max())
+
+
 CROSS_CASES = ["pixart_cross", "pixart_cross_k77", "pixart_cross_all"]
 
 

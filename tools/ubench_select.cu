@@ -1,0 +1,117 @@
+// Selection inner-loop microbenchmark: cycles per "count keys >= candidate" pass over one thread's
+// 128 register-resident keys, for the instruction sequences a top-k bisection can be built from.
+//   A  HSET2.GE + HADD2 over 64 words of two fp16-pattern keys          (K1's round-1 loop)
+//   B  VABSDIFF4.U8.ACC over 32 words of four byte keys, two candidates (count = slope of sum |k - c|)
+//   C  VIADDMNMX.S16x2.RELU + IADD over 64 words
+//   D  VABSDIFF4 once over 32 words (a single sum |k - c|)
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o ubench_select tools/ubench_select.cu
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdio>
+#include <cstdint>
+
+constexpr int PASSES = 512;
+
+__device__ __forceinline__ __half2 u2h(uint32_t x) { return *reinterpret_cast<__half2*>(&x); }
+__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256, 2) bench(const uint32_t* in, uint32_t* out, long long* cycles, int kk) {
+    uint32_t kw[64];
+#pragma unroll
+    for (int w = 0; w < 64; ++w) kw[w] = in[w * 256 + threadIdx.x] & (V == 0 ? 0x7bff7bffu : 0xffffffffu);
+    uint32_t T = 0;
+    __syncthreads();
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int p = 0; p < PASSES; ++p) {
+        const uint32_t cand = T | (1u << (p & 7)) | 0x100u;
+        int cnt;
+        if (V == 0) {
+            const __half2 c2 = u2h(cand * 0x00010001u);
+            __half2 a0 = u2h(0u), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+            for (int w = 0; w < 64; w += 4) {
+                a0 = __hadd2(a0, __hge2(u2h(kw[w]), c2));
+                a1 = __hadd2(a1, __hge2(u2h(kw[w + 1]), c2));
+                a2 = __hadd2(a2, __hge2(u2h(kw[w + 2]), c2));
+                a3 = __hadd2(a3, __hge2(u2h(kw[w + 3]), c2));
+            }
+            const __half2 t = __hadd2(__hadd2(a0, a1), __hadd2(a2, a3));
+            cnt = (int)(__low2float(t) + __high2float(t));
+        } else if (V == 1) {
+            const uint32_t c4 = (cand & 0xffu) * 0x01010101u, d4 = ((cand - 1u) & 0xffu) * 0x01010101u;
+            uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+#pragma unroll
+            for (int w = 0; w < 32; w += 2) {
+                a0 = sad4(kw[w], c4, a0); b0 = sad4(kw[w], d4, b0);
+                a1 = sad4(kw[w + 1], c4, a1); b1 = sad4(kw[w + 1], d4, b1);
+            }
+            cnt = (int)(128u + (b0 + b1) - (a0 + a1)) >> 1;
+        } else if (V == 2) {
+            const uint32_t nc = (0x00010001u - cand * 0x00010001u);
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+            for (int w = 0; w < 64; w += 4) {
+                a0 += __viaddmin_s16x2_relu(kw[w], nc, 0x00010001u);
+                a1 += __viaddmin_s16x2_relu(kw[w + 1], nc, 0x00010001u);
+                a2 += __viaddmin_s16x2_relu(kw[w + 2], nc, 0x00010001u);
+                a3 += __viaddmin_s16x2_relu(kw[w + 3], nc, 0x00010001u);
+            }
+            const uint32_t t = a0 + a1 + a2 + a3;
+            cnt = (int)((t & 0xffffu) + (t >> 16));
+        } else {
+            const uint32_t c4 = (cand & 0xffu) * 0x01010101u;
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+            for (int w = 0; w < 32; w += 4) {
+                a0 = sad4(kw[w], c4, a0); a1 = sad4(kw[w + 1], c4, a1);
+                a2 = sad4(kw[w + 2], c4, a2); a3 = sad4(kw[w + 3], c4, a3);
+            }
+            cnt = (int)(a0 + a1 + a2 + a3) >> 4;
+        }
+        const int other = __shfl_xor_sync(0xffffffffu, cnt, 16);
+        if (cnt + other >= kk) T ^= (uint32_t)(p & 3);
+    }
+    long long t1 = clock64();
+    uint32_t acc = T;
+#pragma unroll
+    for (int w = 0; w < 64; ++w) acc += kw[w];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int V>
+void run(const char* name) {
+    const int blocks = 148 * 2;
+    uint32_t *in, *out; long long* cyc;
+    cudaMalloc(&in, 16384 * 4); cudaMalloc(&out, blocks * 256 * 4); cudaMalloc(&cyc, blocks * 8);
+    static uint32_t h_in[16384];
+    for (int i = 0; i < 16384; ++i) h_in[i] = 0x3c003c00u + (uint32_t)i * 2654435761u % 0x0fff0fffu;
+    cudaMemcpy(in, h_in, sizeof h_in, cudaMemcpyHostToDevice);
+    bench<V><<<blocks, 256>>>(in, out, cyc, 60);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a);
+    bench<V><<<blocks, 256>>>(in, out, cyc, 60);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    static long long h[296]; cudaMemcpy(h, cyc, blocks * 8, cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < blocks; ++i) avg += h[i]; avg /= blocks;
+    // 16 warps per SM = 4 per scheduler run concurrently; cycles per pass as one warp sees it and
+    // scheduler cycles per (warp, pass) = that / 4
+    printf("%-34s %.1f cyc/pass/warp (4 warps/scheduler -> %.1f scheduler cyc per warp-pass), %.3f ms, err=%d\n", name,
+           avg / PASSES, avg / PASSES / 4.0, ms, (int)cudaGetLastError());
+    cudaFree(in); cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+    run<0>("A HSET2+HADD2 64 words (128 keys)");
+    run<1>("B SAD4 x2 cand 32 words (128 keys)");
+    run<2>("C VIADDMNMX+IADD 64 words");
+    run<3>("D SAD4 x1 32 words");
+    return 0;
+}
