@@ -6,6 +6,8 @@
 //   pred_mode 2  partial_K   Q = +-2^e, K = MXINT8 value        funcs/exponent_based_prediction.py:274-298, main.py:113-114
 //   pred_mode 3  exact       top-k of the TRUE scores, mx.matmul(q, k^T) * scale - the reference's
 //                            `top_k and not approx_flag` branch  main.py:101-102,130
+//   pred_mode 4  MXINT4      both sides re-quantized as MXINT4, c4 * 2^(e-2), |c4| <= 7 (Sanger)
+//                            funcs/exponent_based_prediction.py:179-199, main.py:117-118
 //
 // Both operand kinds are exact in bf16 and come out of the same per-block quantizer
 // (quantize_block_thread: r.op = c * 2^(e-6), r.pp = +-2^e), so a mode only chooses which of the two
@@ -24,7 +26,35 @@
 
 namespace mxp {
 
-constexpr int PRED_EX = 0, PRED_PARTIAL_Q = 1, PRED_PARTIAL_K = 2, PRED_TRUE = 3;
+constexpr int PRED_EX = 0, PRED_PARTIAL_Q = 1, PRED_PARTIAL_K = 2, PRED_TRUE = 3, PRED_MXINT4 = 4;
+
+// MXINT4 operand of one block: value = sign(x) * min(7, floor(|x| * 2^(2-e) + 0.5)) * 2^(e-2), the int4 element
+// format of the reference (formats.py:86-88: mbits 4, emax 0 -> the MXINT8 shared exponent e; lshift by
+// mbits - 2 = 2, round nearest, clamp to 7/4: elemwise_ops.py:155,64-65,163-164).  xv holds the block after
+// A1; <= 3 significant bits, so the bf16 truncation is exact.
+__device__ __forceinline__ void int4_operand(const uint32_t (&xv)[32], int e, bool dead, uint4 (&op4)[4]) {
+    const bool tiny = e < -100;                                     // keep 2^(2-e) finite: pre-scale by 2^60
+    const float up = tiny ? 1152921504606846976.0f : 1.0f;
+    const float s1 = dead ? 0.f : exp2i(2 - e - (tiny ? 60 : 0));
+    const float wgt = exp2i(e - 2);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            float f[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t x = xv[8 * c + 2 * h + t];
+                const float a = fabsf(__uint_as_float(x)) * up;
+                const float m = fminf(floorf(fmaf(a, s1, 0.5f)), 7.0f) * wgt;
+                f[t] = __uint_as_float(__float_as_uint(m) | (x & 0x80000000u));
+            }
+            w[h] = pack_bf16_trunc(f[0], f[1]);
+        }
+        op4[c] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
 
 template <int NC>
 __global__ void __launch_bounds__(K1C_T, 2)
@@ -38,6 +68,7 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
     const bool q_exact = mode == PRED_PARTIAL_Q || mode == PRED_TRUE;
     const bool k_exact = mode == PRED_PARTIAL_K || mode == PRED_TRUE;
     const bool true_mode = mode == PRED_TRUE;
+    const bool int4_mode = mode == PRED_MXINT4;
     const K1cSmem L = k1c_smem_layout(hd, NC, ring, G, false);
     const int nfull = L.nfull, tail = L.tail, nb = L.nb;
     const int kch = L.hdp >> 3;
@@ -152,7 +183,9 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
                 }
             }
             BlockQ r;
-            quantize_block_thread<false>(xv, full ? 32 : tail, bf16, flush, r);
+            quantize_block_thread<false>(xv, full ? 32 : tail, bf16, flush, r);      // xv: A1 applied in place
+            uint4 op4[4];
+            if (int4_mode) int4_operand(xv, r.e, flush && r.e <= -127, op4);
             const int nchunk = full ? 4 : tail_chunks, nchunk_hbm = full ? 4 : tail_chunks_hbm;
             const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
             if (is_k) {
@@ -162,7 +195,7 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
                     for (int ch = 0; ch < 4; ++ch)
                         if (ch < nchunk)
                             *reinterpret_cast<uint4*>(dst + ch * (NMMA * 16)) =
-                                !in_range ? zero4 : k_exact ? r.op[ch] : r.pp[ch];
+                                !in_range ? zero4 : int4_mode ? op4[ch] : k_exact ? r.op[ch] : r.pp[ch];
                 }
                 if (write_kop && row < kb_rows) {
                     unsigned char* dst = k_op + ((size_t)(4 * b) * kb_rows + row) * 16;
@@ -175,7 +208,8 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
                 unsigned char* dst = s_qop + ((4 * b) * K1C_TILE + rt) * 16;
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch)
-                    if (ch < nchunk) *reinterpret_cast<uint4*>(dst + ch * (K1C_TILE * 16)) = q_exact ? r.op[ch] : r.pp[ch];
+                    if (ch < nchunk) *reinterpret_cast<uint4*>(dst + ch * (K1C_TILE * 16)) =
+                        int4_mode ? op4[ch] : q_exact ? r.op[ch] : r.pp[ch];
                 if (q_op) {
                     unsigned char* gdst = q_op + (size_t)tile * OL.q_tile_bytes + ((size_t)(4 * b) * K1C_TILE + rt) * 16;
 #pragma unroll

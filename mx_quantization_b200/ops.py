@@ -110,14 +110,14 @@ def exp_sign_approx(x: torch.Tensor, mx_specs) -> torch.Tensor:
 
 # The reference's sources of the top-k ranking (workloads/deit/scripts/main.py:105-131): pred_mode strings as
 # the reference spells them, plus "exact" for its `top_k and not approx_flag` branch (top-k of the true scores).
-PRED_MODES = {"ex_pred": 0, "partial_Q": 1, "partial_K": 2, "exact": 3}
+PRED_MODES = {"ex_pred": 0, "partial_Q": 1, "partial_K": 2, "exact": 3, "MXINT4": 4}
 
 
 def _pred_mode_code(pred_mode: str) -> int:
     if pred_mode not in PRED_MODES:
         raise NotImplementedError(
-            f"pred_mode={pred_mode!r}: built modes are {sorted(PRED_MODES)}; two_step_leading_ones (EXION), MXINT4 "
-            "(Sanger) and ELSA are not built (SURVEY.md 8f3) and there is no fallback")
+            f"pred_mode={pred_mode!r}: built modes are {sorted(PRED_MODES)}; two_step_leading_ones (EXION) and ELSA "
+            "are not built (SURVEY.md 8f3) and there is no fallback")
     return PRED_MODES[pred_mode]
 
 
@@ -149,8 +149,8 @@ def predict_topk(q: torch.Tensor, k: torch.Tensor, mx_specs, top_k: int, return_
 
     Returns a dict: mask int32 (B,H,Nq,ceil(Nk/32)) [bit j%32 of word j//32 = key j kept],
     optionally idx int32 (B,H,Nq,top_k) ascending key order, and q/k codes+exps.
-    pred_mode: "ex_pred" (exponent-sign, default), "partial_Q", "partial_K" or "exact" (top-k of the true
-    scores * scale) - see PRED_MODES."""
+    pred_mode: "ex_pred" (exponent-sign, default), "partial_Q", "partial_K", "MXINT4" or "exact" (top-k of the
+    true scores * scale) - see PRED_MODES."""
     mode = _pred_mode_code(pred_mode)
     if mode != 0:
         return _predict_topk_mode(q, k, mx_specs, top_k, mode, scale, return_idx, return_codes)
@@ -236,8 +236,8 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
                      key_bias: Optional[torch.Tensor] = None, pred_mode: str = "ex_pred"):
     """MXINT8 exponent-sign predicted top-k attention: q,k,v (B,H,N,hd) fp32 -> out (B,H,Nq,hd).
 
-    ``pred_mode``: what ranks the keys - "ex_pred" (default), "partial_Q", "partial_K" (the reference's
-    pred_mode values, workloads/deit/scripts/main.py:109-114) or "exact" (its approx_flag=False branch:
+    ``pred_mode``: what ranks the keys - "ex_pred" (default), "partial_Q", "partial_K", "MXINT4" (the reference's
+    pred_mode values, workloads/deit/scripts/main.py:109-118) or "exact" (its approx_flag=False branch:
     top-k of the true scores, main.py:130).  Everything after the selection is the same.
 
     Drop-in for lines 101-152 of workloads/deit/scripts/main.py (DiT models.py:168-225, PixArt

@@ -149,6 +149,31 @@ def quantize_mxint8(x: torch.Tensor, block: int = BLOCK, bfloat: int = 32,
     return codes.contiguous(), e.to(torch.int8).contiguous()
 
 
+def fake_quant_mxint4(x: torch.Tensor, block: int = BLOCK, bfloat: int = 32,
+                      flush_subnorms: bool = False) -> torch.Tensor:
+    """quantize_mx_op(quantize_elemwise_op(x), elem_format='int4', axes=[-1]) as fp32 - the operands of the
+    reference's "MXINT4" (Sanger) predictor, funcs/exponent_based_prediction.py:179-199.
+
+    int4: ebits 0, mbits 4, emax 0 (formats.py:86-88) -> the shared exponent is the MXINT8 one; the element
+    is sign * min(7, floor(|x| / 2^e * 4 + 0.5)) / 4 (lshift by mbits-2 = 2, elemwise_ops.py:155; nearest
+    :64-65; clamp to max_norm 7/4 :163-164): value = c4 * 2^(e-2), c4 in [-7, 7]."""
+    if bfloat == 16:
+        x = bf16_round_half_away(x)
+    elif bfloat != 32:
+        raise ValueError("only bfloat in {16, 32} is on the path")
+    xb, d = _blocks_last(x.to(torch.float32), block)
+    amax = xb.abs().amax(dim=-1)
+    e = shared_exponent_from_absmax(amax)
+    if flush_subnorms:
+        xb = xb * (e > -127).to(xb.dtype).unsqueeze(-1)
+    e = e.clamp(min=-127)
+    scale = torch.ldexp(torch.ones_like(amax), e)
+    t = (xb.abs() / scale.unsqueeze(-1)) * 4.0
+    mag = torch.clamp(torch.floor(t + 0.5), max=7.0)
+    val = torch.ldexp(torch.where(xb < 0, -mag, mag), (e - 2).unsqueeze(-1))
+    return val.reshape(*val.shape[:-2], -1)[..., :d].contiguous()
+
+
 def dequantize_mxint8(codes: torch.Tensor, exps: torch.Tensor, block: int = BLOCK) -> torch.Tensor:
     """fake-quant fp32 value c * 2^(e-6) (what quantize_mx_op returns)."""
     d = codes.shape[-1]
@@ -253,6 +278,7 @@ def pred_scores_mode(qc, qe, kc, ke, pred_mode: str = "ex_pred", block: int = BL
       ex_pred    both sides +-2^e                             funcs/exponent_based_prediction.py:44-94
       partial_Q  Q = MXINT8 value c * 2^(e-6), K = +-2^e      funcs/exponent_based_prediction.py:300-318
       partial_K  Q = +-2^e, K = MXINT8 value                  funcs/exponent_based_prediction.py:274-298
+      (MXINT4: both sides MXINT4 values - takes the fp32 inputs, see pruned_attention)
     fp32 matmul, as the reference computes it."""
     if pred_mode not in ("ex_pred", "partial_Q", "partial_K"):
         raise ValueError(f"pred_mode {pred_mode!r}")
@@ -336,7 +362,7 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
     set).  use_torch_topk: leave torch.topk in place as the reference does (timing only).
     integer_scores: rank on pred_scores_integer (block-exact sums; what the CUDA kernel
     computes) instead of the fp32 matmul - identical wherever pred_window_ok holds.
-    pred_mode: "ex_pred" | "partial_Q" | "partial_K" (pred_scores_mode) or "exact" - the reference's
+    pred_mode: "ex_pred" | "partial_Q" | "partial_K" (pred_scores_mode), "MXINT4", or "exact" - the reference's
     approx_flag=False branch, `torch.topk(true_scores, k)` (main.py:130).
     """
     q, k, v = (t.to(torch.float32) for t in (q, k, v))
@@ -352,6 +378,8 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
     if idx is None:
         if pred_mode == "exact":
             pred = true
+        elif pred_mode == "MXINT4":                                  # funcs/exponent_based_prediction.py:179-199
+            pred = fake_quant_mxint4(q, BLOCK, bfloat, flush) @ fake_quant_mxint4(k, BLOCK, bfloat, flush).transpose(-2, -1)
         elif pred_mode != "ex_pred":
             pred = pred_scores_mode(qc, qe, kc, ke, pred_mode)
         else:

@@ -6,6 +6,8 @@ UNMODIFIED reference functions on seeded inputs.
   partial_Q / partial_K   funcs.exponent_approximation(...).partial_Q() / .partial_K()
                           (funcs/exponent_based_prediction.py:274-318) then `ex_q @ ex_k^T`
                           (workloads/deit/scripts/main.py:111-118)
+  MXINT4                  .MXINT4() (Sanger; funcs/exponent_based_prediction.py:179-199): both sides re-quantized
+                          with elem_format="int4"
   exact                   the `top_k and not approx_flag` branch: top-k of
                           mx.matmul(q, k^T) * scale  (main.py:101-102,130)
 followed by the same gather / softmax / scatter_ / mx.matmul(attn, v) as every mode (main.py:124,147-152).
@@ -19,7 +21,7 @@ import torch
 
 from make_golden import HERE, exponent_approximation, make_inputs, mx_matmul, mx_specs
 
-MODES = ("partial_Q", "partial_K", "exact")
+MODES = ("partial_Q", "partial_K", "MXINT4", "exact")
 
 CASES = [
     # name,              B  H  N    hd  k   bfloat flush  kind     seed
@@ -38,7 +40,7 @@ def reference_mode(q, k, v, top_k, scale, specs, mode):
         rank = true_scores
     else:
         obj = exponent_approximation(Q=q, K=k, mx_specs=specs)
-        ex_q, ex_k = obj.partial_Q() if mode == "partial_Q" else obj.partial_K()
+        ex_q, ex_k = {"partial_Q": obj.partial_Q, "partial_K": obj.partial_K, "MXINT4": obj.MXINT4}[mode]()
         rank = ex_q @ ex_k.transpose(-2, -1)
     out["rank_scores"] = rank
     out["topk_idx_torch"] = torch.topk(rank, top_k, dim=-1, largest=True, sorted=True).indices

@@ -140,10 +140,10 @@ def test_scatter_script_kat():
 MODE_CASES = ["modes_deit", "modes_dit_bf16", "modes_pixart", "modes_deit_197"]
 
 
-@pytest.mark.parametrize("mode", ["partial_Q", "partial_K", "exact"])
+@pytest.mark.parametrize("mode", ["partial_Q", "partial_K", "MXINT4", "exact"])
 @pytest.mark.parametrize("name", MODE_CASES)
 def test_other_rankings_against_reference(golden_dir, name, mode):
-    """partial_Q / partial_K (funcs/exponent_based_prediction.py:274-318) and the approx_flag=False branch
+    """partial_Q / partial_K / MXINT4 (funcs/exponent_based_prediction.py:179-199,274-318) and the approx_flag=False branch
     (workloads/deit/scripts/main.py:130), outputs of the unmodified reference
     (tests/golden/make_golden_modes.py)."""
     d, m = load(golden_dir, name)
