@@ -16,15 +16,24 @@
 // 22 bits; beyond it the reference's own BLAS summation order decides and parity is unpinned).
 //
 // These scores are not small integers (7 more bits per MXINT8 operand than the +-2^e predictor), so
-// the selection works on the full 32-bit ORDERED fp32 key: three digit levels (14 + 14 + 4 bits),
-// each re-reads the score tile from TMEM, maps this row's keys to a digit relative to the prefix
-// chosen so far (below prefix -> 0, above -> max) and runs K1-TC's register bisection (HSET2/HADD2 on
-// fp16 bit patterns, two lanes per query row).  32 counting passes instead of ~10: these are the
-// reference's comparison modes, not the headline path.  Ties: ascending key index, as everywhere.
+// the selection works on the full 32-bit ORDERED fp32 key (written back over the accumulator once): three
+// digit levels (14 + 14 + 4 bits), each re-reads the keys from TMEM, maps this row's keys to a digit
+// relative to the prefix chosen so far (below prefix / inside / above) and runs K1-TC's register bisection
+// (HSET2/HADD2 on fp16 bit patterns, two lanes per query row).  32 counting passes instead of ~10: these
+// are the reference's comparison modes, not the headline path.  Ties: ascending key index, as everywhere.
 #pragma once
 #include "mxprune_predict_tc.cuh"
 
 namespace mxp {
+
+template <int SPLIT>
+__device__ __forceinline__ void tmem_st_16x32bx2_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x32bx2.x16.b32 [%0], %1, {%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17};" ::
+        "r"(taddr), "n"(SPLIT), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 
 constexpr int PRED_EX = 0, PRED_PARTIAL_Q = 1, PRED_PARTIAL_K = 2, PRED_TRUE = 3, PRED_MXINT4 = 4;
 
@@ -253,27 +262,54 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
         tcgen05_fence_after_sync();
         if (!__any_sync(FULL, valid)) continue;                     // a warp of rows past Nq has nothing to select
 
-        // ordered 32-bit key of an accumulator value: the exact mode ranks A1(s) * scale as the
-        // reference does (matmul.py:89-91 then main.py:102); -0 is canonicalised by ordered_key
-        auto key_of = [&](uint32_t raw) -> uint32_t {
-            float s = __uint_as_float(raw);
-            if (true_mode) {
-                if (bf16) s = bf16_half_away(s);
-                s = __fmul_rn(s, sscale);
-            }
-            return ordered_key(s);
-        };
         const int col0 = part * NCH * 32;                           // this thread's first key column
 
-        // ---- select: three digit levels over the ordered key, most significant first
-        uint32_t P = 0u;                                            // digits chosen so far
+        // ---- convert once: the SIGNED ordered key of the ranked value (int order == float order), written
+        // back over the accumulator.  The exact mode ranks A1(s) * scale as the reference does
+        // (matmul.py:89-91 then main.py:102); + 0.0f folds -0 into +0; columns past Nk sort below everything.
+#pragma unroll
+        for (int w = 0; w < NCH; ++w) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t r[16];
+                tmem_ld_16x32bx2_x16<NCH * 32>(my_tmem + w * 32 + h * 16, r);
+                tmem_ld_wait();
+                const int nv = Nk - (col0 + w * 32 + h * 16);       // valid columns among these 16
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    float sc = __uint_as_float(r[t]);
+                    if (true_mode) {
+                        if (bf16) sc = bf16_half_away(sc);
+                        sc = __fmul_rn(sc, sscale);
+                    }
+                    const int b = __float_as_int(sc + 0.0f);
+                    const int o = b ^ ((b >> 31) & 0x7fffffff);
+                    r[t] = t < nv ? (uint32_t)o : 0x80000000u;
+                }
+                tmem_st_16x32bx2_x16<NCH * 32>(my_tmem + w * 32 + h * 16, r);
+            }
+        }
+        tmem_st_wait();
+
+        // ---- select: three digit levels of the 32-bit key, most significant first (14 + 14 + 4 bits).  A level
+        // maps this row's keys to fp16 bit patterns - 0x401 + digit inside the prefix chosen so far, anything
+        // <= 0x400 below it, a larger pattern above it - and bisects the digit with K1-TC's register counting.
+        uint32_t kw[NCH * 16];
+        int base28 = 0;                                             // chosen prefix, in the (key >> 4) domain
+        uint32_t Tpat = 0u;
 #pragma unroll 1
         for (int level = 0; level < 3; ++level) {
-            const int D = level == 2 ? 4 : 14;
-            const int shift = level == 0 ? 18 : level == 1 ? 4 : 0;
-            const uint32_t dmask = (1u << D) - 1u;
-            const uint32_t above = dmask + 2u;                      // digit code of a key above the prefix
-            uint32_t kw[NCH * 16];
+            // one branch-free mapping for the three levels:
+            //   y = clamp((key >> sh) - base + addc, 0, maxc);  pattern = y * mul + ((key & lowm) | orc)
+            //   level 0  digit = (key >> 18) + 8192                      -> 0x401 + digit
+            //   level 1  digit = (key >> 4) - prefix (28-bit operands)   -> 0x401 + digit, <= 0x400 below, 0x4401 above
+            //   level 2  y = 0 below / 1 inside / 2 above the 28-bit prefix -> 0x400 + 32 y + (key & 15)
+            const int sh = level == 0 ? 18 : 4;
+            const int base = level == 0 ? -8192 : base28;
+            const int addc = level == 2 ? 1 : 1 + (int)K1_KEY_BIAS;
+            const int maxc = level == 2 ? 2 : 16384 + 1 + (int)K1_KEY_BIAS;
+            const uint32_t mul = level == 2 ? 32u : 1u;
+            const uint32_t lowm = level == 2 ? 15u : 0u, orc = level == 2 ? K1_KEY_BIAS : 0u;
 #pragma unroll
             for (int w = 0; w < NCH; ++w) {
 #pragma unroll
@@ -281,59 +317,54 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
                     uint32_t r[16];
                     tmem_ld_16x32bx2_x16<NCH * 32>(my_tmem + w * 32 + h * 16, r);
                     tmem_ld_wait();
-                    const int nv = Nk - (col0 + w * 32 + h * 16);   // valid columns among these 16
 #pragma unroll
                     for (int t = 0; t < 16; ++t) {
-                        const uint32_t u = key_of(r[t]);
-                        const uint32_t hi = level == 0 ? 0u : (u >> shift) >> D;
-                        uint32_t v = ((u >> shift) & dmask) + 1u;
-                        v = hi > P ? above : v;
-                        v = (hi < P || t >= nv) ? 0u : v;
-                        const uint32_t f = v + K1_KEY_BIAS;
+                        const int y = __viaddmin_s32_relu(((int)r[t] >> sh) - base, addc, maxc);
+                        const uint32_t f = (uint32_t)y * mul + ((r[t] & lowm) | orc);
                         if (h == 0) kw[16 * w + t] = f;
                         else kw[16 * w + t] = __byte_perm(kw[16 * w + t], f, 0x5410);
                     }
                 }
             }
+            const int D = level == 2 ? 4 : 14;
+            const uint32_t pat0 = level == 2 ? K1_KEY_BIAS + 32u : K1_KEY_BIAS + 1u;        // pattern of digit 0
             uint32_t tsel = 0u;
 #pragma unroll 1
             for (int bit = D - 1; bit >= 0; --bit) {
                 const uint32_t cand = tsel | (1u << bit);
-                const int mine = count_ge_regs<NCH * 16>(kw, cand + 1u + K1_KEY_BIAS);
+                const int mine = count_ge_regs<NCH * 16>(kw, pat0 + cand);
                 const int theirs = __shfl_xor_sync(FULL, mine, 16);
                 if (mine + theirs >= kk) tsel = cand;
             }
-            P = (P << D) | tsel;
-        }
-        const uint32_t T = P;                                       // ordered key of the top_k-th largest score
-
-        // ---- emit: keys > T kept, keys == T kept in ascending key index until top_k
-        uint32_t gtw[NCH], eqw[NCH];
-        int ngt_m = 0, neq_m = 0;
-#pragma unroll
-        for (int w = 0; w < NCH; ++w) {
-            uint32_t gt = 0u, eq = 0u;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t r[16];
-                tmem_ld_16x32bx2_x16<NCH * 32>(my_tmem + w * 32 + h * 16, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    const uint32_t u = key_of(r[t]);
-                    gt |= u > T ? 1u << (16 * h + t) : 0u;
-                    eq |= u == T ? 1u << (16 * h + t) : 0u;
-                }
-            }
-            const int nv = Nk - (col0 + w * 32);
-            const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : (1u << nv) - 1u);
-            gtw[w] = gt & vm;
-            eqw[w] = eq & vm;
-            ngt_m += __popc(gtw[w]);
-            neq_m += __popc(eqw[w]);
+            if (level == 0) base28 = ((int)tsel - 8192) << 14;
+            else if (level == 1) base28 += (int)tsel;
+            else Tpat = pat0 + tsel;
         }
         // the tile's scores are consumed: TMEM and the Q-side shared memory may be reused
         tcgen05_fence_before_sync();
+
+        // ---- emit from the last level's patterns: > Tpat kept, == Tpat kept in ascending key index until top_k
+        uint32_t gtw[NCH], eqw[NCH];
+        int ngt_m = 0, neq_m = 0;
+        {
+            const __half2 t2 = u32_as_h2(Tpat * 0x00010001u);
+#pragma unroll
+            for (int w = 0; w < NCH; ++w) {
+                uint32_t gt = 0u, eq = 0u;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const __half2 kv = u32_as_h2(kw[16 * w + t]);
+                    gt |= __hgt2_mask(kv, t2) & (0x00010001u << t);
+                    eq |= __heq2_mask(kv, t2) & (0x00010001u << t);
+                }
+                const int nv = Nk - (col0 + w * 32);
+                const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : (1u << nv) - 1u);
+                gtw[w] = gt & vm;
+                eqw[w] = eq & vm;
+                ngt_m += __popc(gtw[w]);
+                neq_m += __popc(eqw[w]);
+            }
+        }
         {
             const int ngt_o = __shfl_xor_sync(FULL, ngt_m, 16);
             const int neq_o = __shfl_xor_sync(FULL, neq_m, 16);
