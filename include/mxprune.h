@@ -173,7 +173,9 @@ int mxp_pruned_attention_biased(const float* q, int64_t q_sB, int64_t q_sH, int6
  *   MXP_PRED_MXINT4     pred_mode == "MXINT4"      both sides MXINT4 values (Sanger)    funcs/exponent_based_prediction.py:179-199
  * (callers: main.py:107-123, DiT models.py:178-194).  Modes 1-4 need Nk <= 256 and head_dim a multiple
  * of 8, >= 32 (MXP_E_UNSUPPORTED otherwise); `scale` ranks the exact mode and scales the attention in
- * every mode.  mxp_predict_topk_mode is the selection alone (mask / idx as mxp_predict_topk).
+ * every mode.  key_bias (may be NULL) is the additive cross-attention bias of mxp_pruned_attention_biased, added
+ * in fp32 to the ranked value of every mode (MX_transformer_block.py:803,822).  mxp_predict_topk_mode is the
+ * selection alone (mask / idx as mxp_predict_topk).
  */
 #define MXP_PRED_EXP_SIGN  0
 #define MXP_PRED_PARTIAL_Q 1
@@ -186,12 +188,14 @@ int mxp_pruned_attention_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_
                               int B, int H, int Nq, int Nk, int hd, int top_k, int pred_mode,
                               float scale, int bfloat_bits, int flush,
                               float* out, int64_t o_sB, int64_t o_sH, int64_t o_sN,
+                              const float* key_bias, int64_t kb_sB,
                               uint32_t* mask_out,
                               void* workspace, size_t workspace_bytes, void* stream);
 int mxp_predict_topk_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
                           const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
                           int B, int H, int Nq, int Nk, int hd, int top_k, int pred_mode,
                           float scale, int bfloat_bits, int flush,
+                          const float* key_bias, int64_t kb_sB,
                           uint32_t* mask, int32_t* idx,
                           void* workspace, size_t workspace_bytes, void* stream);
 

@@ -700,8 +700,8 @@ static int predict_topk_wide(const PredParams& p, cudaStream_t st) {
     if (p.Nk > 256 || p.hd < 32 || (p.hd & 7))
         return fail(MXP_E_UNSUPPORTED, "pred_mode %d needs Nk <= 256 and head_dim a multiple of 8, >= 32 (got Nk=%d hd=%d)",
                     p.pred_mode, p.Nk, p.hd);
-    if (p.key_bias || p.q_codes || p.k_codes)
-        return fail(MXP_E_UNSUPPORTED, "pred_mode %d: key_bias and code outputs are implemented for the exponent-sign predictor only",
+    if (p.q_codes || p.k_codes)
+        return fail(MXP_E_UNSUPPORTED, "pred_mode %d: code outputs are implemented for the exponent-sign predictor only",
                     p.pred_mode);
     K1cMaps maps;
     if (!make_view_maps(p.q, p.B, p.H, p.Nq, p.hd, &maps.q_main, &maps.q_tail) ||
@@ -1145,20 +1145,20 @@ int mxp_pruned_attention_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_
                               const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
                               int B, int H, int Nq, int Nk, int hd, int top_k, int pred_mode, float scale,
                               int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
-                              int64_t o_sN, uint32_t* mask_out, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+                              int64_t o_sN, const float* key_bias, int64_t kb_sB, uint32_t* mask_out,
+                              void* workspace, size_t workspace_bytes, void* stream) {
     if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_MXINT4)
         return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 4]", pred_mode);
     return pruned_attention_impl(q, q_sB, q_sH, q_sN, k, k_sB, k_sH, k_sN, v, v_sB, v_sH, v_sN, B, H, Nq, Nk, hd,
-                                 top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, nullptr, 0, mask_out,
+                                 top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, key_bias, kb_sB, mask_out,
                                  workspace, workspace_bytes, stream, pred_mode);
 }
 
 int mxp_predict_topk_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
                           const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
                           int B, int H, int Nq, int Nk, int hd, int top_k, int pred_mode, float scale,
-                          int bfloat_bits, int flush, uint32_t* mask, int32_t* idx,
-                          void* workspace, size_t workspace_bytes, void* stream) {
+                          int bfloat_bits, int flush, const float* key_bias, int64_t kb_sB,
+                          uint32_t* mask, int32_t* idx, void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
     int rc = check_shape(B, H, Nq, Nk, hd, bfloat_bits);
     if (rc) return rc;
@@ -1175,6 +1175,7 @@ int mxp_predict_topk_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_
     p.bf16 = bfloat_bits == 16; p.flush = flush != 0;
     p.mask = mask; p.idx = idx;
     p.pred_mode = pred_mode; p.score_scale = scale;
+    p.key_bias = key_bias; p.kb_sB = kb_sB;
     p.long_ws = workspace; p.long_ws_bytes = workspace_bytes;
     return predict_topk_impl(p, (cudaStream_t)stream);
 }

@@ -101,6 +101,9 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
     unsigned char* q_op = p.q_op ? p.q_op + (size_t)head * OL.q_head_bytes : nullptr;
     const int kb_rows = OL.kb_rows;
     const float sscale = p.score_scale;
+    // additive key bias (PixArt cross-attention text mask): added in fp32 to the ranked value of every mode, as
+    // the reference does (MX_transformer_block.py:803 true_scores += attn_bias, :822 pred_scores + attn_bias)
+    const float* kbias = p.key_bias ? p.key_bias + bb * p.kb_sB : nullptr;
 
     const int CR = K1C_ROWS * G, cr_shift = G == 2 ? 7 : 6;
     const int nks = (NMMA + CR - 1) / CR;
@@ -282,6 +285,7 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
                         if (bf16) sc = bf16_half_away(sc);
                         sc = __fmul_rn(sc, sscale);
                     }
+                    if (kbias != nullptr && t < nv) sc = __fadd_rn(sc, __ldg(kbias + col0 + w * 32 + h * 16 + t));
                     const int b = __float_as_int(sc + 0.0f);
                     const int o = b ^ ((b >> 31) & 0x7fffffff);
                     r[t] = t < nv ? (uint32_t)o : 0x80000000u;

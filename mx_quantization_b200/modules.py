@@ -38,14 +38,16 @@ class PrunedAttentionCore(nn.Module):
         self.pred_mode = pred_mode
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
-                key_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+                key_bias: Optional[torch.Tensor] = None, dense: bool = False,
+                pred_mode: Optional[str] = None) -> torch.Tensor:
+        """dense / pred_mode: per-call overrides for the reference's exclude_timesteps steps."""
         B, H, N, hd = q.shape
         buf = torch.empty((B, N, H, hd), dtype=torch.float32, device=q.device)
         # write straight into (B,N,H,hd): the reference's x.transpose(1,2).reshape(B,N,C) is free
         # k <= 0: dense MXINT8 attention (the reference's top_k=False blocks) = every key kept
-        top_k = self.k if self.k > 0 else k.shape[2]
+        top_k = self.k if (self.k > 0 and not dense) else k.shape[2]
         ops.pruned_attention(q, k, v, self.mx_specs, top_k, scale=self.scale, out=buf.permute(0, 2, 1, 3),
-                             key_bias=key_bias, pred_mode=self.pred_mode)
+                             key_bias=key_bias, pred_mode=pred_mode or self.pred_mode)
         return buf.reshape(B, N, H * hd)
 
 
@@ -117,8 +119,10 @@ class Attention(nn.Module):
         super().__init__()
         assert dim % num_heads == 0, 'dim should be divisible by num_heads'
         mode = _require_hot_path(mx_quant, top_k, ex_pred, pred_mode, "Attention")
-        if anal or exclude_timesteps:
-            raise NotImplementedError("anal / exclude_timesteps (dense steps) are out of scope")
+        if anal:
+            raise NotImplementedError("--anal analysis dumps are out of scope (SURVEY.md 8f4)")
+        # steps listed here run dense attention (models.py:172: `top_k and current_timestep not in exclude_timesteps`)
+        self.exclude_timesteps = set(exclude_timesteps or ())
         self.num_heads, self.head_dim = num_heads, dim // num_heads
         self.scale = self.head_dim ** -0.5
         self.qkv = MxLinear(dim, dim * 3, bias=qkv_bias, mx_specs=mx_specs)        # models.py:129 (mx Linear)
@@ -135,7 +139,7 @@ class Attention(nn.Module):
         qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4)
         q, k, v = qkv.unbind(0)
         q, k = self.q_norm(q), self.k_norm(k)
-        x = self.core(q, k, v)
+        x = self.core(q, k, v, dense=self.current_timestep in self.exclude_timesteps)
         x = self.proj_drop(self.proj(x))
         self.current_timestep += 1
         return x
@@ -157,8 +161,11 @@ class MXSelfAttention(nn.Module):
     def set_config(self, mx_quant=False, mx_specs=None, top_k=False, k=20, ex_pred=False, exclude_timesteps=None,
                    pred_mode="ex_pred", block_idx=None, anal=False, file_name_dict=None, orthogonal_matrix=None):
         mode = _require_hot_path(mx_quant, top_k, ex_pred, pred_mode, "MXSelfAttention.set_config")
-        if anal or exclude_timesteps:
-            raise NotImplementedError("anal / exclude_timesteps (dense steps) are out of scope")
+        if anal:
+            raise NotImplementedError("--anal analysis dumps are out of scope (SURVEY.md 8f4)")
+        # self-attention: listed steps run dense (MX_transformer_block.py:656); cross-attention: listed steps rank
+        # on the true scores instead of the predictor's (:806, else-branch :845-848)
+        self.exclude_timesteps = set(exclude_timesteps or ())
         self.block_idx = block_idx
         # the block's set_config swaps nn.Linear -> mx.Linear (MX_transformer_block.py:344-362)
         self.to_q, self.to_k, self.to_v = (to_mx_linear(m, mx_specs) for m in (self.to_q, self.to_k, self.to_v))
@@ -175,7 +182,7 @@ class MXSelfAttention(nn.Module):
         q = self.to_q(hidden_states).view(B, N, self.num_heads, self.head_dim).transpose(1, 2)
         k = self.to_k(hidden_states).view(B, N, self.num_heads, self.head_dim).transpose(1, 2)
         v = self.to_v(hidden_states).view(B, N, self.num_heads, self.head_dim).transpose(1, 2)
-        x = self.to_out(self.core(q, k, v))
+        x = self.to_out(self.core(q, k, v, dense=self.current_timestep in self.exclude_timesteps))
         self.current_timestep += 1
         return x
 
@@ -198,7 +205,8 @@ class MXCrossAttention(MXSelfAttention):
         if attention_mask is not None and attention_mask.dtype == torch.bool:
             raise NotImplementedError("boolean masks (-inf bias) are not on the path; pass the additive fp32 mask")
         bias = None if attention_mask is None else attention_mask.to(torch.float32).reshape(B, S)
-        x = self.to_out(self.core(q, k, v, key_bias=bias))
+        excluded = self.current_timestep in self.exclude_timesteps
+        x = self.to_out(self.core(q, k, v, key_bias=bias, pred_mode="exact" if excluded else None))
         self.current_timestep += 1
         return x
 

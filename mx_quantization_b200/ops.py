@@ -144,7 +144,8 @@ def predict_scores(q: torch.Tensor, k: torch.Tensor, mx_specs) -> torch.Tensor:
 
 
 def predict_topk(q: torch.Tensor, k: torch.Tensor, mx_specs, top_k: int, return_idx: bool = False,
-                 return_codes: bool = False, pred_mode: str = "ex_pred", scale: Optional[float] = None):
+                 return_codes: bool = False, pred_mode: str = "ex_pred", scale: Optional[float] = None,
+                 key_bias: Optional[torch.Tensor] = None):
     """Fused quantize + predictor + per-row top-k.
 
     Returns a dict: mask int32 (B,H,Nq,ceil(Nk/32)) [bit j%32 of word j//32 = key j kept],
@@ -153,7 +154,9 @@ def predict_topk(q: torch.Tensor, k: torch.Tensor, mx_specs, top_k: int, return_
     true scores * scale) - see PRED_MODES."""
     mode = _pred_mode_code(pred_mode)
     if mode != 0:
-        return _predict_topk_mode(q, k, mx_specs, top_k, mode, scale, return_idx, return_codes)
+        return _predict_topk_mode(q, k, mx_specs, top_k, mode, scale, return_idx, return_codes, key_bias)
+    if key_bias is not None:
+        raise ValueError("predict_topk with pred_mode='ex_pred' takes no key_bias (use pruned_attention)")
     sp = resolve_specs(mx_specs)
     lib = _lib.load()
     q, k = _view4(q, "q"), _view4(k, "k")
@@ -181,7 +184,13 @@ def predict_topk(q: torch.Tensor, k: torch.Tensor, mx_specs, top_k: int, return_
     return res
 
 
-def _predict_topk_mode(q, k, mx_specs, top_k, mode, scale, return_idx, return_codes):
+def _key_bias_2d(key_bias, B, Nk, dev):
+    if key_bias.dtype != torch.float32 or key_bias.numel() != B * Nk or key_bias.device != dev:
+        raise ValueError("key_bias must be an fp32 tensor with B*Nk elements, (B, ..., Nk), on q's device")
+    return key_bias.reshape(B, Nk).contiguous()
+
+
+def _predict_topk_mode(q, k, mx_specs, top_k, mode, scale, return_idx, return_codes, key_bias=None):
     if return_codes:
         raise ValueError("return_codes is available with pred_mode='ex_pred' only")
     sp = resolve_specs(mx_specs)
@@ -195,8 +204,9 @@ def _predict_topk_mode(q, k, mx_specs, top_k, mode, scale, return_idx, return_co
         res["mask"] = torch.empty((B, H, Nq, (Nk + 31) // 32), dtype=torch.int32, device=dev)
         if return_idx:
             res["idx"] = torch.empty((B, H, Nq, int(top_k)), dtype=torch.int32, device=dev)
+        kb = None if key_bias is None else _key_bias_2d(key_bias, B, Nk, q.device)
         rc = lib.mxp_predict_topk_mode(_ptr(q), *_strides(q), _ptr(k), *_strides(k), B, H, Nq, Nk, hd, int(top_k),
-                                       mode, scale, sp.bfloat_bits, int(sp.flush), _ptr(res["mask"]),
+                                       mode, scale, sp.bfloat_bits, int(sp.flush), _ptr(kb), Nk, _ptr(res["mask"]),
                                        _ptr(res.get("idx")), _ptr(None), 0, _stream())
     _lib.check(rc, "mxp_predict_topk_mode")
     return res
@@ -259,8 +269,8 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
         raise ValueError(f"v {tuple(v.shape)} must be (B,H,Nk,head_dim) = {(B, H, Nk, hd)}")
     scale = float(hd) ** -0.5 if scale is None else float(scale)
     mode = _pred_mode_code(pred_mode)
-    if mode != 0 and (key_bias is not None or _kernel_ms is not None):
-        raise ValueError("key_bias / the per-kernel profile entry are available with pred_mode='ex_pred' only")
+    if mode != 0 and _kernel_ms is not None:
+        raise ValueError("the per-kernel profile entry is available with pred_mode='ex_pred' only")
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((B, H, Nq, hd), dtype=torch.float32, device=dev)
@@ -272,14 +282,12 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
         args = (_ptr(q), *_strides(q), _ptr(k), *_strides(k), _ptr(v), *_strides(v),
                 B, H, Nq, Nk, hd, int(top_k), scale, sp.bfloat_bits, int(sp.flush),
                 _ptr(out), *_strides(out), _ptr(mask), _ptr(ws), ws_bytes, _stream())
+        kb = None if key_bias is None else _key_bias_2d(key_bias, B, Nk, q.device)
         if mode != 0:
-            rc = lib.mxp_pruned_attention_mode(*args[:18], mode, *args[18:])
+            rc = lib.mxp_pruned_attention_mode(*args[:18], mode, *args[18:-4], _ptr(kb), Nk, *args[-4:])
         elif key_bias is not None:
-            if key_bias.dtype != torch.float32 or key_bias.numel() != B * Nk or key_bias.device != q.device:
-                raise ValueError("key_bias must be an fp32 tensor with B*Nk elements, (B, ..., Nk), on q's device")
             if _kernel_ms is not None:
                 raise ValueError("the per-kernel profile entry takes no key_bias")
-            kb = key_bias.reshape(B, Nk).contiguous()
             rc = lib.mxp_pruned_attention_biased(*args[:-4], _ptr(kb), Nk, *args[-4:])
         elif _kernel_ms is None:
             rc = lib.mxp_pruned_attention(*args)

@@ -53,8 +53,60 @@ def reference_mode(q, k, v, top_k, scale, specs, mode):
     return out
 
 
+def reference_cross_mode(q, k, v, attention_mask, top_k, scale, specs, mode):
+    """PixArt cross-attention (workloads/PixArt/models/MX_transformer_block.py:791-859) in the given ranking mode:
+    the additive mask goes onto the true scores (:803) and onto the predicted ones (:822); "exact" is the
+    else-branch of :806 (an excluded timestep / ex_pred off): torch.topk(true_scores) (:833-834)."""
+    B, H, N, _ = q.shape
+    S = k.shape[2]
+    out = {}
+    attention_mask = attention_mask.unsqueeze(1).repeat(1, H, 1, 1)
+    true_scores = mx_matmul(q, k.transpose(-2, -1), mx_specs=specs, mode_config='aa') * scale
+    attn_bias = attention_mask + torch.zeros([N, S], dtype=q.dtype)
+    true_scores += attn_bias
+    if mode == "exact":
+        rank = true_scores
+    else:
+        obj = exponent_approximation(Q=q, K=k, mx_specs=specs)
+        ex_q, ex_k = {"partial_Q": obj.partial_Q, "partial_K": obj.partial_K, "MXINT4": obj.MXINT4}[mode]()
+        rank = ex_q @ ex_k.transpose(-2, -1) + attn_bias
+    out["rank_scores"] = rank
+    out["topk_idx_torch"] = torch.topk(rank, top_k, dim=-1, largest=True, sorted=True).indices
+    idx = torch.sort(rank, dim=-1, descending=True, stable=True).indices[..., :top_k].contiguous()
+    out["idx"] = idx
+    vals = true_scores.gather(dim=-1, index=idx)
+    attn = torch.zeros_like(true_scores)
+    attn.scatter_(-1, idx, torch.softmax(vals, dim=-1))
+    out["out"] = mx_matmul(attn, v, mx_specs=specs, mode_config='aa')
+    return out
+
+
+def cross_case():
+    name, B, H, Nq, S, hd, top_k, valid, bias, bfloat, flush, seed = \
+        ("modes_pixart_cross", 2, 2, 64, 40, 72, 20, (13, 27), -10000.0, 32, True, 25)
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, H, Nq, hd, generator=g)
+    k = torch.randn(B, H, S, hd, generator=g)
+    v = torch.randn(B, H, S, hd, generator=g)
+    mask = torch.zeros(B, S)
+    for b, n in enumerate(valid):
+        mask[b, :n] = 1.0
+    attention_mask = ((1.0 - mask) * bias).reshape(B, 1, S)
+    arrays = {"q": q.numpy(), "k": k.numpy(), "v": v.numpy(), "key_bias": attention_mask.reshape(B, S).numpy()}
+    for mode in MODES:
+        ref = reference_cross_mode(q, k, v, attention_mask, top_k, 1.0 / (hd ** 0.5), mx_specs(bfloat, flush), mode)
+        for key, val in ref.items():
+            a = val.numpy()
+            arrays[f"{mode}.{key}"] = a.astype(np.int16) if "idx" in key else a
+    arrays["meta"] = np.array([B, H, Nq, S, hd, top_k, bfloat, int(flush)], dtype=np.int64)
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: wrote {os.path.getsize(path) / 1024:.1f} KiB")
+
+
 def main():
     torch.set_num_threads(1)
+    cross_case()
     for name, B, H, N, hd, top_k, bfloat, flush, kind, seed in CASES:
         specs = mx_specs(bfloat, flush)
         q, k, v = make_inputs(B, H, N, hd, seed, kind)

@@ -595,3 +595,51 @@ def test_other_rankings_module_and_errors(mxq):
         mxq.predict_topk(q, q, specs, 10, pred_mode="partial_K")
     with pytest.raises(NotImplementedError):
         mxq.predict_topk(q, q, specs, 10, pred_mode="ELSA")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_cross_attention_other_rankings_golden(mxq, mode):
+    """Cross-attention (Nq != Nk) with the additive text mask in the other ranking modes; "exact" is what an
+    excluded timestep runs (MX_transformer_block.py:806,833-834).  Reference-generated fixture."""
+    d, m = _load_cross("modes_pixart_cross")
+    specs = mx_specs(m["bfloat"], m["flush"])
+    bias = d["key_bias"].reshape(m["B"], 1, 1, m["S"]).cuda()
+    out, mask = mxq.pruned_attention(d["q"].cuda(), d["k"].cuda(), d["v"].cuda(), specs, m["top_k"],
+                                     scale=1.0 / (m["hd"] ** 0.5), return_mask=True, key_bias=bias, pred_mode=mode)
+    got = unpack_mask(mask, m["S"])
+    idx = d[f"{mode}.idx"].to(torch.int64)
+    want = torch.zeros_like(got)
+    want.scatter_(-1, idx, True)
+    assert torch.equal(got, want)
+    r = O.pruned_attention(d["q"], d["k"], d["v"], m["top_k"], scale=1.0 / (m["hd"] ** 0.5), bfloat=m["bfloat"],
+                           flush=m["flush"], key_bias=d["key_bias"].reshape(m["B"], 1, 1, m["S"]), idx=idx)
+    ref = {"true_vals": r["true_vals"], "idx": idx, "out": d[f"{mode}.out"]}
+    assert_out_close(out.cpu(), ref, d["v"], m["S"], m["bfloat"], OUT_TOL)
+    sel = mxq.predict_topk(d["q"].cuda(), d["k"].cuda(), specs, m["top_k"], pred_mode=mode,
+                           scale=1.0 / (m["hd"] ** 0.5), key_bias=bias)
+    assert torch.equal(sel["mask"], mask)
+
+
+def test_exclude_timesteps_in_shims(mxq):
+    """DiT / PixArt self-attention run dense attention on the listed steps (models.py:172,
+    MX_transformer_block.py:656); PixArt cross-attention ranks on the true scores there (:806,833-834)."""
+    from mx_quantization_b200.modules import Attention, MXCrossAttention
+    specs = mx_specs(16, False)
+    torch.manual_seed(0)
+    x = torch.randn(2, 64, 128, device="cuda")
+    torch.manual_seed(1)
+    a = Attention(128, num_heads=2, qkv_bias=True, mx_quant=True, mx_specs=specs, top_k=True, k=16, ex_pred=True,
+                  exclude_timesteps=[1]).cuda()
+    torch.manual_seed(1)
+    dense = Attention(128, num_heads=2, qkv_bias=True, mx_quant=True, mx_specs=specs, top_k=False).cuda()
+    y0, y1, y2 = a(x), a(x), a(x)
+    assert torch.equal(y0, y2) and not torch.equal(y0, y1)
+    assert torch.equal(y1, dense(x))
+    torch.manual_seed(2)
+    c = MXCrossAttention(128, 2).cuda().set_config(mx_quant=True, mx_specs=specs, top_k=True, k=8, ex_pred=True,
+                                                    exclude_timesteps=[0])
+    enc = torch.randn(2, 40, 128, device="cuda")
+    am = torch.zeros(2, 1, 40, device="cuda")
+    am[0, 0, 25:] = -10000.0
+    z0, z1 = c(x, encoder_hidden_states=enc, attention_mask=am), c(x, encoder_hidden_states=enc, attention_mask=am)
+    assert z0.shape == x.shape and bool(torch.isfinite(z0).all()) and not torch.equal(z0, z1)

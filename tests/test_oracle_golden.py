@@ -162,6 +162,19 @@ def test_other_rankings_against_reference(golden_dir, name, mode):
 CROSS_CASES = ["pixart_cross", "pixart_cross_k77", "pixart_cross_all"]
 
 
+@pytest.mark.parametrize("mode", ["partial_Q", "partial_K", "MXINT4", "exact"])
+def test_cross_attention_other_rankings(mode):
+    """PixArt cross-attention with the additive text mask in the other ranking modes ("exact" = the branch an
+    excluded timestep takes, MX_transformer_block.py:806,833-834) - oracle vs the reference's outputs."""
+    d, m = load_cross("modes_pixart_cross")
+    bias = d["key_bias"].reshape(m["B"], 1, 1, m["S"])
+    r = O.pruned_attention(d["q"], d["k"], d["v"], m["top_k"], scale=1.0 / (m["hd"] ** 0.5),
+                           bfloat=m["bfloat"], flush=m["flush"], key_bias=bias, pred_mode=mode)
+    assert torch.equal(r["pred_scores"], d[f"{mode}.rank_scores"])
+    assert torch.equal(r["idx"], d[f"{mode}.idx"].to(torch.int64))
+    assert float((r["out"] - d[f"{mode}.out"]).abs().max()) <= 1e-6 * float(d[f"{mode}.out"].abs().max())
+
+
 def load_cross(name):
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
     d = {k: torch.from_numpy(z[k]) for k in z.files}
