@@ -23,7 +23,7 @@ template <int V>
 __global__ void __launch_bounds__(256, 2) bench(const uint32_t* in, uint32_t* out, long long* cycles, int kk) {
     uint32_t kw[64];
 #pragma unroll
-    for (int w = 0; w < 64; ++w) kw[w] = in[w * 256 + threadIdx.x] & (V == 0 ? 0x7bff7bffu : 0xffffffffu);
+    for (int w = 0; w < 64; ++w) kw[w] = in[w * 256 + threadIdx.x] & ((V == 0 || V >= 4) ? 0x7bff7bffu : 0xffffffffu);
     uint32_t T = 0;
     __syncthreads();
     long long t0 = clock64();
@@ -43,6 +43,50 @@ __global__ void __launch_bounds__(256, 2) bench(const uint32_t* in, uint32_t* ou
             }
             const __half2 t = __hadd2(__hadd2(a0, a1), __hadd2(a2, a3));
             cnt = (int)(__low2float(t) + __high2float(t));
+        } else if (V == 4 || V == 5) {
+            // all accumulations forced onto one instruction kind: 4 = fma.rn.f16x2 (HFMA2), 5 = add.f16x2 (HADD2)
+            const uint32_t c2 = cand * 0x00010001u;
+            uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+            const uint32_t one2 = V == 4 ? (uint32_t)(kk > 0) * 0x3c003c00u : 0x3c003c00u;   // runtime 1.0: stays an HFMA2
+#pragma unroll
+            for (int w = 0; w < 64; w += 4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t ind;
+                    asm("set.ge.f16x2.f16x2 %0, %1, %2;" : "=r"(ind) : "r"(kw[w + j]), "r"(c2));
+                    uint32_t& a = j == 0 ? a0 : j == 1 ? a1 : j == 2 ? a2 : a3;
+                    if (V == 4) asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(a) : "r"(ind), "r"(one2));
+                    else asm("add.f16x2 %0, %0, %1;" : "+r"(a) : "r"(ind));
+                }
+            }
+            const __half2 t = __hadd2(__hadd2(u2h(a0), u2h(a1)), __hadd2(u2h(a2), u2h(a3)));
+            cnt = (int)(__low2float(t) + __high2float(t));
+        } else if (V == 6) {
+            // HSET2 mask form (0xffff per hit) accumulated by integer multiply-add on the FMA pipe:
+            // sum = 0xffff * (65536 n_hi + n_lo) mod 2^32, decoded with the inverse of 0xffff
+            const __half2 c2 = u2h(cand * 0x00010001u);
+            uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+            const uint32_t one = (uint32_t)kk | 1u;                       // runtime multiplier: stays an IMAD (timing only)
+#pragma unroll
+            for (int w = 0; w < 64; w += 4) {
+                a0 = __hge2_mask(u2h(kw[w]), c2) * one + a0;
+                a1 = __hge2_mask(u2h(kw[w + 1]), c2) * one + a1;
+                a2 = __hge2_mask(u2h(kw[w + 2]), c2) * one + a2;
+                a3 = __hge2_mask(u2h(kw[w + 3]), c2) * one + a3;
+            }
+            const uint32_t x = (a0 + a1 + a2 + a3) * 0xFFFEFFFFu;     // 0xffff^-1 mod 2^32
+            cnt = (int)((x & 0xffffu) + (x >> 16));
+        } else if (V == 7) {
+            // mask form, two masks per IADD3
+            const __half2 c2 = u2h(cand * 0x00010001u);
+            uint32_t a0 = 0u, a1 = 0u;
+#pragma unroll
+            for (int w = 0; w < 64; w += 4) {
+                a0 = a0 + __hge2_mask(u2h(kw[w]), c2) + __hge2_mask(u2h(kw[w + 1]), c2);
+                a1 = a1 + __hge2_mask(u2h(kw[w + 2]), c2) + __hge2_mask(u2h(kw[w + 3]), c2);
+            }
+            const uint32_t x = (a0 + a1) * 0xFFFEFFFFu;
+            cnt = (int)((x & 0xffffu) + (x >> 16));
         } else if (V == 1) {
             const uint32_t c4 = (cand & 0xffu) * 0x01010101u, d4 = ((cand - 1u) & 0xffu) * 0x01010101u;
             uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
@@ -113,5 +157,9 @@ int main() {
     run<1>("B SAD4 x2 cand 32 words (128 keys)");
     run<2>("C VIADDMNMX+IADD 64 words");
     run<3>("D SAD4 x1 32 words");
+    run<4>("E HSET2 + HFMA2 only");
+    run<5>("F HSET2 + HADD2 only");
+    run<6>("G HSET2 mask + IMAD");
+    run<7>("H HSET2 mask + IADD3 (2 masks/add)");
     return 0;
 }
