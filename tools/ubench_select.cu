@@ -87,6 +87,23 @@ __global__ void __launch_bounds__(256, 2) bench(const uint32_t* in, uint32_t* ou
             }
             const uint32_t x = (a0 + a1) * 0xFFFEFFFFu;
             cnt = (int)((x & 0xffffu) + (x >> 16));
+        } else if (V == 8) {
+            // integer-VALUED fp16 keys (|v| <= 2048): indicator = sat(key - cand + 1) in one HADD2.SAT on the FMA
+            // pipe, accumulated by HFMA2/HADD2 - no ALU-pipe instruction in the loop
+            const uint32_t c2 = cand * 0x00010001u;          // stands for the fp16x2 value (1 - cand)
+            uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+#pragma unroll
+            for (int w = 0; w < 64; w += 4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t ind;
+                    asm("add.sat.f16x2 %0, %1, %2;" : "=r"(ind) : "r"(kw[w + j]), "r"(c2));
+                    uint32_t& a = j == 0 ? a0 : j == 1 ? a1 : j == 2 ? a2 : a3;
+                    asm("add.f16x2 %0, %0, %1;" : "+r"(a) : "r"(ind));
+                }
+            }
+            const __half2 t = __hadd2(__hadd2(u2h(a0), u2h(a1)), __hadd2(u2h(a2), u2h(a3)));
+            cnt = (int)(__low2float(t) + __high2float(t));
         } else if (V == 1) {
             const uint32_t c4 = (cand & 0xffu) * 0x01010101u, d4 = ((cand - 1u) & 0xffu) * 0x01010101u;
             uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
@@ -161,5 +178,6 @@ int main() {
     run<5>("F HSET2 + HADD2 only");
     run<6>("G HSET2 mask + IMAD");
     run<7>("H HSET2 mask + IADD3 (2 masks/add)");
+    run<8>("I HADD2.SAT + HADD2 (value keys)");
     return 0;
 }
