@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MXP_ABI_VERSION 1
+#define MXP_ABI_VERSION 2
 
 #define MXP_OK             0
 #define MXP_E_BADARG      -1   /* null pointer, bad shape/stride/alignment, k out of range */
