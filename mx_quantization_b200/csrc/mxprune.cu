@@ -682,17 +682,17 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
 }
 
 // ---- K1-wide: partial_Q / partial_K / exact-score top-k, Nk <= 256, tensor-core domain only
-template <int NC>
+template <int NC, bool TWO>
 static int launch_predict_topk_wide_one(const PredParams& p, const K1cMaps& maps, const K1cSmem& L, size_t dyn,
                                         dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_wide<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_wide<NC, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              227 * 1024);
         if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    k_predict_topk_wide<NC><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
+    k_predict_topk_wide<NC, TWO><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
     return check_launch("k_predict_topk_wide");
 }
 
@@ -707,14 +707,17 @@ static int predict_topk_wide(const PredParams& p, cudaStream_t st) {
     if (!make_view_maps(p.q, p.B, p.H, p.Nq, p.hd, &maps.q_main, &maps.q_tail) ||
         !make_view_maps(p.k, p.B, p.H, p.Nk, p.hd, &maps.k_main, &maps.k_tail))
         return fail(MXP_E_UNSUPPORTED, "pred_mode %d: the q/k views cannot be described by a TMA tensor map", p.pred_mode);
-    const size_t per_cta2 = 232448 / 2 - 1024, per_cta1 = 232448 - 1024;
+    // two_step_leading_ones carries two operand parts per side: twice the operand shared memory, one CTA per SM
+    const bool two = p.pred_mode == PRED_TWO_STEP;
+    const int opw = two ? 2 : 1;
+    const size_t per_cta1 = 232448 - 1024, per_cta2 = two ? per_cta1 : 232448 / 2 - 1024;
     const int nc = p.Nk <= 32 ? 1 : p.Nk <= 64 ? 2 : p.Nk <= 128 ? 4 : p.Nk <= 224 ? 7 : 8;
     const int nb = (p.hd + 31) / 32;
     int G = nb <= 2 ? 2 : 1;
-    if (k1c_smem_layout(p.hd, nc, 2, G, false).total > per_cta2) G = 1;
+    if (k1c_smem_layout(p.hd, nc, 2, G, false, opw).total > per_cta2) G = 1;
     int ring = K1C_MAXR;
-    while (ring > 2 && k1c_smem_layout(p.hd, nc, ring, G, false).total > per_cta2) --ring;
-    K1cSmem L = k1c_smem_layout(p.hd, nc, ring, G, false);
+    while (ring > (two ? 1 : 2) && k1c_smem_layout(p.hd, nc, ring, G, false, opw).total > per_cta2) --ring;
+    K1cSmem L = k1c_smem_layout(p.hd, nc, ring, G, false, opw);
     if (L.total > per_cta1) return fail(MXP_E_UNSUPPORTED, "pred_mode %d: shape needs %zu bytes of shared memory", p.pred_mode, L.total);
     const int heads = p.B * p.H;
     const int tiles = (p.Nq + K1C_TILE - 1) / K1C_TILE;
@@ -726,13 +729,16 @@ static int predict_topk_wide(const PredParams& p, cudaStream_t st) {
     size_t dyn = L.total;
     const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
     if (dyn < floor_bytes) dyn = floor_bytes;
+#define MXP_WIDE(NC_) (two ? launch_predict_topk_wide_one<NC_, true>(p, maps, L, dyn, grid, st)   \
+                           : launch_predict_topk_wide_one<NC_, false>(p, maps, L, dyn, grid, st))
     switch (nc) {
-        case 1: return launch_predict_topk_wide_one<1>(p, maps, L, dyn, grid, st);
-        case 2: return launch_predict_topk_wide_one<2>(p, maps, L, dyn, grid, st);
-        case 4: return launch_predict_topk_wide_one<4>(p, maps, L, dyn, grid, st);
-        case 7: return launch_predict_topk_wide_one<7>(p, maps, L, dyn, grid, st);
-        default: return launch_predict_topk_wide_one<8>(p, maps, L, dyn, grid, st);
+        case 1: return MXP_WIDE(1);
+        case 2: return MXP_WIDE(2);
+        case 4: return MXP_WIDE(4);
+        case 7: return MXP_WIDE(7);
+        default: return MXP_WIDE(8);
     }
+#undef MXP_WIDE
 }
 
 // ---- K1-long-TC (Nk > 256): operand pre-pass + tensor-core radix select + CUDA-core clean-up ----
@@ -931,7 +937,7 @@ static int predict_topk_impl(const PredParams& p, cudaStream_t st) {
     int rc = MXP_OK;
     if (p.key_bias && p.Nk > K1_MAX_KEYS)
         return fail(MXP_E_UNSUPPORTED, "key_bias: the additive key bias is implemented for Nk <= 256 (cross-attention)");
-    if (p.pred_mode < 0 || p.pred_mode > 4) return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 4]", p.pred_mode);
+    if (p.pred_mode < 0 || p.pred_mode > 5) return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 5]", p.pred_mode);
     if (p.pred_mode != 0) return predict_topk_wide(p, st);
     if (try_predict_topk_tc(p, st, &rc) == 0) return rc;
     if (try_predict_topk_long_tc(p, st, &rc) == 0) return rc;
@@ -1147,8 +1153,8 @@ int mxp_pruned_attention_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_
                               int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
                               int64_t o_sN, const float* key_bias, int64_t kb_sB, uint32_t* mask_out,
                               void* workspace, size_t workspace_bytes, void* stream) {
-    if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_MXINT4)
-        return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 4]", pred_mode);
+    if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_TWO_STEP)
+        return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 5]", pred_mode);
     return pruned_attention_impl(q, q_sB, q_sH, q_sN, k, k_sB, k_sH, k_sN, v, v_sB, v_sH, v_sN, B, H, Nq, Nk, hd,
                                  top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, key_bias, kb_sB, mask_out,
                                  workspace, workspace_bytes, stream, pred_mode);
@@ -1166,8 +1172,8 @@ int mxp_predict_topk_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_
     if ((rc = check_view("k", k, k_sB, k_sH, k_sN, hd))) return rc;
     if (!mask) return fail(MXP_E_BADARG, "mask: null pointer");
     if (top_k < 1 || top_k > Nk) return fail(MXP_E_BADARG, "top_k=%d outside [1, Nk=%d]", top_k, Nk);
-    if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_MXINT4)
-        return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 4]", pred_mode);
+    if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_TWO_STEP)
+        return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 5]", pred_mode);
     PredParams p{};
     p.q = View{q, q_sB, q_sH, q_sN};
     p.k = View{k, k_sB, k_sH, k_sN};

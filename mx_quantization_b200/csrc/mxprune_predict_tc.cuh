@@ -56,7 +56,9 @@ struct K1cSmem {
 // of the predictor operand are zero so that padding keys score exactly 0.
 // G = TMA boxes (of 64 rows) per ring slot == per quantize step.
 // biased: two extra K columns carry the additive key bias through the MMA (see the kernel).
-__host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring, int G, bool biased = false) {
+// opw = operand width multiplier: 2 when each side carries two operand parts [A | B] per row (K1-wide's
+// two_step_leading_ones mode), chunk c of part B at chunk index (hdp >> 3) + c.
+__host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring, int G, bool biased = false, int opw = 1) {
     K1cSmem L;
     L.nfull = hd >> 5;
     L.tail = hd & 31;
@@ -72,8 +74,8 @@ __host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring, int
     L.box_tail = (size_t)K1C_ROWS * L.tail * 4;
     L.slot_bytes = (G * (L.box_main + L.box_tail) + 1023) & ~(size_t)1023;
     size_t o = L.slot_bytes * ring;
-    L.off_kop = o;   o += (size_t)(L.hdp >> 3) * L.n_mma * 16;
-    L.off_qop = o;   o += (size_t)(L.hdp >> 3) * K1C_TILE * 16;
+    L.off_kop = o;   o += (size_t)opw * (L.hdp >> 3) * L.n_mma * 16;
+    L.off_qop = o;   o += (size_t)opw * (L.hdp >> 3) * K1C_TILE * 16;
     L.off_ksign = o; o += (size_t)L.nb * 256 * 4;
     L.off_kexp = o;  o += (size_t)L.nb * 256;
     L.off_qsign = o; o += (size_t)L.nb * K1C_TILE * 4;

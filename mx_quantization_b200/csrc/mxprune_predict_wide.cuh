@@ -8,6 +8,13 @@
 //                            `top_k and not approx_flag` branch  main.py:101-102,130
 //   pred_mode 4  MXINT4      both sides re-quantized as MXINT4, c4 * 2^(e-2), |c4| <= 7 (Sanger)
 //                            funcs/exponent_based_prediction.py:179-199, main.py:117-118
+//   pred_mode 5  two_step_leading_ones (EXION)   funcs/exponent_based_prediction.py:96-177, main.py:115-116
+//                            value = sign(c) * e * (2^f1 + 2^f2) / 64 as the reference computes it: e is the shared
+//                            exponent's VALUE, f1 the leading one of |c|, f2 the leading one of c - 2^f1 for
+//                            c > 0 only (negative codes keep one term), zero codes give 0.  e * (2^f1 + 2^f2)
+//                            can need more than bf16's 8 significant bits, so each side carries two exact parts
+//                            A = sign * e * 2^(f1-6), B = e * 2^(f2-6) and the score is the sum of the four
+//                            part products (TWO = true: operands twice as wide, one CTA per SM).
 //
 // Both operand kinds are exact in bf16 and come out of the same per-block quantizer
 // (quantize_block_thread: r.op = c * 2^(e-6), r.pp = +-2^e), so a mode only chooses which of the two
@@ -35,7 +42,7 @@ __device__ __forceinline__ void tmem_st_16x32bx2_x16(uint32_t taddr, const uint3
         : "memory");
 }
 
-constexpr int PRED_EX = 0, PRED_PARTIAL_Q = 1, PRED_PARTIAL_K = 2, PRED_TRUE = 3, PRED_MXINT4 = 4;
+constexpr int PRED_EX = 0, PRED_PARTIAL_Q = 1, PRED_PARTIAL_K = 2, PRED_TRUE = 3, PRED_MXINT4 = 4, PRED_TWO_STEP = 5;
 
 // MXINT4 operand of one block: value = sign(x) * min(7, floor(|x| * 2^(2-e) + 0.5)) * 2^(e-2), the int4 element
 // format of the reference (formats.py:86-88: mbits 4, emax 0 -> the MXINT8 shared exponent e; lshift by
@@ -65,8 +72,38 @@ __device__ __forceinline__ void int4_operand(const uint32_t (&xv)[32], int e, bo
     }
 }
 
-template <int NC>
-__global__ void __launch_bounds__(K1C_T, 2)
+// two_step_leading_ones parts of one block from its int8 codes (cw: element 8c + 4h + t in byte t of word 2c + h)
+// and the predictor exponent ep (funcs/exponent_based_prediction.py:104-127):
+//   sign = torch.sign(MX) (0 for a zero code); f1 = floor(log2 |c|); temp = max(c - 2^f1, 0) on the SIGNED code,
+//   so only positive codes get a second term f2 = floor(log2 temp); value = sign * ep * (2^f1 + 2^f2) / 64.
+__device__ __forceinline__ void two_step_operands(const uint32_t (&cw)[8], int ep, uint4 (&pa)[4], uint4 (&pb)[4]) {
+    const float fe = (float)ep;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t wa[4], wb[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float fa[4], fb[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int code = (int)(signed char)((cw[2 * c + h] >> (8 * t)) & 0xffu);
+                const int a = abs(code);
+                const int f1 = 31 - __clz(a | 1);
+                const int rest = code > 0 ? a - (1 << f1) : 0;
+                const int f2 = 31 - __clz(rest | 1);
+                fa[t] = code == 0 ? 0.f : (code < 0 ? -fe : fe) * exp2i(f1 - 6);
+                fb[t] = rest == 0 ? 0.f : fe * exp2i(f2 - 6);
+            }
+            wa[2 * h] = pack_bf16_trunc(fa[0], fa[1]); wa[2 * h + 1] = pack_bf16_trunc(fa[2], fa[3]);
+            wb[2 * h] = pack_bf16_trunc(fb[0], fb[1]); wb[2 * h + 1] = pack_bf16_trunc(fb[2], fb[3]);
+        }
+        pa[c] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+        pb[c] = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+    }
+}
+
+template <int NC, bool TWO>
+__global__ void __launch_bounds__(K1C_T, TWO ? 1 : 2)
 k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring, const int G) {
     extern __shared__ __align__(1024) unsigned char smem_k1w[];
     unsigned char* const smem = smem_k1w;
@@ -78,7 +115,7 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
     const bool k_exact = mode == PRED_PARTIAL_K || mode == PRED_TRUE;
     const bool true_mode = mode == PRED_TRUE;
     const bool int4_mode = mode == PRED_MXINT4;
-    const K1cSmem L = k1c_smem_layout(hd, NC, ring, G, false);
+    const K1cSmem L = k1c_smem_layout(hd, NC, ring, G, false, TWO ? 2 : 1);
     const int nfull = L.nfull, tail = L.tail, nb = L.nb;
     const int kch = L.hdp >> 3;
     const int tail_chunks_hbm = (((hd + 15) & ~15) >> 3) - 4 * nfull;
@@ -195,9 +232,10 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
                 }
             }
             BlockQ r;
-            quantize_block_thread<false>(xv, full ? 32 : tail, bf16, flush, r);      // xv: A1 applied in place
-            uint4 op4[4];
+            quantize_block_thread<TWO>(xv, full ? 32 : tail, bf16, flush, r);        // xv: A1 applied in place
+            uint4 op4[4], opb[4];                                   // first / second operand part of the mode
             if (int4_mode) int4_operand(xv, r.e, flush && r.e <= -127, op4);
+            if (TWO) two_step_operands(r.cw, r.ep, op4, opb);
             const int nchunk = full ? 4 : tail_chunks, nchunk_hbm = full ? 4 : tail_chunks_hbm;
             const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
             if (is_k) {
@@ -207,7 +245,13 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
                     for (int ch = 0; ch < 4; ++ch)
                         if (ch < nchunk)
                             *reinterpret_cast<uint4*>(dst + ch * (NMMA * 16)) =
-                                !in_range ? zero4 : int4_mode ? op4[ch] : k_exact ? r.op[ch] : r.pp[ch];
+                                !in_range ? zero4 : (int4_mode || TWO) ? op4[ch] : k_exact ? r.op[ch] : r.pp[ch];
+                    if (TWO) {
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch)
+                            if (ch < nchunk)
+                                *reinterpret_cast<uint4*>(dst + (kch + ch) * (NMMA * 16)) = in_range ? opb[ch] : zero4;
+                    }
                 }
                 if (write_kop && row < kb_rows) {
                     unsigned char* dst = k_op + ((size_t)(4 * b) * kb_rows + row) * 16;
@@ -221,7 +265,12 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch)
                     if (ch < nchunk) *reinterpret_cast<uint4*>(dst + ch * (K1C_TILE * 16)) =
-                        int4_mode ? op4[ch] : q_exact ? r.op[ch] : r.pp[ch];
+                        (int4_mode || TWO) ? op4[ch] : q_exact ? r.op[ch] : r.pp[ch];
+                if (TWO) {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        if (ch < nchunk) *reinterpret_cast<uint4*>(dst + (kch + ch) * (K1C_TILE * 16)) = opb[ch];
+                }
                 if (q_op) {
                     unsigned char* gdst = q_op + (size_t)tile * OL.q_tile_bytes + ((size_t)(4 * b) * K1C_TILE + rt) * 16;
 #pragma unroll
@@ -253,11 +302,14 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
         }
         if (tid == 0) {
             tcgen05_fence_after_sync();
-            for (int ks = 0; ks < (L.hdp >> 4); ++ks) {
-                const uint64_t da = umma_smem_desc(smem_u32(s_qop + (size_t)(2 * ks) * K1C_TILE * 16), K1C_TILE * 16, 128);
-                const uint64_t db = umma_smem_desc(smem_u32(s_kop + (size_t)(2 * ks) * NMMA * 16), NMMA * 16, 128);
-                umma_bf16_ss(tmem, da, db, idesc, ks > 0);
-            }
+            // TWO: (A_q + B_q) . (A_k + B_k) as the four part products into one accumulator
+            for (int pq = 0; pq < (TWO ? 2 : 1); ++pq)
+                for (int pk = 0; pk < (TWO ? 2 : 1); ++pk)
+                    for (int ks = 0; ks < (L.hdp >> 4); ++ks) {
+                        const uint64_t da = umma_smem_desc(smem_u32(s_qop + (size_t)(pq * kch + 2 * ks) * K1C_TILE * 16), K1C_TILE * 16, 128);
+                        const uint64_t db = umma_smem_desc(smem_u32(s_kop + (size_t)(pk * kch + 2 * ks) * NMMA * 16), NMMA * 16, 128);
+                        umma_bf16_ss(tmem, da, db, idesc, (pq | pk | ks) != 0);
+                    }
             umma_commit(bar_mma);
         }
         mbar_wait(bar_mma, ph_mma);

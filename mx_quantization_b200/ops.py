@@ -110,14 +110,14 @@ def exp_sign_approx(x: torch.Tensor, mx_specs) -> torch.Tensor:
 
 # The reference's sources of the top-k ranking (workloads/deit/scripts/main.py:105-131): pred_mode strings as
 # the reference spells them, plus "exact" for its `top_k and not approx_flag` branch (top-k of the true scores).
-PRED_MODES = {"ex_pred": 0, "partial_Q": 1, "partial_K": 2, "exact": 3, "MXINT4": 4}
+PRED_MODES = {"ex_pred": 0, "partial_Q": 1, "partial_K": 2, "exact": 3, "MXINT4": 4, "two_step_leading_ones": 5}
 
 
 def _pred_mode_code(pred_mode: str) -> int:
     if pred_mode not in PRED_MODES:
         raise NotImplementedError(
-            f"pred_mode={pred_mode!r}: built modes are {sorted(PRED_MODES)}; two_step_leading_ones (EXION) and ELSA "
-            "are not built (SURVEY.md 8f3) and there is no fallback")
+            f"pred_mode={pred_mode!r}: built modes are {sorted(PRED_MODES)}; ELSA is not built (SURVEY.md 8f3) "
+            "and there is no fallback")
     return PRED_MODES[pred_mode]
 
 

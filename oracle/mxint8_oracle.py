@@ -272,6 +272,27 @@ def pred_scores_matmul(qc, qe, kc, ke, block: int = BLOCK) -> torch.Tensor:
     return aq @ ak.transpose(-2, -1)
 
 
+def two_step_leading_ones(codes: torch.Tensor, exps: torch.Tensor, block: int = BLOCK) -> torch.Tensor:
+    """The reference's EXION emulation, funcs/exponent_based_prediction.py:96-127, on the MXINT8 codes:
+        raw   = MX / 2^e_shared * 64                    == the int8 code c
+        sign  = torch.sign(MX)                          (0 for a zero code)
+        f1    = floor(log2 |c|)
+        temp  = where(c - 2^f1 < 0, 0, c - 2^f1)        on the SIGNED code: only c > 0 keeps a remainder
+        f2    = floor(log2 temp)                        (temp = 0 -> log2(2^-126): 2^f2 vanishes in fp32)
+        value = sign * e_shared * (2^f1 + 2^f2) / 64    e_shared is the exponent's VALUE, as the reference writes it
+    """
+    d = codes.shape[-1]
+    c = codes.to(torch.int64)
+    a = c.abs()
+    f1 = torch.floor(torch.log2(a.clamp(min=1).to(torch.float64))).to(torch.int64)
+    rest = torch.where(c > 0, a - (1 << f1), torch.zeros_like(a))
+    f2 = torch.floor(torch.log2(rest.clamp(min=1).to(torch.float64))).to(torch.int64)
+    m = (1 << f1) + torch.where(rest > 0, 1 << f2, torch.zeros_like(rest))
+    ep = predictor_exponents(codes, exps, block).repeat_interleave(block, dim=-1)[..., :d].to(torch.int64)
+    val = torch.sign(c) * ep * m
+    return (val.to(torch.float32) / 64.0)                         # |val| < 2^24: exact
+
+
 def pred_scores_mode(qc, qe, kc, ke, pred_mode: str = "ex_pred", block: int = BLOCK) -> torch.Tensor:
     """`pred_scores = ex_quant_q @ ex_quant_k^T` (workloads/deit/scripts/main.py:118) for the predictor
     variants that reuse the MXINT8 codes:
@@ -280,6 +301,8 @@ def pred_scores_mode(qc, qe, kc, ke, pred_mode: str = "ex_pred", block: int = BL
       partial_K  Q = +-2^e, K = MXINT8 value                  funcs/exponent_based_prediction.py:274-298
       (MXINT4: both sides MXINT4 values - takes the fp32 inputs, see pruned_attention)
     fp32 matmul, as the reference computes it."""
+    if pred_mode == "two_step_leading_ones":                       # funcs/exponent_based_prediction.py:96-177
+        return two_step_leading_ones(qc, qe, block) @ two_step_leading_ones(kc, ke, block).transpose(-2, -1)
     if pred_mode not in ("ex_pred", "partial_Q", "partial_K"):
         raise ValueError(f"pred_mode {pred_mode!r}")
     aq = dequantize_mxint8(qc, qe, block) if pred_mode == "partial_Q" else exponent_based_sign(qc, qe, block)
@@ -362,7 +385,7 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
     set).  use_torch_topk: leave torch.topk in place as the reference does (timing only).
     integer_scores: rank on pred_scores_integer (block-exact sums; what the CUDA kernel
     computes) instead of the fp32 matmul - identical wherever pred_window_ok holds.
-    pred_mode: "ex_pred" | "partial_Q" | "partial_K" (pred_scores_mode), "MXINT4", or "exact" - the reference's
+    pred_mode: "ex_pred" | "partial_Q" | "partial_K" | "two_step_leading_ones" (pred_scores_mode), "MXINT4", or "exact" - the reference's
     approx_flag=False branch, `torch.topk(true_scores, k)` (main.py:130).
     """
     q, k, v = (t.to(torch.float32) for t in (q, k, v))

@@ -8,6 +8,7 @@ UNMODIFIED reference functions on seeded inputs.
                           (workloads/deit/scripts/main.py:111-118)
   MXINT4                  .MXINT4() (Sanger; funcs/exponent_based_prediction.py:179-199): both sides re-quantized
                           with elem_format="int4"
+  two_step_leading_ones   .two_step_leading_ones() (EXION; funcs/exponent_based_prediction.py:96-177)
   exact                   the `top_k and not approx_flag` branch: top-k of
                           mx.matmul(q, k^T) * scale  (main.py:101-102,130)
 followed by the same gather / softmax / scatter_ / mx.matmul(attn, v) as every mode (main.py:124,147-152).
@@ -21,7 +22,7 @@ import torch
 
 from make_golden import HERE, exponent_approximation, make_inputs, mx_matmul, mx_specs
 
-MODES = ("partial_Q", "partial_K", "MXINT4", "exact")
+MODES = ("partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "exact")
 
 CASES = [
     # name,              B  H  N    hd  k   bfloat flush  kind     seed
@@ -40,7 +41,8 @@ def reference_mode(q, k, v, top_k, scale, specs, mode):
         rank = true_scores
     else:
         obj = exponent_approximation(Q=q, K=k, mx_specs=specs)
-        ex_q, ex_k = {"partial_Q": obj.partial_Q, "partial_K": obj.partial_K, "MXINT4": obj.MXINT4}[mode]()
+        ex_q, ex_k = {"partial_Q": obj.partial_Q, "partial_K": obj.partial_K, "MXINT4": obj.MXINT4,
+                      "two_step_leading_ones": obj.two_step_leading_ones}[mode]()
         rank = ex_q @ ex_k.transpose(-2, -1)
     out["rank_scores"] = rank
     out["topk_idx_torch"] = torch.topk(rank, top_k, dim=-1, largest=True, sorted=True).indices
@@ -68,7 +70,8 @@ def reference_cross_mode(q, k, v, attention_mask, top_k, scale, specs, mode):
         rank = true_scores
     else:
         obj = exponent_approximation(Q=q, K=k, mx_specs=specs)
-        ex_q, ex_k = {"partial_Q": obj.partial_Q, "partial_K": obj.partial_K, "MXINT4": obj.MXINT4}[mode]()
+        ex_q, ex_k = {"partial_Q": obj.partial_Q, "partial_K": obj.partial_K, "MXINT4": obj.MXINT4,
+                      "two_step_leading_ones": obj.two_step_leading_ones}[mode]()
         rank = ex_q @ ex_k.transpose(-2, -1) + attn_bias
     out["rank_scores"] = rank
     out["topk_idx_torch"] = torch.topk(rank, top_k, dim=-1, largest=True, sorted=True).indices

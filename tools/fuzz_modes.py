@@ -32,7 +32,7 @@ def main():
         top_k = ri(1, Nk)
         bfloat = 16 if ri(0, 1) else 32
         flush = bool(ri(0, 1))
-        mode = ["partial_Q", "partial_K", "MXINT4", "exact"][ri(0, 3)]
+        mode = ["partial_Q", "partial_K", "MXINT4", "exact", "two_step_leading_ones"][ri(0, 4)]
         kind = ["randn", "lognormal", "edges"][ri(0, 2)] if min(Nq, Nk) >= 16 and Nq == Nk and hd >= 64 else "randn"
         q, _, _ = make_qkv(B, H, Nq, hd, seed=3000 + c, kind=kind)
         _, k, v = make_qkv(B, H, Nk, hd, seed=4000 + c, kind=kind)
@@ -43,8 +43,14 @@ def main():
         tag = (f"case {c}: {mode} B{B} H{H} Nq{Nq} Nk{Nk} hd{hd} k{top_k} bf{bfloat} flush{int(flush)} {kind} "
                f"bias{int(bias is not None)}")
         specs = mx_specs(bfloat, flush)
-        res = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k, pred_mode=mode,
-                               key_bias=None if bias is None else bias.cuda())
+        try:
+            res = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k, pred_mode=mode,
+                                   key_bias=None if bias is None else bias.cuda())
+        except ValueError as e:
+            if mode == "two_step_leading_ones" and "shared memory" in str(e) and hd == 128 and Nk > 224:
+                print(tag, "skipped (two-part operands of head_dim 128 x 256 keys exceed shared memory)")
+                continue
+            raise
         ref = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, flush=flush, key_bias=bias, pred_mode=mode)
         want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], Nk), Nk)
         got = unpack_mask(res["mask"], Nk)
