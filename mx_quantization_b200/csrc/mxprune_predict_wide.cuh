@@ -330,15 +330,23 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
                 tmem_ld_16x32bx2_x16<NCH * 32>(my_tmem + w * 32 + h * 16, r);
                 tmem_ld_wait();
                 const int nv = Nk - (col0 + w * 32 + h * 16);       // valid columns among these 16
+                if (true_mode) {                                    // warp-uniform branches: the common modes skip them
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        float sc = __uint_as_float(r[t]);
+                        if (bf16) sc = bf16_half_away(sc);
+                        r[t] = __float_as_uint(__fmul_rn(sc, sscale));
+                    }
+                }
+                if (kbias != nullptr) {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t)
+                        if (t < nv)
+                            r[t] = __float_as_uint(__fadd_rn(__uint_as_float(r[t]), __ldg(kbias + col0 + w * 32 + h * 16 + t)));
+                }
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    float sc = __uint_as_float(r[t]);
-                    if (true_mode) {
-                        if (bf16) sc = bf16_half_away(sc);
-                        sc = __fmul_rn(sc, sscale);
-                    }
-                    if (kbias != nullptr && t < nv) sc = __fadd_rn(sc, __ldg(kbias + col0 + w * 32 + h * 16 + t));
-                    const int b = __float_as_int(sc + 0.0f);
+                    const int b = __float_as_int(__uint_as_float(r[t]) + 0.0f);
                     const int o = b ^ ((b >> 31) & 0x7fffffff);
                     r[t] = t < nv ? (uint32_t)o : 0x80000000u;
                 }
