@@ -414,13 +414,16 @@ k_predict_topk_rows(const PredParams p) {
         int wbits = 32 - __clz(moff + 1);
         wbits = __reduce_max_sync(FULL, wbits);
         uint32_t Tv = 0u;                                   // unbiased key value
+        // the last rejected candidate is T + 1 (T's lowest zero bit set, the accepted ones below it cleared), so
+        // its count is the number of keys > T; nothing rejected: T is all ones and no key lies above it
+        int ngt = 0;
         for (int bit = wbits - 1; bit >= 0; --bit) {
             const uint32_t cand = Tv | (1u << bit);
-            if (h2_count_ge(my_sc, ng, cand + K1_KEY_BIAS) >= kk) Tv = cand;
+            const int cnt = h2_count_ge(my_sc, ng, cand + K1_KEY_BIAS);
+            if (cnt >= kk) Tv = cand; else ngt = cnt;
         }
         const uint32_t T = Tv + K1_KEY_BIAS;
         const bool has_gt = true;                           // T + 1 <= 0x7C00 - 1 by construction of K1_MAX_M
-        const int ngt = h2_count_ge(my_sc, ng, T + 1u);
 
         // ---- emit the row bitmask (ties: ascending key index)
         {

@@ -694,17 +694,19 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
         // candidate, and each accepted candidate brings its own counts along
         int nge_m = min(my_cols_end, max(Nk, my_cols_beg)) - my_cols_beg;
         int nge_o = Nk - nge_m;
+        // keys > T: T + 1 clears T's trailing ones and sets its lowest zero bit j - exactly the candidate that was
+        // tested (and rejected) at bit j, and every later bit was accepted, so the counts of the LAST rejected
+        // candidate are the counts of keys >= T + 1 (none rejected: T is all ones, nothing lies above it)
+        int ngt_m = 0, ngt_o = 0;
 #pragma unroll 1
         for (int bit = wbits - 1; bit >= 0; --bit) {
             const uint32_t cand = (Tv | (1u << bit)) + K1_KEY_BIAS;
             const int mine = count_ge_regs<NCH * 16>(kw, cand) - (key0 >= cand ? my_pad : 0);
             const int theirs = __shfl_xor_sync(FULL, mine, 16);
             if (mine + theirs >= kk) { Tv |= 1u << bit; nge_m = mine; nge_o = theirs; }
+            else { ngt_m = mine; ngt_o = theirs; }
         }
         const uint32_t T = Tv + K1_KEY_BIAS;
-        // keys > T among this thread's columns, and the partner's
-        const int ngt_m = count_ge_regs<NCH * 16>(kw, T + 1u) - (key0 > T ? my_pad : 0);
-        const int ngt_o = __shfl_xor_sync(FULL, ngt_m, 16);
 
         // ---- emit the row bitmask (ties: ascending key index; the lower lane owns the lower columns)
         {
