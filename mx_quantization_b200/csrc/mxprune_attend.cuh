@@ -626,7 +626,12 @@ k_attend_pair(const AttnParams p) {
                     uint32_t pb = __float_as_uint(__uint_as_float(r[c]) * inv);
                     if (bf16) pb = bf16_half_away(pb);
                     r[c] = pb;
-                    mx4[c & 3] = max(mx4[c & 3], pb);               // p >= 0: bit patterns order like the values
+                }
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {                   // p >= 0: bit patterns order like the values;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)                     // three-input max: one VIMNMX3 per two elements
+                        mx4[q] = __vimax3_u32(mx4[q], r[c + 2 * q], r[c + 2 * q + 1]);
                 }
                 const uint32_t mx = max(max(mx4[0], mx4[1]), max(mx4[2], mx4[3]));
                 const int e = mx_shared_exp(mx);
