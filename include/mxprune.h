@@ -173,7 +173,9 @@ int mxp_pruned_attention_biased(const float* q, int64_t q_sB, int64_t q_sH, int6
  *   MXP_PRED_MXINT4     pred_mode == "MXINT4"      both sides MXINT4 values (Sanger)    funcs/exponent_based_prediction.py:179-199
  *   MXP_PRED_TWO_STEP   pred_mode == "two_step_leading_ones" (EXION)  sign * e * (2^f1 + 2^f2) / 64
  *                                                                       funcs/exponent_based_prediction.py:96-177
- * (callers: main.py:107-123, DiT models.py:178-194).  Modes 1-5 need Nk <= 256 and head_dim a multiple
+ *   MXP_PRED_TRUE_EX    pred_mode == "true_ex"     sign * 2^floor(log2 |element|) per element
+ *                                                   microxscaling/examples/deit/exponent_based_prediction.py:163-178
+ * (callers: main.py:107-123, DiT models.py:178-194, MX_transformer_block.py:659-673).  Modes 1-6 need Nk <= 256 and head_dim a multiple
  * of 8, >= 32 (MXP_E_UNSUPPORTED otherwise); `scale` ranks the exact mode and scales the attention in
  * every mode.  key_bias (may be NULL) is the additive cross-attention bias of mxp_pruned_attention_biased, added
  * in fp32 to the ranked value of every mode (MX_transformer_block.py:803,822).  mxp_predict_topk_mode is the
@@ -185,6 +187,7 @@ int mxp_pruned_attention_biased(const float* q, int64_t q_sB, int64_t q_sH, int6
 #define MXP_PRED_EXACT     3
 #define MXP_PRED_MXINT4    4
 #define MXP_PRED_TWO_STEP  5
+#define MXP_PRED_TRUE_EX   6
 int mxp_pruned_attention_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
                               const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
                               const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,

@@ -937,7 +937,7 @@ static int predict_topk_impl(const PredParams& p, cudaStream_t st) {
     int rc = MXP_OK;
     if (p.key_bias && p.Nk > K1_MAX_KEYS)
         return fail(MXP_E_UNSUPPORTED, "key_bias: the additive key bias is implemented for Nk <= 256 (cross-attention)");
-    if (p.pred_mode < 0 || p.pred_mode > 5) return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 5]", p.pred_mode);
+    if (p.pred_mode < 0 || p.pred_mode > 6) return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 6]", p.pred_mode);
     if (p.pred_mode != 0) return predict_topk_wide(p, st);
     if (try_predict_topk_tc(p, st, &rc) == 0) return rc;
     if (try_predict_topk_long_tc(p, st, &rc) == 0) return rc;
@@ -1153,8 +1153,8 @@ int mxp_pruned_attention_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_
                               int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
                               int64_t o_sN, const float* key_bias, int64_t kb_sB, uint32_t* mask_out,
                               void* workspace, size_t workspace_bytes, void* stream) {
-    if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_TWO_STEP)
-        return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 5]", pred_mode);
+    if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_TRUE_EX)
+        return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 6]", pred_mode);
     return pruned_attention_impl(q, q_sB, q_sH, q_sN, k, k_sB, k_sH, k_sN, v, v_sB, v_sH, v_sN, B, H, Nq, Nk, hd,
                                  top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, key_bias, kb_sB, mask_out,
                                  workspace, workspace_bytes, stream, pred_mode);
@@ -1172,8 +1172,8 @@ int mxp_predict_topk_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_
     if ((rc = check_view("k", k, k_sB, k_sH, k_sN, hd))) return rc;
     if (!mask) return fail(MXP_E_BADARG, "mask: null pointer");
     if (top_k < 1 || top_k > Nk) return fail(MXP_E_BADARG, "top_k=%d outside [1, Nk=%d]", top_k, Nk);
-    if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_TWO_STEP)
-        return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 5]", pred_mode);
+    if (pred_mode < MXP_PRED_EXP_SIGN || pred_mode > MXP_PRED_TRUE_EX)
+        return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 6]", pred_mode);
     PredParams p{};
     p.q = View{q, q_sB, q_sH, q_sN};
     p.k = View{k, k_sB, k_sH, k_sN};

@@ -8,6 +8,9 @@
 //                            `top_k and not approx_flag` branch  main.py:101-102,130
 //   pred_mode 4  MXINT4      both sides re-quantized as MXINT4, c4 * 2^(e-2), |c4| <= 7 (Sanger)
 //                            funcs/exponent_based_prediction.py:179-199, main.py:117-118
+//   pred_mode 6  true_ex     sign * 2^floor(log2 |MX element|) per element (zero elements: +1, as the example's
+//                            get_true_exponents leaves their exponent at 0): the leading one of every element  microxscaling/examples/deit/exponent_based_prediction.py:163-178 (the
+//                            copy under funcs/ lacks the method), PixArt MX_transformer_block.py:663-664,811-812
 //   pred_mode 5  two_step_leading_ones (EXION)   funcs/exponent_based_prediction.py:96-177, main.py:115-116
 //                            value = sign(c) * e * (2^f1 + 2^f2) / 64 as the reference computes it: e is the shared
 //                            exponent's VALUE, f1 the leading one of |c|, f2 the leading one of c - 2^f1 for
@@ -42,7 +45,7 @@ __device__ __forceinline__ void tmem_st_16x32bx2_x16(uint32_t taddr, const uint3
         : "memory");
 }
 
-constexpr int PRED_EX = 0, PRED_PARTIAL_Q = 1, PRED_PARTIAL_K = 2, PRED_TRUE = 3, PRED_MXINT4 = 4, PRED_TWO_STEP = 5;
+constexpr int PRED_EX = 0, PRED_PARTIAL_Q = 1, PRED_PARTIAL_K = 2, PRED_TRUE = 3, PRED_MXINT4 = 4, PRED_TWO_STEP = 5, PRED_TRUE_EX = 6;
 
 // MXINT4 operand of one block: value = sign(x) * min(7, floor(|x| * 2^(2-e) + 0.5)) * 2^(e-2), the int4 element
 // format of the reference (formats.py:86-88: mbits 4, emax 0 -> the MXINT8 shared exponent e; lshift by
@@ -69,6 +72,25 @@ __device__ __forceinline__ void int4_operand(const uint32_t (&xv)[32], int e, bo
             w[h] = pack_bf16_trunc(f[0], f[1]);
         }
         op4[c] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// true_ex operand from the exact bf16 operand c * 2^(e-6): its exponent field IS floor(log2 |value|), so the leading
+// one is the operand with the mantissa cleared; a zero element (either sign: `MX < 0` is false for -0) is +1.0:
+// get_true_exponents (:98-110) leaves the exponent of zeros at 0.  nd: elements of the block that exist.
+__device__ __forceinline__ void true_ex_operand(const uint4 (&op)[4], int nd, uint4 (&out)[4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t w[4] = {op[c].x, op[c].y, op[c].z, op[c].w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const uint32_t m = w[h] & 0xff80ff80u;
+            const uint32_t t = m & 0x7f807f80u;
+            const uint32_t nz = ((t + 0x7f807f80u) | t) & 0x80008000u;        // bit 15 of a half: magnitude != 0
+            const uint32_t z = ~nz & 0x80008000u;                            // zero halves
+            w[h] = (m & ~z) | ((z >> 8) * 0x7fu);                           // -0 loses its sign; zero -> 0x3f80 = 1.0
+        }
+        out[c] = 8 * c < nd ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -114,7 +136,8 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
     const bool q_exact = mode == PRED_PARTIAL_Q || mode == PRED_TRUE;
     const bool k_exact = mode == PRED_PARTIAL_K || mode == PRED_TRUE;
     const bool true_mode = mode == PRED_TRUE;
-    const bool int4_mode = mode == PRED_MXINT4;
+    const bool int4_mode = mode == PRED_MXINT4 || mode == PRED_TRUE_EX;       // modes whose operand is formed in op4
+    const bool true_ex_mode = mode == PRED_TRUE_EX;
     const K1cSmem L = k1c_smem_layout(hd, NC, ring, G, false, TWO ? 2 : 1);
     const int nfull = L.nfull, tail = L.tail, nb = L.nb;
     const int kch = L.hdp >> 3;
@@ -234,7 +257,8 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
             BlockQ r;
             quantize_block_thread<TWO>(xv, full ? 32 : tail, bf16, flush, r);        // xv: A1 applied in place
             uint4 op4[4], opb[4];                                   // first / second operand part of the mode
-            if (int4_mode) int4_operand(xv, r.e, flush && r.e <= -127, op4);
+            if (true_ex_mode) true_ex_operand(r.op, full ? 32 : tail, op4);
+            else if (int4_mode) int4_operand(xv, r.e, flush && r.e <= -127, op4);
             if (TWO) two_step_operands(r.cw, r.ep, op4, opb);
             const int nchunk = full ? 4 : tail_chunks, nchunk_hbm = full ? 4 : tail_chunks_hbm;
             const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);

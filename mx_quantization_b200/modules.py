@@ -12,9 +12,9 @@ projections stay whatever the host model uses (``mx.Linear`` in the reference - 
 path); here they are plain ``nn.Linear`` unless the caller passes its own.
 
 Implemented: mx_quant && top_k && approx/ex_pred with pred_mode "ex_pred" (the pruned hot path),
-"partial_Q", "partial_K", "MXINT4" or "two_step_leading_ones"; mx_quant && top_k && !approx (top-k of the true scores); and
+"partial_Q", "partial_K", "MXINT4", "two_step_leading_ones" or "true_ex"; mx_quant && top_k && !approx (top-k of the true scores); and
 mx_quant && !top_k (dense MXINT8 attention, what the reference runs in the last block of each
-model - same kernels with every key kept).  Every other combination (ELSA, true_ex,
+model - same kernels with every key kept).  Every other combination (ELSA,
 mx_quant=False) raises - no silent fallback.
 """
 from typing import Optional
@@ -61,10 +61,10 @@ def _require_hot_path(mx_quant, top_k, approx, pred_mode, where) -> str:
                                   "B200 path and there is no fallback")
     if not approx:
         return "exact"
-    if pred_mode not in ("ex_pred", "partial_Q", "partial_K", "MXINT4", "two_step_leading_ones"):
+    if pred_mode not in ("ex_pred", "partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex"):
         raise NotImplementedError(
             f"{where}: pred_mode={pred_mode!r} is not built (built: 'ex_pred', 'partial_Q', 'partial_K', 'MXINT4', "
-            "'two_step_leading_ones' and approx=False); ELSA / true_ex are predictors outside the path "
+            "'two_step_leading_ones', 'true_ex' and approx=False); ELSA is a predictor outside the path "
             "(SURVEY.md 8f3) and there is no fallback")
     return pred_mode
 

@@ -110,7 +110,8 @@ def exp_sign_approx(x: torch.Tensor, mx_specs) -> torch.Tensor:
 
 # The reference's sources of the top-k ranking (workloads/deit/scripts/main.py:105-131): pred_mode strings as
 # the reference spells them, plus "exact" for its `top_k and not approx_flag` branch (top-k of the true scores).
-PRED_MODES = {"ex_pred": 0, "partial_Q": 1, "partial_K": 2, "exact": 3, "MXINT4": 4, "two_step_leading_ones": 5}
+PRED_MODES = {"ex_pred": 0, "partial_Q": 1, "partial_K": 2, "exact": 3, "MXINT4": 4, "two_step_leading_ones": 5,
+              "true_ex": 6}
 
 
 def _pred_mode_code(pred_mode: str) -> int:

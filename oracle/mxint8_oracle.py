@@ -293,6 +293,18 @@ def two_step_leading_ones(codes: torch.Tensor, exps: torch.Tensor, block: int = 
     return (val.to(torch.float32) / 64.0)                         # |val| < 2^24: exact
 
 
+def sign_leading_ones(codes: torch.Tensor, exps: torch.Tensor, block: int = BLOCK) -> torch.Tensor:
+    """"true_ex": microxscaling/examples/deit/exponent_based_prediction.py:163-178 -
+    where(MX < 0, -1, +1) * 2^floor(log2 |MX|) per element; a zero element (either sign) gives +1.0
+    (get_true_exponents :98-110 leaves the exponent of zeros at 0).  |MX| = |c| * 2^(e-6)."""
+    d = codes.shape[-1]
+    c = codes.to(torch.int64)
+    f1 = torch.floor(torch.log2(c.abs().clamp(min=1).to(torch.float64))).to(torch.int32)
+    e = exps.to(torch.int32).repeat_interleave(block, dim=-1)[..., :d]
+    t = torch.where(c == 0, torch.zeros_like(f1), e - 6 + f1)
+    return torch.ldexp(torch.where(c < 0, -1.0, 1.0).to(torch.float32), t)
+
+
 def pred_scores_mode(qc, qe, kc, ke, pred_mode: str = "ex_pred", block: int = BLOCK) -> torch.Tensor:
     """`pred_scores = ex_quant_q @ ex_quant_k^T` (workloads/deit/scripts/main.py:118) for the predictor
     variants that reuse the MXINT8 codes:
@@ -301,6 +313,8 @@ def pred_scores_mode(qc, qe, kc, ke, pred_mode: str = "ex_pred", block: int = BL
       partial_K  Q = +-2^e, K = MXINT8 value                  funcs/exponent_based_prediction.py:274-298
       (MXINT4: both sides MXINT4 values - takes the fp32 inputs, see pruned_attention)
     fp32 matmul, as the reference computes it."""
+    if pred_mode == "true_ex":
+        return sign_leading_ones(qc, qe, block) @ sign_leading_ones(kc, ke, block).transpose(-2, -1)
     if pred_mode == "two_step_leading_ones":                       # funcs/exponent_based_prediction.py:96-177
         return two_step_leading_ones(qc, qe, block) @ two_step_leading_ones(kc, ke, block).transpose(-2, -1)
     if pred_mode not in ("ex_pred", "partial_Q", "partial_K"):
@@ -385,7 +399,7 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
     set).  use_torch_topk: leave torch.topk in place as the reference does (timing only).
     integer_scores: rank on pred_scores_integer (block-exact sums; what the CUDA kernel
     computes) instead of the fp32 matmul - identical wherever pred_window_ok holds.
-    pred_mode: "ex_pred" | "partial_Q" | "partial_K" | "two_step_leading_ones" (pred_scores_mode), "MXINT4", or "exact" - the reference's
+    pred_mode: "ex_pred" | "partial_Q" | "partial_K" | "two_step_leading_ones" | "true_ex" (pred_scores_mode), "MXINT4", or "exact" - the reference's
     approx_flag=False branch, `torch.topk(true_scores, k)` (main.py:130).
     """
     q, k, v = (t.to(torch.float32) for t in (q, k, v))

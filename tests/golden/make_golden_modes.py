@@ -9,6 +9,8 @@ UNMODIFIED reference functions on seeded inputs.
   MXINT4                  .MXINT4() (Sanger; funcs/exponent_based_prediction.py:179-199): both sides re-quantized
                           with elem_format="int4"
   two_step_leading_ones   .two_step_leading_ones() (EXION; funcs/exponent_based_prediction.py:96-177)
+  true_ex                 .exponent_based_sign_leading_ones() of the example copy of the predictor file
+                          (microxscaling/examples/deit/exponent_based_prediction.py:163-178)
   exact                   the `top_k and not approx_flag` branch: top-k of
                           mx.matmul(q, k^T) * scale  (main.py:101-102,130)
 followed by the same gather / softmax / scatter_ / mx.matmul(attn, v) as every mode (main.py:124,147-152).
@@ -20,9 +22,9 @@ import os
 import numpy as np
 import torch
 
-from make_golden import HERE, exponent_approximation, make_inputs, mx_matmul, mx_specs
+from make_golden import HERE, _example, exponent_approximation, make_inputs, mx_matmul, mx_specs
 
-MODES = ("partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "exact")
+MODES = ("partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex", "exact")
 
 CASES = [
     # name,              B  H  N    hd  k   bfloat flush  kind     seed
@@ -33,6 +35,16 @@ CASES = [
 ]
 
 
+def predictor_operands(q, k, specs, mode):
+    """true_ex (exponent_based_sign_leading_ones) exists only in the example copy of the predictor file
+    (microxscaling/examples/deit/exponent_based_prediction.py:163-178); everything else comes from funcs/."""
+    if mode == "true_ex":
+        return _example.exponent_approximation(Q=q, K=k, mx_specs=specs).exponent_based_sign_leading_ones()
+    obj = exponent_approximation(Q=q, K=k, mx_specs=specs)
+    return {"partial_Q": obj.partial_Q, "partial_K": obj.partial_K, "MXINT4": obj.MXINT4,
+            "two_step_leading_ones": obj.two_step_leading_ones}[mode]()
+
+
 def reference_mode(q, k, v, top_k, scale, specs, mode):
     out = {}
     true_scores = mx_matmul(q, k.transpose(-2, -1), mx_specs=specs, mode_config='aa')
@@ -40,9 +52,7 @@ def reference_mode(q, k, v, top_k, scale, specs, mode):
     if mode == "exact":
         rank = true_scores
     else:
-        obj = exponent_approximation(Q=q, K=k, mx_specs=specs)
-        ex_q, ex_k = {"partial_Q": obj.partial_Q, "partial_K": obj.partial_K, "MXINT4": obj.MXINT4,
-                      "two_step_leading_ones": obj.two_step_leading_ones}[mode]()
+        ex_q, ex_k = predictor_operands(q, k, specs, mode)
         rank = ex_q @ ex_k.transpose(-2, -1)
     out["rank_scores"] = rank
     out["topk_idx_torch"] = torch.topk(rank, top_k, dim=-1, largest=True, sorted=True).indices
@@ -69,9 +79,7 @@ def reference_cross_mode(q, k, v, attention_mask, top_k, scale, specs, mode):
     if mode == "exact":
         rank = true_scores
     else:
-        obj = exponent_approximation(Q=q, K=k, mx_specs=specs)
-        ex_q, ex_k = {"partial_Q": obj.partial_Q, "partial_K": obj.partial_K, "MXINT4": obj.MXINT4,
-                      "two_step_leading_ones": obj.two_step_leading_ones}[mode]()
+        ex_q, ex_k = predictor_operands(q, k, specs, mode)
         rank = ex_q @ ex_k.transpose(-2, -1) + attn_bias
     out["rank_scores"] = rank
     out["topk_idx_torch"] = torch.topk(rank, top_k, dim=-1, largest=True, sorted=True).indices

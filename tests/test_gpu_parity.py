@@ -499,7 +499,7 @@ def test_cuda_graph_capture_and_replay(mxq):
 
 
 # ---- the reference's other rankings: partial_Q / partial_K / top-k of the true scores ----
-MODES = ["partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "exact"]
+MODES = ["partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex", "exact"]
 
 
 @pytest.mark.gpu
@@ -589,7 +589,7 @@ def test_other_rankings_module_and_errors(mxq):
         assert outs[name].shape == x.shape and bool(torch.isfinite(outs[name]).all())
     assert not torch.equal(outs["ex"], outs["exact"])
     with pytest.raises(NotImplementedError):
-        Attention(128, num_heads=2, mx_quant=True, mx_specs=specs, top_k=True, k=16, ex_pred=True, pred_mode="true_ex")
+        Attention(128, num_heads=2, mx_quant=True, mx_specs=specs, top_k=True, k=16, ex_pred=True, pred_mode="ELSA")
     q = torch.randn(1, 1, 300, 64, device="cuda")
     with pytest.raises(ValueError):                      # modes 1-3: Nk <= 256
         mxq.predict_topk(q, q, specs, 10, pred_mode="partial_K")

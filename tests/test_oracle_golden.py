@@ -140,7 +140,7 @@ def test_scatter_script_kat():
 MODE_CASES = ["modes_deit", "modes_dit_bf16", "modes_pixart", "modes_deit_197"]
 
 
-@pytest.mark.parametrize("mode", ["partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "exact"])
+@pytest.mark.parametrize("mode", ["partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex", "exact"])
 @pytest.mark.parametrize("name", MODE_CASES)
 def test_other_rankings_against_reference(golden_dir, name, mode):
     """partial_Q / partial_K / MXINT4 (funcs/exponent_based_prediction.py:179-199,274-318) and the approx_flag=False branch
@@ -162,7 +162,7 @@ def test_other_rankings_against_reference(golden_dir, name, mode):
 CROSS_CASES = ["pixart_cross", "pixart_cross_k77", "pixart_cross_all"]
 
 
-@pytest.mark.parametrize("mode", ["partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "exact"])
+@pytest.mark.parametrize("mode", ["partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex", "exact"])
 def test_cross_attention_other_rankings(mode):
     """PixArt cross-attention with the additive text mask in the other ranking modes ("exact" = the branch an
     excluded timestep takes, MX_transformer_block.py:806,833-834) - oracle vs the reference's outputs."""

@@ -37,7 +37,7 @@ def main():
         specs = mx_specs(bfloat, False)
         g = torch.Generator(device="cuda").manual_seed(0)
         q, kk, v = (torch.randn(B, H, N, hd, device="cuda", generator=g) for _ in range(3))
-        for mode in ("ex_pred", "partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "exact"):
+        for mode in ("ex_pred", "partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex", "exact"):
             t_sel = timed(lambda: mxq.predict_topk(q, kk, specs, k, pred_mode=mode), args.reps)
             t_all = timed(lambda: mxq.pruned_attention(q, kk, v, specs, k, pred_mode=mode), args.reps)
             print(json.dumps({"workload": name, "pred_mode": mode, "B": B, "H": H, "N": N, "hd": hd, "top_k": k,

@@ -32,7 +32,7 @@ def main():
         top_k = ri(1, Nk)
         bfloat = 16 if ri(0, 1) else 32
         flush = bool(ri(0, 1))
-        mode = ["partial_Q", "partial_K", "MXINT4", "exact", "two_step_leading_ones"][ri(0, 4)]
+        mode = ["partial_Q", "partial_K", "MXINT4", "exact", "two_step_leading_ones", "true_ex"][ri(0, 5)]
         kind = ["randn", "lognormal", "edges"][ri(0, 2)] if min(Nq, Nk) >= 16 and Nq == Nk and hd >= 64 else "randn"
         q, _, _ = make_qkv(B, H, Nq, hd, seed=3000 + c, kind=kind)
         _, k, v = make_qkv(B, H, Nk, hd, seed=4000 + c, kind=kind)
