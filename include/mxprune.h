@@ -206,6 +206,28 @@ int mxp_predict_topk_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * ELSA ranking (funcs/elsa_approximation.py:60-145, workloads/deit/scripts/main.py:119-121): keys are ranked per
+ * query row on  ||K_i|| * cos(max(pi/d * h - 0.127, 0)),  h = Hamming distance of the d-bit sign hashes of the MXINT8
+ * rows of Q and K under the d x d orthogonal matrix `proj` (fp32 row-major on the device, 16-byte aligned; hash j =
+ * (x . proj[j] >= 0)).  Inside a row that is the order of min(d - 2h, rank_cap), rank_cap = d - 2 h_c with h_c the
+ * largest h the reference's fp32 clamp maps to angle 0 (the caller evaluates that clamp; mx_quantization_b200.ops
+ * does).  Nq == Nk = N as in the reference, d = head_dim <= 80, N <= 256.  Hash bits of projections within fp32
+ * rounding distance of 0 depend on the summation order (the reference's BLAS vs. this library).
+ */
+int mxp_pruned_attention_elsa(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                              const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                              const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                              int B, int H, int N, int hd, int top_k, const float* proj, float rank_cap,
+                              float scale, int bfloat_bits, int flush,
+                              float* out, int64_t o_sB, int64_t o_sH, int64_t o_sN,
+                              uint32_t* mask_out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int mxp_predict_topk_elsa(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                          const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                          int B, int H, int N, int hd, int top_k, const float* proj, float rank_cap,
+                          int bfloat_bits, int flush, uint32_t* mask, int32_t* idx, void* stream);
+
+/*
  * MX Linear (the step either side of the attention core): the forward of the
  * reference's mx.Linear (microxscaling/mx/linear.py:20-103) for MXINT8 activations and weights,
  *     y = A1( A1( MXq(A1(x)) . MXq(A1(W))^T ) + A1(bias) )

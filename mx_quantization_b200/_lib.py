@@ -38,6 +38,10 @@ _SIGNATURES = {
                                   + [c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mxp_predict_topk_mode": (c_int, _VIEW * 2 + [c_int] * 7 + [c_float, c_int, c_int]
                               + [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mxp_pruned_attention_elsa": (c_int, _VIEW * 3 + [c_int] * 5 + [c_void_p, c_float] + [c_float, c_int, c_int] + _VIEW
+                                  + [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mxp_predict_topk_elsa": (c_int, _VIEW * 2 + [c_int] * 5 + [c_void_p, c_float] + [c_int, c_int]
+                              + [c_void_p, c_void_p, c_void_p]),
     "mxp_mx_linear_weight_bytes": (c_size_t, [c_int, c_int]),
     "mxp_mx_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mxp_mx_linear_prepare_weight": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

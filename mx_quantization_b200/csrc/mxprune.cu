@@ -682,17 +682,17 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
 }
 
 // ---- K1-wide: partial_Q / partial_K / exact-score top-k, Nk <= 256, tensor-core domain only
-template <int NC, bool TWO>
+template <int NC, bool TWO, bool ELSA>
 static int launch_predict_topk_wide_one(const PredParams& p, const K1cMaps& maps, const K1cSmem& L, size_t dyn,
                                         dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_wide<NC, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_wide<NC, TWO, ELSA>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    k_predict_topk_wide<NC, TWO><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
+    k_predict_topk_wide<NC, TWO, ELSA><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
     return check_launch("k_predict_topk_wide");
 }
 
@@ -707,10 +707,20 @@ static int predict_topk_wide(const PredParams& p, cudaStream_t st) {
     if (!make_view_maps(p.q, p.B, p.H, p.Nq, p.hd, &maps.q_main, &maps.q_tail) ||
         !make_view_maps(p.k, p.B, p.H, p.Nk, p.hd, &maps.k_main, &maps.k_tail))
         return fail(MXP_E_UNSUPPORTED, "pred_mode %d: the q/k views cannot be described by a TMA tensor map", p.pred_mode);
-    // two_step_leading_ones carries two operand parts per side: twice the operand shared memory, one CTA per SM
-    const bool two = p.pred_mode == PRED_TWO_STEP;
+    // two_step_leading_ones carries two operand parts per side (twice the operand shared memory), ELSA keeps its
+    // projection matrix in shared memory: one CTA per SM for both
+    const bool two = p.pred_mode == PRED_TWO_STEP, elsa = p.pred_mode == PRED_ELSA;
+    if (elsa) {
+        if (!p.elsa_proj || ((uintptr_t)p.elsa_proj & 15))
+            return fail(MXP_E_BADARG, "ELSA: the projection matrix must be a 16-byte aligned device pointer");
+        if (p.Nq != p.Nk || p.hd > ELSA_MAX_HD)
+            return fail(MXP_E_UNSUPPORTED, "ELSA needs Nq == Nk (the reference broadcasts the key norms over rows) and "
+                        "head_dim <= %d (got Nq=%d Nk=%d hd=%d)", ELSA_MAX_HD, p.Nq, p.Nk, p.hd);
+        if (p.key_bias) return fail(MXP_E_UNSUPPORTED, "ELSA takes no key bias (the reference's cross-attention has no ELSA branch)");
+    }
     const int opw = two ? 2 : 1;
-    const size_t per_cta1 = 232448 - 1024, per_cta2 = two ? per_cta1 : 232448 / 2 - 1024;
+    const size_t extra = elsa ? 16 + (size_t)p.hd * p.hd * 4 : 0;
+    const size_t per_cta1 = 232448 - 1024 - extra, per_cta2 = (two || elsa) ? per_cta1 : 232448 / 2 - 1024;
     const int nc = p.Nk <= 32 ? 1 : p.Nk <= 64 ? 2 : p.Nk <= 128 ? 4 : p.Nk <= 224 ? 7 : 8;
     const int nb = (p.hd + 31) / 32;
     int G = nb <= 2 ? 2 : 1;
@@ -726,11 +736,13 @@ static int predict_topk_wide(const PredParams& p, cudaStream_t st) {
     if (splits < 1) splits = 1;
     dim3 grid((unsigned)heads, (unsigned)splits);
     const int max_ctas = 512 / L.tmem_cols;
-    size_t dyn = L.total;
+    size_t dyn = L.total + extra;
     const size_t floor_bytes = (size_t)232448 / (size_t)(max_ctas + 1) + 1024;
     if (dyn < floor_bytes) dyn = floor_bytes;
-#define MXP_WIDE(NC_) (two ? launch_predict_topk_wide_one<NC_, true>(p, maps, L, dyn, grid, st)   \
-                           : launch_predict_topk_wide_one<NC_, false>(p, maps, L, dyn, grid, st))
+    if (elsa && dyn < 232448 / 2) dyn = 232448 / 2;                 // one CTA per SM (launch bounds assume it)
+#define MXP_WIDE(NC_) (two ? launch_predict_topk_wide_one<NC_, true, false>(p, maps, L, dyn, grid, st)   \
+                     : elsa ? launch_predict_topk_wide_one<NC_, false, true>(p, maps, L, dyn, grid, st) \
+                            : launch_predict_topk_wide_one<NC_, false, false>(p, maps, L, dyn, grid, st))
     switch (nc) {
         case 1: return MXP_WIDE(1);
         case 2: return MXP_WIDE(2);
@@ -937,7 +949,7 @@ static int predict_topk_impl(const PredParams& p, cudaStream_t st) {
     int rc = MXP_OK;
     if (p.key_bias && p.Nk > K1_MAX_KEYS)
         return fail(MXP_E_UNSUPPORTED, "key_bias: the additive key bias is implemented for Nk <= 256 (cross-attention)");
-    if (p.pred_mode < 0 || p.pred_mode > 6) return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 6]", p.pred_mode);
+    if (p.pred_mode < 0 || p.pred_mode > 7) return fail(MXP_E_BADARG, "pred_mode=%d outside [0, 7]", p.pred_mode);
     if (p.pred_mode != 0) return predict_topk_wide(p, st);
     if (try_predict_topk_tc(p, st, &rc) == 0) return rc;
     if (try_predict_topk_long_tc(p, st, &rc) == 0) return rc;
@@ -1050,7 +1062,8 @@ static int pruned_attention_impl(const float* q, int64_t q_sB, int64_t q_sH, int
                                  int B, int H, int Nq, int Nk, int hd, int top_k, float scale,
                                  int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
                                  int64_t o_sN, const float* key_bias, int64_t kb_sB, uint32_t* mask_out,
-                                 void* workspace, size_t workspace_bytes, void* stream, int pred_mode = 0) {
+                                 void* workspace, size_t workspace_bytes, void* stream, int pred_mode = 0,
+                                 const float* elsa_proj = nullptr, float elsa_cap = 0.f) {
     g_launches = 0;
     if (pred_mode != 0 && g_attn_path != 0)
         return fail(MXP_E_UNSUPPORTED, "pred_mode %d needs the tcgen05 attention path", pred_mode);
@@ -1083,6 +1096,7 @@ static int pruned_attention_impl(const float* q, int64_t q_sB, int64_t q_sH, int
     pp.mask = mask; pp.idx = nullptr;
     pp.key_bias = key_bias; pp.kb_sB = kb_sB;
     pp.pred_mode = pred_mode; pp.score_scale = scale;
+    pp.elsa_proj = elsa_proj; pp.elsa_cap = elsa_cap;
     pp.long_ws = long_bytes ? w + need - long_bytes : nullptr;
     pp.long_ws_bytes = long_bytes;
     if (tc) {
@@ -1183,6 +1197,39 @@ int mxp_predict_topk_mode(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_
     p.pred_mode = pred_mode; p.score_scale = scale;
     p.key_bias = key_bias; p.kb_sB = kb_sB;
     p.long_ws = workspace; p.long_ws_bytes = workspace_bytes;
+    return predict_topk_impl(p, (cudaStream_t)stream);
+}
+
+int mxp_pruned_attention_elsa(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                              const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                              const float* v, int64_t v_sB, int64_t v_sH, int64_t v_sN,
+                              int B, int H, int N, int hd, int top_k, const float* proj, float rank_cap,
+                              float scale, int bfloat_bits, int flush, float* out, int64_t o_sB, int64_t o_sH,
+                              int64_t o_sN, uint32_t* mask_out, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+    return pruned_attention_impl(q, q_sB, q_sH, q_sN, k, k_sB, k_sH, k_sN, v, v_sB, v_sH, v_sN, B, H, N, N, hd,
+                                 top_k, scale, bfloat_bits, flush, out, o_sB, o_sH, o_sN, nullptr, 0, mask_out,
+                                 workspace, workspace_bytes, stream, PRED_ELSA, proj, rank_cap);
+}
+
+int mxp_predict_topk_elsa(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
+                          const float* k, int64_t k_sB, int64_t k_sH, int64_t k_sN,
+                          int B, int H, int N, int hd, int top_k, const float* proj, float rank_cap,
+                          int bfloat_bits, int flush, uint32_t* mask, int32_t* idx, void* stream) {
+    g_launches = 0;
+    int rc = check_shape(B, H, N, N, hd, bfloat_bits);
+    if (rc) return rc;
+    if ((rc = check_view("q", q, q_sB, q_sH, q_sN, hd))) return rc;
+    if ((rc = check_view("k", k, k_sB, k_sH, k_sN, hd))) return rc;
+    if (!mask) return fail(MXP_E_BADARG, "mask: null pointer");
+    if (top_k < 1 || top_k > N) return fail(MXP_E_BADARG, "top_k=%d outside [1, N=%d]", top_k, N);
+    PredParams p{};
+    p.q = View{q, q_sB, q_sH, q_sN};
+    p.k = View{k, k_sB, k_sH, k_sN};
+    p.B = B; p.H = H; p.Nq = N; p.Nk = N; p.hd = hd; p.top_k = top_k;
+    p.bf16 = bfloat_bits == 16; p.flush = flush != 0;
+    p.mask = mask; p.idx = idx;
+    p.pred_mode = PRED_ELSA; p.elsa_proj = proj; p.elsa_cap = rank_cap;
     return predict_topk_impl(p, (cudaStream_t)stream);
 }
 

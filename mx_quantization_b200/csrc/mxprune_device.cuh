@@ -36,8 +36,10 @@ struct PredParams {
     const uint8_t* row_filter;   // k_predict_topk_long only: [heads][Nq], process rows with a non-zero flag (null = all)
     void* long_ws;               // host side: workspace of the long-sequence tensor-core path (may be null)
     size_t long_ws_bytes;
-    int pred_mode;               // 0 exponent-sign (default), 1 partial_Q, 2 partial_K, 3 exact scores, 4 MXINT4, 5 two-step, 6 true_ex (mxprune_predict_wide.cuh)
+    int pred_mode;               // 0 exponent-sign (default), 1 partial_Q, 2 partial_K, 3 exact scores, 4 MXINT4, 5 two-step, 6 true_ex, 7 ELSA (mxprune_predict_wide.cuh)
     float score_scale;           // pred_mode 3: the attention scale the true scores are ranked with
+    const float* elsa_proj;      // pred_mode 7 (ELSA): the hd x hd projection matrix, fp32 row-major (hash j = sign(x . P[j]))
+    float elsa_cap;              // pred_mode 7: hash dot products above this value tie (the reference's angle clamp)
 };
 
 // 2^e as fp32 for e in [-149, 127] (subnormal below -126).

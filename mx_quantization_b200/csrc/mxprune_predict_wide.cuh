@@ -11,6 +11,14 @@
 //   pred_mode 6  true_ex     sign * 2^floor(log2 |MX element|) per element (zero elements: +1, as the example's
 //                            get_true_exponents leaves their exponent at 0): the leading one of every element  microxscaling/examples/deit/exponent_based_prediction.py:163-178 (the
 //                            copy under funcs/ lacks the method), PixArt MX_transformer_block.py:663-664,811-812
+//   pred_mode 7  ELSA        funcs/elsa_approximation.py:112-145, main.py:119-121: hash signs s = (MX . P^T >= 0 ? +1 : -1)
+//                            of the MXINT8 rows under a d x d orthogonal matrix P, h = (d - s_q . s_k) / 2, ranked
+//                            on  ||K_i|| * cos(max(pi/d * h - 0.127, 0))  - the key norm is broadcast over ROWS (:140),
+//                            so inside a row the order is that of  min(s_q . s_k, cap)  (cap: the dot product of
+//                            the largest h the fp32 clamp sends to angle 0, computed by the host) and an all-zero
+//                            key row i ties the whole query row i.  The projections are fp32 FMAs on the CUDA cores
+//                            over the exact operands the quantizer left in shared memory; the +-1 signs replace
+//                            them as the MMA operands.  Needs Nq == Nk (as the reference's broadcast does), d <= 80.
 //   pred_mode 5  two_step_leading_ones (EXION)   funcs/exponent_based_prediction.py:96-177, main.py:115-116
 //                            value = sign(c) * e * (2^f1 + 2^f2) / 64 as the reference computes it: e is the shared
 //                            exponent's VALUE, f1 the leading one of |c|, f2 the leading one of c - 2^f1 for
@@ -45,7 +53,7 @@ __device__ __forceinline__ void tmem_st_16x32bx2_x16(uint32_t taddr, const uint3
         : "memory");
 }
 
-constexpr int PRED_EX = 0, PRED_PARTIAL_Q = 1, PRED_PARTIAL_K = 2, PRED_TRUE = 3, PRED_MXINT4 = 4, PRED_TWO_STEP = 5, PRED_TRUE_EX = 6;
+constexpr int PRED_EX = 0, PRED_PARTIAL_Q = 1, PRED_PARTIAL_K = 2, PRED_TRUE = 3, PRED_MXINT4 = 4, PRED_TWO_STEP = 5, PRED_TRUE_EX = 6, PRED_ELSA = 7;
 
 // MXINT4 operand of one block: value = sign(x) * min(7, floor(|x| * 2^(2-e) + 0.5)) * 2^(e-2), the int4 element
 // format of the reference (formats.py:86-88: mbits 4, emax 0 -> the MXINT8 shared exponent e; lshift by
@@ -124,8 +132,10 @@ __device__ __forceinline__ void two_step_operands(const uint32_t (&cw)[8], int e
     }
 }
 
-template <int NC, bool TWO>
-__global__ void __launch_bounds__(K1C_T, TWO ? 1 : 2)
+constexpr int ELSA_MAX_HD = 80;
+
+template <int NC, bool TWO, bool ELSA = false>
+__global__ void __launch_bounds__(K1C_T, (TWO || ELSA) ? 1 : 2)
 k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring, const int G) {
     extern __shared__ __align__(1024) unsigned char smem_k1w[];
     unsigned char* const smem = smem_k1w;
@@ -133,8 +143,8 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
     constexpr int NCH = (NC + 1) / 2;                               // key chunks per thread
     const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
     const int mode = p.pred_mode;
-    const bool q_exact = mode == PRED_PARTIAL_Q || mode == PRED_TRUE;
-    const bool k_exact = mode == PRED_PARTIAL_K || mode == PRED_TRUE;
+    const bool q_exact = mode == PRED_PARTIAL_Q || mode == PRED_TRUE || ELSA;
+    const bool k_exact = mode == PRED_PARTIAL_K || mode == PRED_TRUE || ELSA;
     const bool true_mode = mode == PRED_TRUE;
     const bool int4_mode = mode == PRED_MXINT4 || mode == PRED_TRUE_EX;       // modes whose operand is formed in op4
     const bool true_ex_mode = mode == PRED_TRUE_EX;
@@ -148,6 +158,10 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.off_misc + 32);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_misc + 64);   // [K1C_MAXR]
     uint64_t* bar_mma = bar_full + K1C_MAXR;
+    // ELSA: the projection matrix (fp32, hd x hd) behind the regular layout; key-row "all zero" flags in the
+    // (otherwise unused) key-exponent bytes
+    float* s_proj = reinterpret_cast<float*>(smem + ((L.total + 15) & ~(size_t)15));
+    unsigned char* s_kzero = smem + L.off_kexp;
 
     const int head = blockIdx.x, bb = head / p.H, hh = head - bb * p.H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -200,6 +214,10 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
         if (tail) { prefetch_tmap(&maps.k_tail); prefetch_tmap(&maps.q_tail); }
     }
     if (warp == 0) tmem_alloc(s_tmem, (uint32_t)L.tmem_cols);
+    if (ELSA) {
+        for (int t = tid; t < hd * hd; t += K1C_T) s_proj[t] = __ldg(p.elsa_proj + t);
+        s_kzero[tid] = 1;                                           // K1C_T == 256 == the most key rows
+    }
     tcgen05_fence_before_sync();
     __syncthreads();
     tcgen05_fence_after_sync();
@@ -303,6 +321,56 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
                 }
             }
         }
+        if (ELSA) {
+            // ---- hash signs of the step's rows: x = the row's exact operand (bf16 in shared memory), hash j =
+            // (sum_d x[d] * P[j][d] >= 0); thread <-> (row, slice of the d hashes), a warp shares its slice of P
+            __syncthreads();                                        // the step's operand rows are complete
+            const int rl = tid & (CR - 1), jpart = tid >> cr_shift, nparts = K1C_T >> cr_shift;
+            const int JT = hd / nparts, j0 = jpart * JT;            // hd % 4 == 0, nparts in {2, 4}
+            const int ROWS = is_k ? NMMA : K1C_TILE;
+            const int rindex = is_k ? row0 + rl : qstep * CR + rl;
+            const bool present = !is_k || rindex < NMMA;
+            unsigned char* base = (is_k ? s_kop : s_qop) + (size_t)rindex * 16;
+            float xf[ELSA_MAX_HD];
+            uint32_t any = 0u;
+#pragma unroll
+            for (int ch = 0; ch < ELSA_MAX_HD / 8; ++ch) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (present && ch < kch) v = *reinterpret_cast<const uint4*>(base + (size_t)ch * ROWS * 16);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    xf[8 * ch + 2 * h] = __uint_as_float(w[h] << 16);
+                    xf[8 * ch + 2 * h + 1] = __uint_as_float(w[h] & 0xffff0000u);
+                    any |= w[h] & 0x7fff7fffu;
+                }
+            }
+            uint64_t bits = 0ull;                                   // bit jj: hash j0 + jj is negative
+            for (int jj = 0; jj < JT; ++jj) {
+                const float* pr = s_proj + (size_t)(j0 + jj) * hd;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int d = 0; d < ELSA_MAX_HD; d += 4) {
+                    if (d < hd) {
+                        const float4 pv = *reinterpret_cast<const float4*>(pr + d);
+                        a0 = fmaf(xf[d], pv.x, a0); a1 = fmaf(xf[d + 1], pv.y, a1);
+                        a2 = fmaf(xf[d + 2], pv.z, a2); a3 = fmaf(xf[d + 3], pv.w, a3);
+                    }
+                }
+                const float acc = (a0 + a1) + (a2 + a3);
+                bits |= (uint64_t)(acc >= 0.f ? 0u : 1u) << jj;
+            }
+            __syncthreads();                                        // every thread has read its row before any overwrite
+            if (present) {
+                for (int jj = 0; jj < JT; jj += 2) {                // JT and j0 are even: two hashes per 32-bit store
+                    const int j = j0 + jj;
+                    const uint32_t two = (((bits >> jj) & 1ull) ? 0xBF80u : 0x3F80u) |
+                                         ((((bits >> (jj + 1)) & 1ull) ? 0xBF80u : 0x3F80u) << 16);
+                    *reinterpret_cast<uint32_t*>(base + (size_t)(j >> 3) * ROWS * 16 + (j & 7) * 2) = two;
+                }
+                if (is_k && jpart == 0 && rindex < 256) s_kzero[rindex] = any == 0u ? 1 : 0;
+            }
+        }
         fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0 && c + ring < nsteps) issue(c + ring, slot_i);
@@ -361,6 +429,12 @@ k_predict_topk_wide(const PredParams p, const __grid_constant__ K1cMaps maps, co
                         if (bf16) sc = bf16_half_away(sc);
                         r[t] = __float_as_uint(__fmul_rn(sc, sscale));
                     }
+                }
+                if (ELSA) {
+                    const bool zrow = i < 256 && s_kzero[valid ? i : 0] != 0;      // ||K_i|| = 0 scales query row i to 0
+#pragma unroll
+                    for (int t = 0; t < 16; ++t)
+                        r[t] = zrow ? 0u : __float_as_uint(fminf(__uint_as_float(r[t]), p.elsa_cap));
                 }
                 if (kbias != nullptr) {
 #pragma unroll

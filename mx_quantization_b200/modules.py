@@ -29,13 +29,17 @@ from .specs import resolve_specs
 class PrunedAttentionCore(nn.Module):
     """q, k, v (B,H,N,hd) fp32 views -> x (B,N,H*hd), ready for the output projection."""
 
-    def __init__(self, mx_specs, k: int, scale: Optional[float] = None, pred_mode: str = "ex_pred"):
+    def __init__(self, mx_specs, k: int, scale: Optional[float] = None, pred_mode: str = "ex_pred",
+                 orthogonal_matrix: Optional[torch.Tensor] = None):
         super().__init__()
         resolve_specs(mx_specs)
         self.mx_specs = mx_specs
         self.k = int(k)
         self.scale = scale
         self.pred_mode = pred_mode
+        if pred_mode == "ELSA" and orthogonal_matrix is None:
+            raise ValueError("pred_mode='ELSA' needs orthogonal_matrix (workloads/deit/scripts/main.py:119-121)")
+        self.orthogonal_matrix = orthogonal_matrix
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
                 key_bias: Optional[torch.Tensor] = None, dense: bool = False,
@@ -46,8 +50,10 @@ class PrunedAttentionCore(nn.Module):
         # write straight into (B,N,H,hd): the reference's x.transpose(1,2).reshape(B,N,C) is free
         # k <= 0: dense MXINT8 attention (the reference's top_k=False blocks) = every key kept
         top_k = self.k if (self.k > 0 and not dense) else k.shape[2]
+        mode = pred_mode or self.pred_mode
         ops.pruned_attention(q, k, v, self.mx_specs, top_k, scale=self.scale, out=buf.permute(0, 2, 1, 3),
-                             key_bias=key_bias, pred_mode=pred_mode or self.pred_mode)
+                             key_bias=key_bias, pred_mode=mode,
+                             orthogonal_matrix=self.orthogonal_matrix if mode == "ELSA" else None)
         return buf.reshape(B, N, H * hd)
 
 
@@ -61,10 +67,10 @@ def _require_hot_path(mx_quant, top_k, approx, pred_mode, where) -> str:
                                   "B200 path and there is no fallback")
     if not approx:
         return "exact"
-    if pred_mode not in ("ex_pred", "partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex"):
+    if pred_mode not in ("ex_pred", "partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex", "ELSA"):
         raise NotImplementedError(
             f"{where}: pred_mode={pred_mode!r} is not built (built: 'ex_pred', 'partial_Q', 'partial_K', 'MXINT4', "
-            "'two_step_leading_ones', 'true_ex' and approx=False); ELSA is a predictor outside the path "
+            "'two_step_leading_ones', 'true_ex', 'ELSA' and approx=False) "
             "(SURVEY.md 8f3) and there is no fallback")
     return pred_mode
 
@@ -98,7 +104,8 @@ class QuantizedAttention(nn.Module):
         self.proj_drop = getattr(orig_attn, "proj_drop", nn.Identity())
         self.block_idx = block_idx
         self.current_timestep = 0
-        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale, pred_mode=mode)
+        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale, pred_mode=mode,
+                                        orthogonal_matrix=orthogonal_matrix)
 
     def forward(self, x):
         B, N, C = x.shape
@@ -132,7 +139,8 @@ class Attention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.block_idx = block_idx
         self.current_timestep = 0
-        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale, pred_mode=mode)
+        self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale, pred_mode=mode,
+                                        orthogonal_matrix=orthogonal_matrix)
 
     def forward(self, x):
         B, N, C = x.shape
@@ -172,7 +180,7 @@ class MXSelfAttention(nn.Module):
         self.to_out[0] = to_mx_linear(self.to_out[0], mx_specs)
         # reference: scale_factor = 1 / math.sqrt(q.size(-1)) applied as an fp32 scalar (:647-653)
         self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=1.0 / (self.head_dim ** 0.5),
-                                        pred_mode=mode)
+                                        pred_mode=mode, orthogonal_matrix=orthogonal_matrix)
         return self
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs):

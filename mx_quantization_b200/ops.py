@@ -116,10 +116,31 @@ PRED_MODES = {"ex_pred": 0, "partial_Q": 1, "partial_K": 2, "exact": 3, "MXINT4"
 
 def _pred_mode_code(pred_mode: str) -> int:
     if pred_mode not in PRED_MODES:
-        raise NotImplementedError(
-            f"pred_mode={pred_mode!r}: built modes are {sorted(PRED_MODES)}; ELSA is not built (SURVEY.md 8f3) "
-            "and there is no fallback")
+        raise NotImplementedError(f"pred_mode={pred_mode!r}: built modes are {sorted(PRED_MODES)} and 'ELSA'; "
+                                  "there is no fallback")
     return PRED_MODES[pred_mode]
+
+
+ELSA_THETA_BIAS = 0.127     # funcs/elsa_approximation.py:101
+
+
+def elsa_rank_cap(d: int) -> float:
+    """d - 2 h_c, h_c the largest Hamming distance the reference's clamp maps to angle 0
+    (funcs/elsa_approximation.py:135-136: clamp((pi / k) * hamming - theta_bias, min=0), evaluated in fp32 as torch does):
+    hash dot products at or above this value tie."""
+    h = torch.arange(0, d + 1, dtype=torch.float32)
+    corrected = torch.clamp((torch.pi / d) * h - ELSA_THETA_BIAS, min=0)
+    hc = int(torch.nonzero(corrected == 0).max())
+    return float(d - 2 * hc)
+
+
+def _elsa_proj(orthogonal_matrix, hd, dev):
+    if orthogonal_matrix is None:
+        raise ValueError("pred_mode='ELSA' needs orthogonal_matrix (the reference's (head_dim, head_dim) projection)")
+    P = orthogonal_matrix.to(device=dev, dtype=torch.float32).contiguous()
+    if tuple(P.shape) != (hd, hd):
+        raise ValueError(f"orthogonal_matrix must be ({hd}, {hd}), got {tuple(P.shape)}")
+    return P
 
 
 def _qk_shapes(q, k):
@@ -146,13 +167,15 @@ def predict_scores(q: torch.Tensor, k: torch.Tensor, mx_specs) -> torch.Tensor:
 
 def predict_topk(q: torch.Tensor, k: torch.Tensor, mx_specs, top_k: int, return_idx: bool = False,
                  return_codes: bool = False, pred_mode: str = "ex_pred", scale: Optional[float] = None,
-                 key_bias: Optional[torch.Tensor] = None):
+                 key_bias: Optional[torch.Tensor] = None, orthogonal_matrix: Optional[torch.Tensor] = None):
     """Fused quantize + predictor + per-row top-k.
 
     Returns a dict: mask int32 (B,H,Nq,ceil(Nk/32)) [bit j%32 of word j//32 = key j kept],
     optionally idx int32 (B,H,Nq,top_k) ascending key order, and q/k codes+exps.
     pred_mode: "ex_pred" (exponent-sign, default), "partial_Q", "partial_K", "MXINT4" or "exact" (top-k of the
     true scores * scale) - see PRED_MODES."""
+    if pred_mode == "ELSA":
+        return _predict_topk_elsa(q, k, mx_specs, top_k, return_idx, return_codes, key_bias, orthogonal_matrix)
     mode = _pred_mode_code(pred_mode)
     if mode != 0:
         return _predict_topk_mode(q, k, mx_specs, top_k, mode, scale, return_idx, return_codes, key_bias)
@@ -213,6 +236,29 @@ def _predict_topk_mode(q, k, mx_specs, top_k, mode, scale, return_idx, return_co
     return res
 
 
+def _predict_topk_elsa(q, k, mx_specs, top_k, return_idx, return_codes, key_bias, orthogonal_matrix):
+    if return_codes or key_bias is not None:
+        raise ValueError("pred_mode='ELSA' takes neither return_codes nor key_bias")
+    sp = resolve_specs(mx_specs)
+    lib = _lib.load()
+    q, k = _view4(q, "q"), _view4(k, "k")
+    dev = _same_device(q, k)
+    B, H, Nq, Nk, hd = _qk_shapes(q, k)
+    if Nq != Nk:
+        raise ValueError("pred_mode='ELSA' needs Nq == Nk (the reference broadcasts the key norms over query rows)")
+    P = _elsa_proj(orthogonal_matrix, hd, dev)
+    res = {}
+    with torch.cuda.device(dev):
+        res["mask"] = torch.empty((B, H, Nq, (Nk + 31) // 32), dtype=torch.int32, device=dev)
+        if return_idx:
+            res["idx"] = torch.empty((B, H, Nq, int(top_k)), dtype=torch.int32, device=dev)
+        rc = lib.mxp_predict_topk_elsa(_ptr(q), *_strides(q), _ptr(k), *_strides(k), B, H, Nq, hd, int(top_k),
+                                       _ptr(P), elsa_rank_cap(hd), sp.bfloat_bits, int(sp.flush),
+                                       _ptr(res["mask"]), _ptr(res.get("idx")), _stream())
+    _lib.check(rc, "mxp_predict_topk_elsa")
+    return res
+
+
 def sparse_attention(q_codes, q_exps, k_codes, k_exps, v: torch.Tensor, mask: torch.Tensor, mx_specs,
                      scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Exact MXINT8 softmax(QK^T*scale)V over the keys selected by ``mask``."""
@@ -244,12 +290,14 @@ def sparse_attention(q_codes, q_exps, k_codes, k_exps, v: torch.Tensor, mask: to
 def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs, top_k: int,
                      scale: Optional[float] = None, return_mask: bool = False,
                      out: Optional[torch.Tensor] = None, _kernel_ms: Optional[list] = None,
-                     key_bias: Optional[torch.Tensor] = None, pred_mode: str = "ex_pred"):
+                     key_bias: Optional[torch.Tensor] = None, pred_mode: str = "ex_pred",
+                     orthogonal_matrix: Optional[torch.Tensor] = None):
     """MXINT8 exponent-sign predicted top-k attention: q,k,v (B,H,N,hd) fp32 -> out (B,H,Nq,hd).
 
     ``pred_mode``: what ranks the keys - "ex_pred" (default), "partial_Q", "partial_K", "MXINT4" (the reference's
     pred_mode values, workloads/deit/scripts/main.py:109-118) or "exact" (its approx_flag=False branch:
-    top-k of the true scores, main.py:130).  Everything after the selection is the same.
+    top-k of the true scores, main.py:130), or "ELSA" with ``orthogonal_matrix`` (head_dim, head_dim) as the
+    reference's modules receive it (main.py:119-121).  Everything after the selection is the same.
 
     Drop-in for lines 101-152 of workloads/deit/scripts/main.py (DiT models.py:168-225, PixArt
     MX_transformer_block.py:647-710) when mx_quant, top_k, approx_flag and pred_mode=="ex_pred".
@@ -269,7 +317,11 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
     if tuple(v.shape) != (B, H, Nk, hd):
         raise ValueError(f"v {tuple(v.shape)} must be (B,H,Nk,head_dim) = {(B, H, Nk, hd)}")
     scale = float(hd) ** -0.5 if scale is None else float(scale)
-    mode = _pred_mode_code(pred_mode)
+    elsa = pred_mode == "ELSA"
+    if elsa and (key_bias is not None or _kernel_ms is not None or Nq != Nk):
+        raise ValueError("pred_mode='ELSA' needs Nq == Nk and takes neither key_bias nor the per-kernel profile entry")
+    P = _elsa_proj(orthogonal_matrix, hd, dev) if elsa else None
+    mode = 0 if elsa else _pred_mode_code(pred_mode)
     if mode != 0 and _kernel_ms is not None:
         raise ValueError("the per-kernel profile entry is available with pred_mode='ex_pred' only")
     with torch.cuda.device(dev):
@@ -284,7 +336,10 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
                 B, H, Nq, Nk, hd, int(top_k), scale, sp.bfloat_bits, int(sp.flush),
                 _ptr(out), *_strides(out), _ptr(mask), _ptr(ws), ws_bytes, _stream())
         kb = None if key_bias is None else _key_bias_2d(key_bias, B, Nk, q.device)
-        if mode != 0:
+        if elsa:
+            rc = lib.mxp_pruned_attention_elsa(*args[:12], B, H, Nq, hd, int(top_k), _ptr(P), elsa_rank_cap(hd),
+                                               *args[18:])
+        elif mode != 0:
             rc = lib.mxp_pruned_attention_mode(*args[:18], mode, *args[18:-4], _ptr(kb), Nk, *args[-4:])
         elif key_bias is not None:
             if _kernel_ms is not None:

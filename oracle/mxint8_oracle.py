@@ -305,6 +305,22 @@ def sign_leading_ones(codes: torch.Tensor, exps: torch.Tensor, block: int = BLOC
     return torch.ldexp(torch.where(c < 0, -1.0, 1.0).to(torch.float32), t)
 
 
+def elsa_scores(qc, qe, kc, ke, projection: torch.Tensor, block: int = BLOCK) -> torch.Tensor:
+    """funcs/elsa_approximation.py:103-145 on the MXINT8 values: k-bit sign hashes of MX @ P^T (>= 0 -> 1),
+    Hamming distance from the +-1 dot product, angle pi/k * h - 0.127 clamped at 0, and the key norms
+    `unsqueeze(-1)`-broadcast over the QUERY rows exactly as the reference writes it (:140; needs Nq == Nk)."""
+    mq, mk = dequantize_mxint8(qc, qe, block), dequantize_mxint8(kc, ke, block)
+    k_bits = mk.shape[-1]
+    P = projection.to(torch.float32)
+    s_q = (torch.matmul(mq, P.T) >= 0).to(torch.int8).mul(2).sub(1).float()
+    s_k = (torch.matmul(mk, P.T) >= 0).to(torch.int8).mul(2).sub(1).float()
+    dots = torch.einsum('bhnk,bhmk->bhnm', s_q, s_k)
+    hamming = 0.5 * (k_bits - dots)
+    est = (torch.pi / k_bits) * hamming.float()
+    corrected = torch.clamp(est - 0.127, min=0)
+    return torch.norm(mk, dim=-1).unsqueeze(-1) * torch.cos(corrected)
+
+
 def pred_scores_mode(qc, qe, kc, ke, pred_mode: str = "ex_pred", block: int = BLOCK) -> torch.Tensor:
     """`pred_scores = ex_quant_q @ ex_quant_k^T` (workloads/deit/scripts/main.py:118) for the predictor
     variants that reuse the MXINT8 codes:
@@ -388,7 +404,8 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
                      idx: Optional[torch.Tensor] = None, use_torch_topk: bool = False,
                      integer_scores: bool = False,
                      key_bias: Optional[torch.Tensor] = None,
-                     pred_mode: str = "ex_pred") -> Dict[str, torch.Tensor]:
+                     pred_mode: str = "ex_pred",
+                     orthogonal_matrix: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """The whole path on CPU (q, k, v: fp32 (B,H,N,hd)); returns every intermediate.
 
     key_bias: additive attention bias broadcastable to (B,1,1,Nk), as PixArt's cross-attention
@@ -415,6 +432,8 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, top_k: i
     if idx is None:
         if pred_mode == "exact":
             pred = true
+        elif pred_mode == "ELSA":                                    # funcs/elsa_approximation.py, main.py:119-121
+            pred = elsa_scores(qc, qe, kc, ke, orthogonal_matrix)
         elif pred_mode == "MXINT4":                                  # funcs/exponent_based_prediction.py:179-199
             pred = fake_quant_mxint4(q, BLOCK, bfloat, flush) @ fake_quant_mxint4(k, BLOCK, bfloat, flush).transpose(-2, -1)
         elif pred_mode != "ex_pred":

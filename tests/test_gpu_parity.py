@@ -589,12 +589,12 @@ def test_other_rankings_module_and_errors(mxq):
         assert outs[name].shape == x.shape and bool(torch.isfinite(outs[name]).all())
     assert not torch.equal(outs["ex"], outs["exact"])
     with pytest.raises(NotImplementedError):
-        Attention(128, num_heads=2, mx_quant=True, mx_specs=specs, top_k=True, k=16, ex_pred=True, pred_mode="ELSA")
+        Attention(128, num_heads=2, mx_quant=True, mx_specs=specs, top_k=True, k=16, ex_pred=True, pred_mode="sanger")
     q = torch.randn(1, 1, 300, 64, device="cuda")
     with pytest.raises(ValueError):                      # modes 1-3: Nk <= 256
         mxq.predict_topk(q, q, specs, 10, pred_mode="partial_K")
     with pytest.raises(NotImplementedError):
-        mxq.predict_topk(q, q, specs, 10, pred_mode="ELSA")
+        mxq.predict_topk(q, q, specs, 10, pred_mode="sanger")
     big = torch.randn(1, 1, 256, 128, device="cuda")       # two-part operands: head_dim 128 x 256 keys do not fit
     with pytest.raises(ValueError, match="shared memory"):
         mxq.predict_topk(big, big, specs, 10, pred_mode="two_step_leading_ones")
@@ -646,3 +646,47 @@ def test_exclude_timesteps_in_shims(mxq):
     am[0, 0, 25:] = -10000.0
     z0, z1 = c(x, encoder_hidden_states=enc, attention_mask=am), c(x, encoder_hidden_states=enc, attention_mask=am)
     assert z0.shape == x.shape and bool(torch.isfinite(z0).all()) and not torch.equal(z0, z1)
+
+
+@pytest.mark.parametrize("name", ["elsa_deit", "elsa_dit", "elsa_edges"])
+def test_elsa_reference_golden(mxq, name):
+    """ELSA ranking (funcs/elsa_approximation.py): masks against the unmodified reference.  A hash bit is the sign of
+    an fp32 projection; the fixture records how close the closest one comes to 0 (relative to its row) - above a few
+    fp32 rounding errors every mask must match, below that a row may differ where its hash flipped."""
+    d, m = load_golden(name)
+    specs = mx_specs(m["bfloat"], m["flush"])
+    q, k, v, P = d["q"].cuda(), d["k"].cuda(), d["v"].cuda(), d["P"].cuda()
+    out, mask = mxq.pruned_attention(q, k, v, specs, m["top_k"], return_mask=True, pred_mode="ELSA", orthogonal_matrix=P)
+    got = unpack_mask(mask, m["N"])
+    want = torch.zeros_like(got)
+    want.scatter_(-1, d["idx"], True)
+    assert bool((got.sum(-1) == m["top_k"]).all())
+    rows_equal = float((got == want).all(-1).float().mean())
+    if float(d["hash_margin"][0]) > 5e-6:
+        assert rows_equal == 1.0
+        r = O.pruned_attention(d["q"], d["k"], d["v"], m["top_k"], bfloat=m["bfloat"], flush=m["flush"], idx=d["idx"])
+        ref = {"true_vals": r["true_vals"], "idx": d["idx"], "out": d["out"]}
+        assert_out_close(out.cpu(), ref, d["v"], m["N"], m["bfloat"], OUT_TOL)
+    else:
+        assert rows_equal > 0.98
+    sel = mxq.predict_topk(q, k, specs, m["top_k"], pred_mode="ELSA", orthogonal_matrix=P, return_idx=True)
+    assert torch.equal(sel["mask"], mask)
+
+
+def test_elsa_module_and_errors(mxq):
+    from mx_quantization_b200.modules import Attention
+    specs = mx_specs(16, False)
+    torch.manual_seed(0)
+    x = torch.randn(2, 64, 128, device="cuda")
+    P = torch.linalg.qr(torch.randn(64, 64))[0].cuda()
+    m = Attention(128, num_heads=2, qkv_bias=True, mx_quant=True, mx_specs=specs, top_k=True, k=16, ex_pred=True,
+                  pred_mode="ELSA", orthogonal_matrix=P).cuda()
+    y = m(x)
+    assert y.shape == x.shape and bool(torch.isfinite(y).all())
+    with pytest.raises(ValueError):
+        Attention(128, num_heads=2, mx_quant=True, mx_specs=specs, top_k=True, k=16, ex_pred=True, pred_mode="ELSA")
+    q = torch.randn(1, 1, 64, 64, device="cuda")
+    with pytest.raises(ValueError):                      # Nq != Nk
+        mxq.predict_topk(q, q[:, :, :32], specs, 8, pred_mode="ELSA", orthogonal_matrix=P)
+    with pytest.raises(ValueError):                      # matrix shape
+        mxq.predict_topk(q, q, specs, 8, pred_mode="ELSA", orthogonal_matrix=P[:32])

@@ -159,6 +159,28 @@ def test_other_rankings_against_reference(golden_dir, name, mode):
     assert float((r["out"] - ref_out).abs().max()) <= 1e-3 * float(ref_out.abs().max())
 
 
+@pytest.mark.parametrize("name", ["elsa_deit", "elsa_dit", "elsa_edges"])
+def test_elsa_ranking_against_reference(golden_dir, name):
+    """ELSA (funcs/elsa_approximation.py:103-145, main.py:119-124): outputs of the unmodified reference class with a
+    projection matrix from its own generator (tests/golden/make_golden_elsa.py)."""
+    d, m = load(golden_dir, name)
+    r = O.pruned_attention(d["q"], d["k"], d["v"], m["top_k"], bfloat=m["bfloat"], flush=m["flush"],
+                           pred_mode="ELSA", orthogonal_matrix=d["P"])
+    assert torch.equal(r["pred_scores"], d["rank_scores"])
+    assert torch.equal(r["idx"], d["idx"])
+    assert float((r["out"] - d["out"]).abs().max()) <= 1e-3 * float(d["out"].abs().max())
+    # inside a row the reference's ranking is that of min(s_q . s_k, cap): what the CUDA kernel ranks on
+    from mx_quantization_b200.ops import elsa_rank_cap
+    qc, qe = O.quantize_mxint8(d["q"], 32, m["bfloat"], m["flush"])
+    kc, ke = O.quantize_mxint8(d["k"], 32, m["bfloat"], m["flush"])
+    mq, mk = O.dequantize_mxint8(qc, qe), O.dequantize_mxint8(kc, ke)
+    s_q = torch.where(mq @ d["P"].T >= 0, 1.0, -1.0)
+    s_k = torch.where(mk @ d["P"].T >= 0, 1.0, -1.0)
+    dots = torch.clamp(s_q @ s_k.transpose(-2, -1), max=elsa_rank_cap(m["hd"]))
+    dots = torch.where((mk.abs().sum(-1) == 0).unsqueeze(-1), torch.zeros_like(dots), dots)
+    assert torch.equal(O.canonical_topk(dots, m["top_k"]), d["idx"])
+
+
 CROSS_CASES = ["pixart_cross", "pixart_cross_k77", "pixart_cross_all"]
 
 

@@ -37,9 +37,11 @@ def main():
         specs = mx_specs(bfloat, False)
         g = torch.Generator(device="cuda").manual_seed(0)
         q, kk, v = (torch.randn(B, H, N, hd, device="cuda", generator=g) for _ in range(3))
-        for mode in ("ex_pred", "partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex", "exact"):
-            t_sel = timed(lambda: mxq.predict_topk(q, kk, specs, k, pred_mode=mode), args.reps)
-            t_all = timed(lambda: mxq.pruned_attention(q, kk, v, specs, k, pred_mode=mode), args.reps)
+        P = torch.linalg.qr(torch.randn(hd, hd, generator=torch.Generator().manual_seed(1)))[0].cuda()
+        for mode in ("ex_pred", "partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex", "ELSA", "exact"):
+            extra = {"orthogonal_matrix": P} if mode == "ELSA" else {}
+            t_sel = timed(lambda: mxq.predict_topk(q, kk, specs, k, pred_mode=mode, **extra), args.reps)
+            t_all = timed(lambda: mxq.pruned_attention(q, kk, v, specs, k, pred_mode=mode, **extra), args.reps)
             print(json.dumps({"workload": name, "pred_mode": mode, "B": B, "H": H, "N": N, "hd": hd, "top_k": k,
                               "select_ms": round(t_sel, 4), "layer_ms": round(t_all, 4),
                               "heads_per_s": round(B * H / (t_all * 1e-3))}), flush=True)
