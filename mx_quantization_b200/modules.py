@@ -40,6 +40,10 @@ class PrunedAttentionCore(nn.Module):
         if pred_mode == "ELSA" and orthogonal_matrix is None:
             raise ValueError("pred_mode='ELSA' needs orthogonal_matrix (workloads/deit/scripts/main.py:119-121)")
         self.orthogonal_matrix = orthogonal_matrix
+        # --anal (main.py:134-136): "Average chosen k" = funcs/analysis.py total_chosen_k, from the kept-key bitmask;
+        # the per-timestep diff_idx text dumps (main.py:137-143) are not produced
+        self.anal = False
+        self.avg_chosen_k = None
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
                 key_bias: Optional[torch.Tensor] = None, dense: bool = False,
@@ -51,9 +55,13 @@ class PrunedAttentionCore(nn.Module):
         # k <= 0: dense MXINT8 attention (the reference's top_k=False blocks) = every key kept
         top_k = self.k if (self.k > 0 and not dense) else k.shape[2]
         mode = pred_mode or self.pred_mode
-        ops.pruned_attention(q, k, v, self.mx_specs, top_k, scale=self.scale, out=buf.permute(0, 2, 1, 3),
-                             key_bias=key_bias, pred_mode=mode,
-                             orthogonal_matrix=self.orthogonal_matrix if mode == "ELSA" else None)
+        res = ops.pruned_attention(q, k, v, self.mx_specs, top_k, scale=self.scale, out=buf.permute(0, 2, 1, 3),
+                                   key_bias=key_bias, pred_mode=mode, return_mask=self.anal,
+                                   orthogonal_matrix=self.orthogonal_matrix if mode == "ELSA" else None)
+        if self.anal:
+            from .analysis import coverage_rate
+            self.avg_chosen_k = coverage_rate(res[1])
+            print(f"Average chosen k: {self.avg_chosen_k:.3f}")         # as main.py:136
         return buf.reshape(B, N, H * hd)
 
 
@@ -95,8 +103,6 @@ class QuantizedAttention(nn.Module):
                  pred_mode="ex_pred", anal=False, file_name_dict=None, block_idx=None, orthogonal_matrix=None):
         super().__init__()
         mode = _require_hot_path(mx_quant, top_k, approx_flag, pred_mode, "QuantizedAttention")
-        if anal:
-            raise NotImplementedError("--anal analysis dumps are out of scope (SURVEY.md 8f4)")
         self.num_heads = orig_attn.num_heads
         self.scale = orig_attn.scale
         # the reference swaps the projections for mx.Linear as well (main.py:262-281)
@@ -106,6 +112,7 @@ class QuantizedAttention(nn.Module):
         self.current_timestep = 0
         self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale, pred_mode=mode,
                                         orthogonal_matrix=orthogonal_matrix)
+        self.core.anal = bool(anal) and bool(top_k)
 
     def forward(self, x):
         B, N, C = x.shape
@@ -126,8 +133,6 @@ class Attention(nn.Module):
         super().__init__()
         assert dim % num_heads == 0, 'dim should be divisible by num_heads'
         mode = _require_hot_path(mx_quant, top_k, ex_pred, pred_mode, "Attention")
-        if anal:
-            raise NotImplementedError("--anal analysis dumps are out of scope (SURVEY.md 8f4)")
         # steps listed here run dense attention (models.py:172: `top_k and current_timestep not in exclude_timesteps`)
         self.exclude_timesteps = set(exclude_timesteps or ())
         self.num_heads, self.head_dim = num_heads, dim // num_heads
@@ -141,6 +146,7 @@ class Attention(nn.Module):
         self.current_timestep = 0
         self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=self.scale, pred_mode=mode,
                                         orthogonal_matrix=orthogonal_matrix)
+        self.core.anal = bool(anal) and bool(top_k)
 
     def forward(self, x):
         B, N, C = x.shape
@@ -169,8 +175,6 @@ class MXSelfAttention(nn.Module):
     def set_config(self, mx_quant=False, mx_specs=None, top_k=False, k=20, ex_pred=False, exclude_timesteps=None,
                    pred_mode="ex_pred", block_idx=None, anal=False, file_name_dict=None, orthogonal_matrix=None):
         mode = _require_hot_path(mx_quant, top_k, ex_pred, pred_mode, "MXSelfAttention.set_config")
-        if anal:
-            raise NotImplementedError("--anal analysis dumps are out of scope (SURVEY.md 8f4)")
         # self-attention: listed steps run dense (MX_transformer_block.py:656); cross-attention: listed steps rank
         # on the true scores instead of the predictor's (:806, else-branch :845-848)
         self.exclude_timesteps = set(exclude_timesteps or ())
@@ -181,6 +185,7 @@ class MXSelfAttention(nn.Module):
         # reference: scale_factor = 1 / math.sqrt(q.size(-1)) applied as an fp32 scalar (:647-653)
         self.core = PrunedAttentionCore(mx_specs, k if top_k else 0, scale=1.0 / (self.head_dim ** 0.5),
                                         pred_mode=mode, orthogonal_matrix=orthogonal_matrix)
+        self.core.anal = bool(anal) and bool(top_k)
         return self
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs):

@@ -690,3 +690,22 @@ def test_elsa_module_and_errors(mxq):
         mxq.predict_topk(q, q[:, :, :32], specs, 8, pred_mode="ELSA", orthogonal_matrix=P)
     with pytest.raises(ValueError):                      # matrix shape
         mxq.predict_topk(q, q, specs, 8, pred_mode="ELSA", orthogonal_matrix=P[:32])
+
+
+def test_anal_flag_reports_coverage(mxq, capsys):
+    """--anal (main.py:134-136): the shims print / keep "Average chosen k" = funcs/analysis.py total_chosen_k,
+    computed from the kept-key bitmask."""
+    from mx_quantization_b200.modules import Attention
+    specs = mx_specs(32, False)
+    torch.manual_seed(0)
+    x = torch.randn(2, 48, 128, device="cuda")
+    torch.manual_seed(1)
+    a = Attention(128, num_heads=2, qkv_bias=True, mx_quant=True, mx_specs=specs, top_k=True, k=12, ex_pred=True,
+                  anal=True).cuda()
+    y = a(x)
+    assert "Average chosen k:" in capsys.readouterr().out
+    qkv = a.qkv(x).reshape(2, 48, 3, 2, 64).permute(2, 0, 3, 1, 4)
+    _, mask = mxq.pruned_attention(qkv[0], qkv[1], qkv[2], specs, 12, return_mask=True)
+    idx = canonical_idx_from_mask(unpack_mask(mask, 48), 12)
+    want = np.mean([len(torch.unique(idx[b, h])) / 48 for b in range(2) for h in range(2)])   # total_chosen_k
+    assert abs(a.core.avg_chosen_k - want) < 1e-12 and y.shape == x.shape
