@@ -123,6 +123,49 @@ class QuantizedAttention(nn.Module):
         return x
 
 
+class QuantizedMlp(nn.Module):
+    """DeiT MLP with MX Linear layers - mirrors workloads/deit/scripts/main.py:159-196 (fc1 -> act -> fc2 -> drop;
+    the activation stays the host model's own module, as in the reference)."""
+
+    def __init__(self, orig_mlp, mx_specs=None):
+        super().__init__()
+        self.mx_specs = mx_specs
+        self.act = orig_mlp.act
+        self.drop = nn.Dropout(getattr(getattr(orig_mlp, "drop", None), "p", 0.0))
+        self.fc1, self.fc2 = to_mx_linear(orig_mlp.fc1, mx_specs), to_mx_linear(orig_mlp.fc2, mx_specs)
+
+    def forward(self, x):
+        return self.drop(self.fc2(self.act(self.fc1(x))))
+
+
+def apply_quantization_to_deit(model, config, mx_quant=True, top_k=True, k=20, approx_flag=True, pred_mode="ex_pred",
+                               anal=False, file_name_dict=None, exclude_blocks=(), exclude_block_type="ex_pred",
+                               orthogonal_matrix=None):
+    """Swap the attention / MLP modules of a timm-style DeiT (``model.blocks[i].attn`` / ``.mlp``) for the shims, with
+    the reference's block policy (workloads/deit/scripts/main.py:231-318): the last block (index 11 in the
+    reference; here ``len(model.blocks) - 1``) runs dense MXINT8 attention (top_k=False), blocks in
+    ``exclude_blocks`` use ``exclude_block_type`` as their pred_mode, every other listed block uses ``pred_mode``."""
+    block_indices = config.get('blocks', [])
+    components = config.get('components', ['attn', 'ffn'])
+    mx_specs = config.get('mx_specs')
+    if mx_specs is None:
+        raise ValueError("config['mx_specs'] is required (the reference's default dict lacks keys this path validates)")
+    last = len(model.blocks) - 1
+    for idx in block_indices:
+        if idx >= len(model.blocks):
+            continue
+        block = model.blocks[idx]
+        if 'attn' in components:
+            dense, excluded = idx == last, idx in exclude_blocks
+            block.attn = QuantizedAttention(
+                orig_attn=block.attn, mx_quant=mx_quant, mx_specs=mx_specs, top_k=top_k and not dense, k=k,
+                approx_flag=approx_flag, pred_mode=exclude_block_type if (dense or excluded) else pred_mode,
+                anal=anal, file_name_dict=file_name_dict, block_idx=idx, orthogonal_matrix=orthogonal_matrix)
+        if 'ffn' in components:
+            block.mlp = QuantizedMlp(orig_mlp=block.mlp, mx_specs=mx_specs)
+    return model
+
+
 class Attention(nn.Module):
     """DiT shim - constructor mirrors workloads/DiT/models.py:105-126."""
 

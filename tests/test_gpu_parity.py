@@ -709,3 +709,46 @@ def test_anal_flag_reports_coverage(mxq, capsys):
     idx = canonical_idx_from_mask(unpack_mask(mask, 48), 12)
     want = np.mean([len(torch.unique(idx[b, h])) / 48 for b in range(2) for h in range(2)])   # total_chosen_k
     assert abs(a.core.avg_chosen_k - want) < 1e-12 and y.shape == x.shape
+
+
+def test_apply_quantization_to_deit(mxq):
+    """The model-patching helper with the reference's block policy (workloads/deit/scripts/main.py:231-318) on a
+    timm-shaped toy model: last block dense, excluded blocks on another ranking, MLPs on MX Linear."""
+    import torch.nn as nn
+    from mx_quantization_b200.modules import (MxLinear, QuantizedAttention, QuantizedMlp, apply_quantization_to_deit)
+
+    class _Attn(nn.Module):
+        def __init__(self, dim, heads):
+            super().__init__()
+            self.num_heads, self.scale = heads, (dim // heads) ** -0.5
+            self.qkv, self.proj, self.proj_drop = nn.Linear(dim, 3 * dim), nn.Linear(dim, dim), nn.Dropout(0.0)
+
+    class _Mlp(nn.Module):
+        def __init__(self, dim):
+            super().__init__()
+            self.fc1, self.act, self.fc2, self.drop = nn.Linear(dim, 4 * dim), nn.GELU(), nn.Linear(4 * dim, dim), nn.Dropout(0.0)
+
+    class _Block(nn.Module):
+        def __init__(self, dim, heads):
+            super().__init__()
+            self.norm1, self.attn, self.norm2, self.mlp = nn.LayerNorm(dim), _Attn(dim, heads), nn.LayerNorm(dim), _Mlp(dim)
+
+        def forward(self, x):
+            x = x + self.attn(self.norm1(x))
+            return x + self.mlp(self.norm2(x))
+
+    torch.manual_seed(0)
+    model = nn.Module()
+    model.blocks = nn.ModuleList([_Block(128, 2) for _ in range(3)])
+    cfg = {"blocks": [0, 1, 2], "components": ["attn", "ffn"], "mx_specs": mx_specs(32, False)}
+    apply_quantization_to_deit(model, cfg, top_k=True, k=10, approx_flag=True, pred_mode="ex_pred",
+                               exclude_blocks=[1], exclude_block_type="partial_Q")
+    model.cuda()
+    assert all(isinstance(b.attn, QuantizedAttention) and isinstance(b.mlp, QuantizedMlp) for b in model.blocks)
+    assert isinstance(model.blocks[0].mlp.fc1, MxLinear)
+    assert [b.attn.core.pred_mode for b in model.blocks] == ["ex_pred", "partial_Q", "ex_pred"]
+    assert [b.attn.core.k for b in model.blocks] == [10, 10, 0]          # last block: every key kept
+    x = torch.randn(2, 50, 128, device="cuda")
+    for b in model.blocks:
+        x = b(x)
+    assert x.shape == (2, 50, 128) and bool(torch.isfinite(x).all())
