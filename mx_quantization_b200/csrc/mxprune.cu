@@ -619,17 +619,17 @@ static bool make_view_maps(const View& v, int B, int H, int N, int hd, CUtensorM
     return true;
 }
 
-template <int NC, bool CODES, bool BIASED>
+template <int NC, bool CODES, bool BIASED, int HG = 0>
 static int launch_predict_topk_tc_one(const PredParams& p, const K1cMaps& maps, const K1cSmem& L, size_t dyn,
                                       dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_tc<NC, CODES, BIASED>,
+        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_tc<NC, CODES, BIASED, HG>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    k_predict_topk_tc<NC, CODES, BIASED><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
+    k_predict_topk_tc<NC, CODES, BIASED, HG><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
     return check_launch("k_predict_topk_tc");
 }
 
@@ -674,7 +674,15 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
         case 1: MXP_TC(1); break;
         case 2: MXP_TC(2); break;
         case 4: MXP_TC(4); break;
-        case 7: MXP_TC(7); break;
+        case 7:
+            // 193 .. 224 keys: the two lanes of a row split the columns at 104 / 112 instead of 128 (no dummy chunk)
+            if (!biased && !codes && p.Nk > 192 && p.Nk <= 208)
+                *rc_out = launch_predict_topk_tc_one<7, false, false, 13>(p, maps, L, dyn, grid, st);
+            else if (!biased && !codes && p.Nk > 208)
+                *rc_out = launch_predict_topk_tc_one<7, false, false, 14>(p, maps, L, dyn, grid, st);
+            else
+                MXP_TC(7);
+            break;
         default: MXP_TC(8); break;
     }
 #undef MXP_TC

@@ -338,16 +338,33 @@ __device__ __forceinline__ void tmem_ld_16x32bx2_x16(uint32_t taddr, uint32_t (&
         : "r"(taddr), "n"(SPLIT));
 }
 
+template <int SPLIT>
+__device__ __forceinline__ void tmem_ld_16x32bx2_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr), "n"(SPLIT));
+}
+
 // NC = number of 32-key TMEM chunks a row's keys occupy (Nk <= 32 * NC); the MMA's N is 32 * NC.
 // BIASED: an additive key bias (cross-attention text mask) is present; compiled separately so that the
 // unbiased kernel carries none of its code.
-template <int NC, bool CODES, bool BIASED>
+// HG != 0: the two lanes of a row split the key columns at 8 HG instead of at a multiple of 32 - lane half 0 owns
+// columns [0, 8 HG), half 1 [8 HG, 16 HG) - so that a key count just above a multiple of 32 (DeiT's 197 -> 2 x 104)
+// does not cost a whole extra 32-key chunk of selection work per lane; the row mask is then written byte-wise
+// (8 HG is a byte boundary of the bitmask).  HG = 0: halves of NCH 32-key chunks, mask written in words.
+template <int NC, bool CODES, bool BIASED, int HG = 0>
 __global__ void __launch_bounds__(K1C_T, 2)
 k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring, const int G) {
     extern __shared__ __align__(1024) unsigned char smem_k1c[];     // 1024-byte aligned: SWIZZLE_128B boxes
     unsigned char* const smem = smem_k1c;
     constexpr int NMMA = 32 * NC;
     constexpr int NCH = (NC + 1) / 2;                               // key chunks per thread
+    constexpr int HW = HG ? 8 * HG : NCH * 32;                      // key columns per lane
+    constexpr int NPAIR = HW / 32, REM = HW - 32 * NPAIR;           // full 32-column chunks + an 8- or 16-column rest
+    constexpr int NWORDS = HW / 2;                                  // packed key words per lane
+    constexpr int NLW = (HW + 31) / 32;                             // bitmask words per lane (lane-local bit order)
+    static_assert(HG == 0 || (!BIASED && !CODES && (REM == 8 || REM == 16) && 16 * HG <= 32 * NC && NWORDS % 4 == 0),
+                  "tight split: unbiased kernel, rest of 8 or 16 columns");
     const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
     constexpr bool biased = BIASED;
     const K1cSmem L = k1c_smem_layout(hd, NC, ring, G, biased);
@@ -437,7 +454,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     const uint32_t idesc = umma_idesc_bf16_f32(128, NMMA);
     const int NW = (Nk + 31) >> 5;
     // padding key columns (index >= Nk, score exactly 0) among THIS thread's chunks [part NCH, part NCH + NCH)
-    const int my_cols_end = min(NC, (part + 1) * NCH) * 32, my_cols_beg = part * NCH * 32;
+    const int my_cols_end = HG ? (part + 1) * HW : min(NC, (part + 1) * NCH) * 32, my_cols_beg = part * HW;
     const int my_pad = max(0, my_cols_end - max(Nk, my_cols_beg));
     uint32_t ph_mma = 0;
     int slot_i = 0;
@@ -663,14 +680,15 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
         // [32 (part NCH + w), +32); word 16w + t = keys (base + t, base + 16 + t).  Padding columns
         // (key index >= Nk) score exactly 0 -> key0; they are discounted below.  A chunk past NC
         // (odd NC, upper half) holds zeros, which no candidate reaches.
-        uint32_t kw[NCH * 16];
+        uint32_t kw[NWORDS];
 #pragma unroll
-        for (int w = 0; w < NCH; ++w) {
-            const bool real = (w < NCH - 1) || (NC % 2 == 0) || part == 0;   // chunk index part * NCH + w < NC
+        for (int w = 0; w < NPAIR; ++w) {
+            // chunk index part * NCH + w < NC (always, with the tight split)
+            const bool real = HG != 0 || (w < NCH - 1) || (NC % 2 == 0) || part == 0;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t r[16];
-                tmem_ld_16x32bx2_x16<NCH * 32>(my_tmem + w * 32 + h * 16, r);
+                tmem_ld_16x32bx2_x16<HW>(my_tmem + w * 32 + h * 16, r);
                 tmem_ld_wait();
                 // r[t] = key column 16h + t of the chunk: low halves come from h = 0, high halves from h = 1
 #pragma unroll
@@ -680,6 +698,24 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                     else kw[16 * w + t] = real ? __byte_perm(kw[16 * w + t], f, 0x5410) : 0u;
                 }
             }
+        }
+        if constexpr (REM == 16) {                                  // word 16 NPAIR + t = keys (base + t, base + 8 + t)
+            uint32_t r[16];
+            tmem_ld_16x32bx2_x16<HW>(my_tmem + NPAIR * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                kw[16 * NPAIR + t] = __byte_perm(__float_as_uint(fmaf(__uint_as_float(r[t]), scl, cadd)),
+                                                 __float_as_uint(fmaf(__uint_as_float(r[t + 8]), scl, cadd)), 0x5410);
+        }
+        if constexpr (REM == 8) {                                   // word 16 NPAIR + t = keys (base + t, base + 4 + t)
+            uint32_t r[8];
+            tmem_ld_16x32bx2_x8<HW>(my_tmem + NPAIR * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                kw[16 * NPAIR + t] = __byte_perm(__float_as_uint(fmaf(__uint_as_float(r[t]), scl, cadd)),
+                                                 __float_as_uint(fmaf(__uint_as_float(r[t + 4]), scl, cadd)), 0x5410);
         }
         // every thread has its row parameters and its keys in registers: TMEM and the Q-side shared
         // memory may be reused by the next tile from here on (warps run the selection unsynchronised)
@@ -701,7 +737,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
 #pragma unroll 1
         for (int bit = wbits - 1; bit >= 0; --bit) {
             const uint32_t cand = (Tv | (1u << bit)) + K1_KEY_BIAS;
-            const int mine = count_ge_regs<NCH * 16>(kw, cand) - (key0 >= cand ? my_pad : 0);
+            const int mine = count_ge_regs<NWORDS>(kw, cand) - (key0 >= cand ? my_pad : 0);
             const int theirs = __shfl_xor_sync(FULL, mine, 16);
             if (mine + theirs >= kk) { Tv |= 1u << bit; nge_m = mine; nge_o = theirs; }
             else { ngt_m = mine; ngt_o = theirs; }
@@ -718,16 +754,27 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
             const __half2 t2 = u32_as_h2(T * 0x00010001u);
             const bool store = valid && fast;
 #pragma unroll
-            for (int w = 0; w < NCH; ++w) {
-                const int gw = part * NCH + w;
-                uint32_t gt = 0u, eq = 0u;
+            for (int w = 0; w < NLW; ++w) {
+                uint32_t gt = 0u, eq = 0u;                          // lane-local bit i <-> key column my_cols_beg + 32 w + i
+                if (w < NPAIR) {
 #pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    const __half2 kv = u32_as_h2(kw[16 * w + t]);
-                    gt |= __hgt2_mask(kv, t2) & (0x00010001u << t);
-                    eq |= __heq2_mask(kv, t2) & (0x00010001u << t);
+                    for (int t = 0; t < 16; ++t) {
+                        const __half2 kv = u32_as_h2(kw[16 * w + t]);
+                        gt |= __hgt2_mask(kv, t2) & (0x00010001u << t);
+                        eq |= __heq2_mask(kv, t2) & (0x00010001u << t);
+                    }
+                } else if constexpr (REM != 0) {                    // the rest: REM / 2 words of keys (t, REM / 2 + t)
+#pragma unroll
+                    for (int t = 0; t < REM / 2; ++t) {
+                        const __half2 kv = u32_as_h2(kw[16 * NPAIR + t]);
+                        gt |= __hgt2_mask(kv, t2) & (0x00010001u << t);
+                        eq |= __heq2_mask(kv, t2) & (0x00010001u << t);
+                    }
+                    // high halves sit at bit 16 + t: move them down to bit REM / 2 + t
+                    gt = (gt & 0xffffu) | ((gt >> 16) << (REM / 2));
+                    eq = (eq & 0xffffu) | ((eq >> 16) << (REM / 2));
                 }
-                const int nv = Nk - 32 * gw;                        // valid key columns in this chunk
+                const int nv = Nk - (my_cols_beg + 32 * w);         // valid key columns in this word
                 const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : (1u << nv) - 1u);
                 gt &= vm;
                 eq &= vm;
@@ -736,15 +783,25 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                 if (cnt > rem) take = keep_lowest_bits_fast(eq, rem);
                 rem -= min(cnt, rem);
                 const uint32_t word = gt | take;
-                if (store && gw < NW) {
-                    p.mask[row * NW + gw] = word;
-                    if (p.idx) {
-                        uint32_t w2 = word;
-                        while (w2) {
-                            const int bpos = __ffs(w2) - 1;
-                            w2 &= w2 - 1u;
-                            p.idx[row * kk + pos++] = gw * 32 + bpos;
-                        }
+                if (HG == 0) {
+                    const int gw = part * NCH + w;
+                    if (store && gw < NW) p.mask[row * NW + gw] = word;
+                } else if (store) {
+                    // 8 HG is a byte boundary of the row's bitmask: this lane owns bytes [part HG, part HG + HG);
+                    // the upper lane also clears what is left of the row's last words
+                    unsigned char* mrow = reinterpret_cast<unsigned char*>(p.mask + row * NW);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (4 * w + b < HG) mrow[part * HG + 4 * w + b] = (unsigned char)(word >> (8 * b));
+                    if (part == 1 && w == NLW - 1)
+                        for (int b = 2 * HG; b < 4 * NW; ++b) mrow[b] = 0;
+                }
+                if (store && p.idx) {
+                    uint32_t w2 = word;
+                    while (w2) {
+                        const int bpos = __ffs(w2) - 1;
+                        w2 &= w2 - 1u;
+                        p.idx[row * kk + pos++] = my_cols_beg + 32 * w + bpos;
                     }
                 }
             }

@@ -752,3 +752,25 @@ def test_apply_quantization_to_deit(mxq):
     for b in model.blocks:
         x = b(x)
     assert x.shape == (2, 50, 128) and bool(torch.isfinite(x).all())
+
+
+@pytest.mark.parametrize("Nk", [193, 197, 200, 207, 208, 209, 216, 223, 224])
+@pytest.mark.parametrize("kind,hd,bfloat", [("randn", 64, 32), ("edges", 72, 16), ("lognormal", 64, 32)])
+def test_tight_lane_split_key_counts(mxq, Nk, kind, hd, bfloat):
+    """193 .. 224 keys: the selection splits a row's key columns between its two lanes at 104 / 112 instead of 128
+    and writes the row mask byte-wise (k_predict_topk_tc<7, .., HG = 13 / 14>); masks, indices and outputs against
+    the oracle, square and rectangular, several k (ties included through the 'edges' rows)."""
+    for Nq, top_k in ((Nk, 30), (Nk, 1), (Nk, Nk - 1), (150, 77), (260, max(2, Nk // 2))):
+        q, k, v = make_qkv(2, 2, Nq, hd, seed=Nk + top_k, kind=kind if Nq == Nk else "randn", Nk=Nk)
+        specs = mx_specs(bfloat, False)
+        res = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k, return_idx=True)
+        ref = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, integer_scores=True)
+        want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], Nk), Nk)
+        assert torch.equal(unpack_mask(res["mask"], Nk), want), (Nq, top_k)
+        assert torch.equal(res["idx"].cpu().to(torch.int64), torch.sort(ref["idx"], dim=-1).values), (Nq, top_k)
+        # bits past Nk in the last mask word stay clear
+        last = res["mask"][..., -1].cpu().to(torch.int64) & 0xFFFFFFFF
+        assert int((last >> (Nk - 32 * ((Nk - 1) // 32))).max()) == 0 or Nk % 32 == 0
+    out, mask = mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), specs, top_k, return_mask=True)
+    assert torch.equal(mask, res["mask"])
+    assert_out_close(out.cpu(), ref, v, Nk, bfloat, OUT_TOL)
