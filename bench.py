@@ -344,6 +344,8 @@ def main():
         kernels = {}
         for kname, tot in kt.items():
             avg_ms = tot / reps
+            if avg_ms <= 0:
+                continue
             ach = bph[kname] * B * H / (avg_ms * 1e-3) / 1e9
             kernels[kname] = {"avg_ms": avg_ms, "achieved_gbs": ach, "frac": ach / peak,
                               "bytes_per_launch": bph[kname] * B * H}

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MXP_ABI_VERSION 2
+#define MXP_ABI_VERSION 3
 
 #define MXP_OK             0
 #define MXP_E_BADARG      -1   /* null pointer, bad shape/stride/alignment, k out of range */
@@ -279,6 +279,21 @@ int mxp_set_attention_path(int path);
  * Both return identical masks.  Process-wide; returns MXP_E_BADARG for any other value.
  */
 int mxp_set_predict_path(int path);
+
+/*
+ * The round-2 kernels behind mxp_pruned_attention (same results as the three-kernel path they replace):
+ *   1 (default)  exact attention whose cost follows top_k when top_k / Nk <= 0.35 (Nk <= 256, no key bias):
+ *                only the k gathered entries of a row are scaled, exponentiated and quantized, as in
+ *                workloads/deit/scripts/main.py:124,147-152; other shapes use the dense-epilogue kernel
+ *   0            always the dense-epilogue kernels (A/B aid)
+ * Process-wide; returns MXP_E_BADARG for any other value.
+ */
+int mxp_set_fused_path(int path);
+
+/* Debug aid: per-phase cycle accounting of the fused kernel.  device_buffer = 320 * 32 uint64 of device memory
+ * (zeroed by the caller), or NULL to switch the accounting off; the next fused launches add, per 256-thread group,
+ * the clock64() cycles its thread 0 spent in each phase (slot meanings: tools/fused_timing.py). */
+int mxp_debug_fused_timing(void* device_buffer);
 
 /* Number of kernel launches the last successful call on this thread enqueued (bench.py's
  * gpu_launches claim is counted from this). */

@@ -8,7 +8,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmxprune.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MXP_OK, MXP_E_BADARG, MXP_E_UNSUPPORTED, MXP_E_CUDA = 0, -1, -2, -3
 
@@ -20,6 +20,8 @@ _SIGNATURES = {
     "mxp_last_launch_count": (c_int, []),
     "mxp_set_attention_path": (c_int, [c_int]),
     "mxp_set_predict_path": (c_int, [c_int]),
+    "mxp_set_fused_path": (c_int, [c_int]),
+    "mxp_debug_fused_timing": (c_int, [c_void_p]),
     "mxp_limits": (None, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "mxp_quantize_mxint8": (c_int, _VIEW + [c_int] * 6 + [c_void_p] * 4),
     "mxp_exp_sign_approx": (c_int, _VIEW + [c_int] * 6 + [c_void_p] * 2),

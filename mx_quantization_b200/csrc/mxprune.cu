@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include "mxprune.h"
+#include "mxprune_host.cuh"
 #include "mxprune_device.cuh"
 #include "mxprune_predict.cuh"
 #include "mxprune_attend.cuh"
@@ -17,27 +18,6 @@
 using namespace mxp;
 
 namespace {
-
-// ------------------------------------------------------------------------------------
-// host-side error plumbing
-// ------------------------------------------------------------------------------------
-thread_local char g_err[512] = "";
-thread_local int g_launches = 0;
-
-int fail(int code, const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-int check_launch(const char* what) {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(MXP_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
-    ++g_launches;
-    return MXP_OK;
-}
 
 constexpr int MAX_HD = 128;
 constexpr int MAX_KEYS_FUSED = 256;   // keys held in registers, 8 per lane
@@ -491,7 +471,6 @@ int launch_attn_nb(const AttnCoreParams& p, dim3 grid, cudaStream_t st) {
     }
 }
 
-int g_attn_path = 0;     // 0 = tcgen05 tensor-core path (default), 1 = CUDA-core dp4a path
 thread_local cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 thread_local bool g_profile = false;
 inline void prof_mark(int i, cudaStream_t st) {
@@ -503,17 +482,12 @@ inline void prof_mark(int i, cudaStream_t st) {
 int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
     const K2Smem L = k2_smem_layout(O);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attend_pair<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_pair<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_pair<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_pair<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_umma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attend_umma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
+    MXP_ENSURE_DYN_SMEM((k_attend_pair<true, false>), 160 * 1024);
+    MXP_ENSURE_DYN_SMEM((k_attend_pair<false, false>), 160 * 1024);
+    MXP_ENSURE_DYN_SMEM((k_attend_pair<true, true>), 160 * 1024);
+    MXP_ENSURE_DYN_SMEM((k_attend_pair<false, true>), 160 * 1024);
+    MXP_ENSURE_DYN_SMEM((k_attend_umma<false, true>), 160 * 1024);
+    MXP_ENSURE_DYN_SMEM((k_attend_umma<false, false>), 160 * 1024);
     if (L.total > 160 * 1024) return fail(MXP_E_UNSUPPORTED, "attention operands need %zu bytes of shared memory", L.total);
     const int heads = p.B * p.H;
     int splits = (148 * 2 + heads - 1) / heads;
@@ -573,67 +547,15 @@ inline OpsBytes ops_bytes(int B, int H, int Nq, int Nk, int hd) {
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// ---- K1-TC: tensor maps over the strided (B,H,N,hd) fp32 views + launch ----------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            f = nullptr;
-        return (EncodeTiledFn)f;
-    }();
-    return fn;
-}
-
-// main map: dims {32 floats, N, hd/32, H, B}, box {32, 64, hd/32, 1, 1}, SWIZZLE_128B;
-// tail map (hd % 32 floats at column 32*(hd/32)): dims {tail, N, H, B}, box {tail, 64, 1, 1}.
-static bool make_view_maps(const View& v, int B, int H, int N, int hd, CUtensorMap* m_main, CUtensorMap* m_tail) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) return false;
-    const int nfull = hd >> 5, tail = hd & 31;
-    const cuuint64_t sN = (cuuint64_t)v.sN * 4, sH = (cuuint64_t)(H > 1 ? v.sH : hd) * 4,
-                     sB = (cuuint64_t)(B > 1 ? v.sB : (int64_t)N * v.sN) * 4;
-    if (!sN || !sH || !sB || (sN >> 40) || (sH >> 40) || (sB >> 40)) return false;
-    if (nfull) {
-        cuuint64_t dims[5] = {32, (cuuint64_t)N, (cuuint64_t)nfull, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[4] = {sN, 128, sH, sB};
-        cuuint32_t box[5] = {32, (cuuint32_t)K1C_ROWS, (cuuint32_t)nfull, 1, 1}, es[5] = {1, 1, 1, 1, 1};
-        if (enc(m_main, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)v.p, dims, strides, box, es,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return false;
-    }
-    if (tail) {
-        cuuint64_t dims[4] = {(cuuint64_t)tail, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {sN, sH, sB};
-        cuuint32_t box[4] = {(cuuint32_t)tail, (cuuint32_t)K1C_ROWS, 1, 1}, es[4] = {1, 1, 1, 1};
-        if (enc(m_tail, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(v.p + 32 * nfull), dims, strides, box, es,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return false;
-    }
-    return true;
-}
-
+// ---- K1-TC launch (tensor maps: make_view_maps, mxprune_predict_tc.cuh) ----------------------
 template <int NC, bool CODES, bool BIASED, int HG = 0>
 static int launch_predict_topk_tc_one(const PredParams& p, const K1cMaps& maps, const K1cSmem& L, size_t dyn,
                                       dim3 grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_tc<NC, CODES, BIASED, HG>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
+    MXP_ENSURE_DYN_SMEM((k_predict_topk_tc<NC, CODES, BIASED, HG>), 227 * 1024);
     k_predict_topk_tc<NC, CODES, BIASED, HG><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
     return check_launch("k_predict_topk_tc");
 }
 
-int g_predict_path = 0;  // 0 = tensor-core scoring (default where it applies), 1 = CUDA-core XOR/POPC kernel
 
 // returns 1 if the shape is outside the tensor-core kernel's domain (caller uses the CUDA-core kernel)
 static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out) {
@@ -693,13 +615,7 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
 template <int NC, bool TWO, bool ELSA>
 static int launch_predict_topk_wide_one(const PredParams& p, const K1cMaps& maps, const K1cSmem& L, size_t dyn,
                                         dim3 grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_predict_topk_wide<NC, TWO, ELSA>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
+    MXP_ENSURE_DYN_SMEM((k_predict_topk_wide<NC, TWO, ELSA>), 227 * 1024);
     k_predict_topk_wide<NC, TWO, ELSA><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
     return check_launch("k_predict_topk_wide");
 }
@@ -817,11 +733,9 @@ static int try_predict_topk_long_tc(const PredParams& p, cudaStream_t st, int* r
         if ((*rc_out = check_launch("k_quantize_ops"))) return 0;
     }
     {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(k_select_long_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (e != cudaSuccess) { *rc_out = fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 0; }
-            attr_set = true;
+        {
+            static std::atomic<uint64_t> done_{0};
+            if ((*rc_out = ensure_dyn_smem(k_select_long_tc, 227 * 1024, done_))) return 0;
         }
         LongSelParams sp{};
         sp.q_pp = w + W.q_pp; sp.k_pp = w + W.k_pp; sp.q_ep = (const int8_t*)(w + W.q_ep);
@@ -868,6 +782,15 @@ int mxp_set_attention_path(int path) {
 int mxp_set_predict_path(int path) {
     if (path != 0 && path != 1) return fail(MXP_E_BADARG, "predict path %d: 0 = tensor-core scoring, 1 = CUDA-core XOR/POPC", path);
     g_predict_path = path;
+    return MXP_OK;
+}
+int mxp_set_fused_path(int path) {
+    if (path != 0 && path != 1) return fail(MXP_E_BADARG, "fused path %d: 1 = fused / cost-follows-k kernels where they apply, 0 = off", path);
+    g_fused_path = path;
+    return MXP_OK;
+}
+int mxp_debug_fused_timing(void* device_buffer) {
+    fused_set_timing_buffer((unsigned long long*)device_buffer);
     return MXP_OK;
 }
 const char* mxp_last_error(void) { return g_err; }
@@ -1061,7 +984,10 @@ size_t mxp_pruned_attention_workspace_bytes(int B, int H, int Nq, int Nk, int hd
     const OpsBytes ob = ops_bytes(B, H, Nq, Nk, hd);
     const size_t ops = align256(ob.q) + align256(ob.k) + align256(ob.v);
     const size_t codes = align256(bh * Nq * hd) + align256(bh * Nq * nb) + align256(bh * Nk * hd) + align256(bh * Nk * nb);
-    return (ops > codes ? ops : codes) + align256(bh * Nq * nw * 4) + long_ws_layout(B, H, Nq, Nk, hd).total;
+    size_t base = (ops > codes ? ops : codes) + align256(bh * Nq * nw * 4);
+    const size_t fused = align256(fused_workspace_bytes(Nq, Nk, hd));      // operand slots of the fused kernel
+    if (base < fused) base = fused;
+    return base + long_ws_layout(B, H, Nq, Nk, hd).total;
 }
 
 static int pruned_attention_impl(const float* q, int64_t q_sB, int64_t q_sH, int64_t q_sN,
@@ -1107,6 +1033,22 @@ static int pruned_attention_impl(const float* q, int64_t q_sB, int64_t q_sH, int
     pp.elsa_proj = elsa_proj; pp.elsa_cap = elsa_cap;
     pp.long_ws = long_bytes ? w + need - long_bytes : nullptr;
     pp.long_ws_bytes = long_bytes;
+    if (tc && pred_mode == 0 && !key_bias) {
+        // one persistent launch for the whole path (mxprune_fused.cuh) where it applies
+        FusedArgs fa{};
+        fa.q = pp.q; fa.k = pp.k; fa.v = View{v, v_sB, v_sH, v_sN};
+        fa.B = B; fa.H = H; fa.Nq = Nq; fa.Nk = Nk; fa.hd = hd; fa.top_k = top_k;
+        fa.bf16 = bfloat_bits == 16; fa.flush = flush != 0; fa.scale = scale;
+        fa.out = out; fa.o_sB = o_sB; fa.o_sH = o_sH; fa.o_sN = o_sN;
+        fa.mask_out = mask_out;
+        fa.slots = w; fa.slots_bytes = need - long_bytes;
+        prof_mark(0, st);
+        if (fused_try(fa, st, &rc) == 0) {
+            prof_mark(1, st); prof_mark(2, st); prof_mark(3, st);
+            return rc;
+        }
+        rc = MXP_OK;
+    }
     if (tc) {
         unsigned char* q_op = w; w += align256(ob.q);
         unsigned char* k_op = w; w += align256(ob.k);
@@ -1123,7 +1065,9 @@ static int pruned_attention_impl(const float* q, int64_t q_sB, int64_t q_sH, int
         ap.scale = scale; ap.bf16 = bfloat_bits == 16; ap.flush = flush != 0;
         ap.out = out; ap.o_sB = o_sB; ap.o_sH = o_sH; ap.o_sN = o_sN;
         ap.key_bias = key_bias; ap.kb_sB = kb_sB;
-        rc = launch_attend_umma(ap, st);
+        int rc2 = MXP_OK;
+        if (attend_sparse_try(ap, top_k, st, &rc2) == 0) rc = rc2;      // cost follows top_k (small top_k / Nk)
+        else rc = launch_attend_umma(ap, st);
         prof_mark(3, st);
         return rc;
     }
@@ -1296,12 +1240,7 @@ int mxp_mx_linear(const float* x, int64_t ldx, int M, int K, const void* w_op, i
         k_round_bias<<<(N + 255) / 256, 256, 0, st>>>(bias, rbias, N, bfloat_bits == 16);
         if ((rc = check_launch("k_round_bias"))) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_mx_linear_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return fail(MXP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
+    MXP_ENSURE_DYN_SMEM(k_mx_linear_umma, 227 * 1024);
     LinearParams lp{};
     lp.a_op = a_op; lp.w_op = (const unsigned char*)w_op; lp.bias = bias ? rbias : nullptr;
     lp.out = out; lp.ldo = ldo; lp.M = M; lp.N = N; lp.K = K; lp.bf16 = bfloat_bits == 16; lp.stages = 4;

@@ -457,44 +457,73 @@ __host__ __device__ inline int k2p_tmem_cols(const OpsLayout& O) {
     return c;
 }
 
+// A 256-thread group of a CTA: its thread index, named barrier, shared-memory window, mbarriers, TMEM columns.
+// The exact-attention bodies below are GROUP functions: the stand-alone kernels run them as a whole CTA (barrier 0),
+// the fused kernel (mxprune_fused.cuh) as one of the two groups of a CTA.
+struct GroupCtx {
+    int tid;                            // 0..255 within the group
+    int bar_id;                         // named barrier of the group (0 when the group is the whole CTA)
+    unsigned char* smem;                // 1024-byte aligned window of the dynamic shared memory
+    uint64_t* bar_ld;                   // mbarriers (count 1), initialised by the caller; phases below
+    uint64_t* bar_s;
+    uint64_t* bar_o;
+    uint32_t tmem;                      // base of the group's TMEM columns
+    uint32_t ph_ld, ph_s, ph_o;
+    unsigned long long* prof;           // debug: per-phase cycle accumulators of the group's thread 0 (null = off)
+    long long t_last;
+};
+// debug phase accounting (mxp_debug_fused_timing): thread 0 of the group adds the cycles since its last mark to slot i
+#ifdef MXP_FUSED_TIMING
+#define MXP_PROF(gc, i)                                                     \
+    do {                                                                    \
+        if ((gc).prof != nullptr && (gc).tid == 0) {                        \
+            const long long now_ = clock64();                               \
+            (gc).prof[i] += (unsigned long long)(now_ - (gc).t_last);       \
+            (gc).t_last = now_;                                             \
+        }                                                                   \
+    } while (0)
+#else
+#define MXP_PROF(gc, i) do { } while (0)
+#endif
+__device__ __forceinline__ void group_sync(const GroupCtx& g) {
+    asm volatile("bar.sync %0, 256;" ::"r"(g.bar_id) : "memory");
+}
+
+// One head (query tiles tile_begin, tile_begin + tile_step, ...) through the dense-epilogue exact attention.
+// q_op / k_op / v_op: this head's MMA-ready operands; mask_head: its [Nq][NW] mask words; out_head: its output rows;
+// bias_b: the batch's additive key bias (BIAS only); s_bias: 256 floats of shared memory (BIAS only).
 template <bool BF16, bool BIAS>
-__global__ void __launch_bounds__(K2P_T, 2)
-k_attend_pair(const AttnParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar_ld, bar_s, bar_o;
-    __shared__ uint32_t tmem_base_s;
-    __shared__ float s_bias[BIAS ? 256 : 1];                        // PixArt cross-attention text mask (:794-803)
+__device__ __forceinline__ void attend_pair_head(GroupCtx& gc, const OpsLayout& O, int Nq, int Nk, int hd, float scale,
+                                                 bool flush, const unsigned char* q_op, const unsigned char* k_op,
+                                                 const unsigned char* v_op, const uint32_t* mask_head, float* out_head,
+                                                 int64_t o_sN, const float* bias_b, float* s_bias, int tile_begin,
+                                                 int tile_step) {
     constexpr bool bf16 = BF16;
-    const int Nk = p.Nk, Nq = p.Nq, hd = p.hd;
-    const OpsLayout O = ops_layout(Nq, Nk, hd);
     const K2Smem L = k2_smem_layout(O);
     const int hdp = O.hdp, NW = O.nw, kbr = O.kb_rows;
     const int NG = (NW + 3) >> 2;                                   // groups of four windows
+    unsigned char* const smem = gc.smem;
     unsigned char* sK = smem;
     unsigned char* sV = smem + L.off_v;
     unsigned char* sP = smem + L.off_p;
-    const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = gc.tid, warp = tid >> 5, lane = tid & 31;
     const int lane_base = 32 * (warp & 3) + 16 * (warp >> 2);
     const int rr = lane_base + (lane & 15);                         // row of the tile
     const int part = lane >> 4;                                     // which window pair of each group
-    const bool flush = p.flush;
-    const unsigned char* q_op = p.q_op + (size_t)head * O.q_head_bytes;
-    const unsigned char* k_op = p.k_op + (size_t)head * O.k_head_bytes;
-    const unsigned char* v_op = p.v_op + (size_t)head * O.v_head_bytes;
-    const uint32_t tcols = (uint32_t)k2p_tmem_cols(O);
-
-    if (tid == 0) { mbar_init(&bar_ld, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1); }
-    if (BIAS) s_bias[tid] = tid < Nk ? __ldg(p.key_bias + bb * p.kb_sB + tid) : 0.f;
-    if (warp == 0) tmem_alloc(&tmem_base_s, tcols);
-    tcgen05_fence_before_sync();
-    __syncthreads();
-    tcgen05_fence_after_sync();
-    const uint32_t tmem = tmem_base_s;
+    uint64_t& bar_ld = *gc.bar_ld;
+    uint64_t& bar_s = *gc.bar_s;
+    uint64_t& bar_o = *gc.bar_o;
+    uint32_t& ph_ld = gc.ph_ld;
+    uint32_t& ph_s = gc.ph_s;
+    uint32_t& ph_o = gc.ph_o;
+    if (BIAS) {
+        s_bias[tid] = tid < Nk ? __ldg(bias_b + tid) : 0.f;
+        group_sync(gc);
+    }
+    const uint32_t tmem = gc.tmem;
     const uint32_t my_tmem = tmem + ((uint32_t)lane_base << 16);
     const uint32_t idesc_s = umma_idesc_bf16_f32(128, kbr);
     const uint32_t idesc_o = umma_idesc_bf16_f32(128, hdp);
-    uint32_t ph_ld = 0, ph_s = 0, ph_o = 0;
 
     if (tid == 0) {                                                 // the head's K and V operands stay resident
         mbar_expect_tx(&bar_ld, (uint32_t)(O.k_blk_bytes + O.v_blk_bytes));
@@ -504,11 +533,10 @@ k_attend_pair(const AttnParams p) {
     mbar_wait(&bar_ld, ph_ld);
     ph_ld ^= 1u;
 
-    for (int tile = blockIdx.y; tile < O.q_tiles; tile += gridDim.y) {
+    for (int tile = tile_begin; tile < O.q_tiles; tile += tile_step) {
         const int i = tile * K2T + rr;
         const bool valid = i < Nq;
-        const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
-        const uint32_t* mrow = p.mask + row * NW;
+        const uint32_t* mrow = mask_head + (size_t)(valid ? i : 0) * NW;
 
         if (tid == 0) {                                             // Q tile (A operand) -> the P buffer region
             mbar_expect_tx(&bar_ld, (uint32_t)O.q_tile_bytes);
@@ -519,7 +547,7 @@ k_attend_pair(const AttnParams p) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int w = 4 * (t >> 1) + 2 * part + (t & 1);
-            mw[t] = (valid && w < NW) ? __ldg(mrow + w) : 0u;
+            mw[t] = (valid && w < NW) ? mrow[w] : 0u;
         }
         mbar_wait(&bar_ld, ph_ld);
         ph_ld ^= 1u;
@@ -553,7 +581,7 @@ k_attend_pair(const AttnParams p) {
                     for (int c = 0; c < 32; ++c) {
                         float s = __uint_as_float(ra[c]);
                         if (bf16) s = bf16_half_away(s);
-                        float tv = __fmul_rn(s, p.scale);
+                        float tv = __fmul_rn(s, scale);
                         if (BIAS) tv = __fadd_rn(tv, s_bias[kb0 + c]);
                         mb4[c & 3] = fmaxf(mb4[c & 3], ((m0 >> c) & 1u) ? tv : -INFINITY);
                         ra[c] = __float_as_uint(tv);
@@ -569,7 +597,7 @@ k_attend_pair(const AttnParams p) {
                     for (int c = 0; c < 32; ++c) {
                         float s = __uint_as_float(rb[c]);
                         if (bf16) s = bf16_half_away(s);
-                        float tv = __fmul_rn(s, p.scale);
+                        float tv = __fmul_rn(s, scale);
                         if (BIAS) tv = __fadd_rn(tv, s_bias[kb1 + c]);
                         mb4[c & 3] = fmaxf(mb4[c & 3], ((m1 >> c) & 1u) ? tv : -INFINITY);
                         rb[c] = __float_as_uint(tv);
@@ -675,7 +703,7 @@ k_attend_pair(const AttnParams p) {
             }
             fence_proxy_async_smem();
             tcgen05_fence_before_sync();
-            __syncthreads();
+            group_sync(gc);
             if (tid == 0) {
                 tcgen05_fence_after_sync();
                 for (int wl = 0; wl < 4; ++wl) {
@@ -700,7 +728,7 @@ k_attend_pair(const AttnParams p) {
         {
             const int io = tile * K2T + 32 * (warp & 3) + lane;
             const bool vo = io < Nq;
-            float* orow = p.out + bb * p.o_sB + hh * p.o_sH + (int64_t)(vo ? io : 0) * p.o_sN;
+            float* orow = out_head + (int64_t)(vo ? io : 0) * o_sN;
             const int half_cols = hdp >> 1;                         // multiple of 8
             const uint32_t ot = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
             for (int c0 = (warp >> 2) * half_cols; c0 < ((warp >> 2) + 1) * half_cols; c0 += 8) {
@@ -723,12 +751,37 @@ k_attend_pair(const AttnParams p) {
                 }
             }
         }
+        fence_proxy_async_smem();               // P writes (generic proxy) before the next TMA into the region
         tcgen05_fence_before_sync();
-        __syncthreads();                        // every lane has read O before TMEM / sP are reused
+        group_sync(gc);                          // every lane has read O before TMEM / sP are reused
         tcgen05_fence_after_sync();
     }
-    if (warp == 0) tmem_dealloc(tmem, tcols);
 }
+
+template <bool BF16, bool BIAS>
+__global__ void __launch_bounds__(K2P_T, 2)
+k_attend_pair(const AttnParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[3];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_bias[BIAS ? 256 : 1];                        // PixArt cross-attention text mask (:794-803)
+    const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
+    const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
+    const int tid = threadIdx.x;
+    const uint32_t tcols = (uint32_t)k2p_tmem_cols(O);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); }
+    if ((tid >> 5) == 0) tmem_alloc(&tmem_base_s, tcols);
+    tcgen05_fence_before_sync();
+    __syncthreads();
+    tcgen05_fence_after_sync();
+    GroupCtx g{tid, 0, smem, &bars[0], &bars[1], &bars[2], tmem_base_s, 0u, 0u, 0u, nullptr, 0};
+    attend_pair_head<BF16, BIAS>(g, O, p.Nq, p.Nk, p.hd, p.scale, p.flush != 0, p.q_op + (size_t)head * O.q_head_bytes,
+                                 p.k_op + (size_t)head * O.k_head_bytes, p.v_op + (size_t)head * O.v_head_bytes,
+                                 p.mask + (size_t)head * p.Nq * O.nw, p.out + bb * p.o_sB + hh * p.o_sH, p.o_sN,
+                                 BIAS ? p.key_bias + bb * p.kb_sB : nullptr, s_bias, (int)blockIdx.y, (int)gridDim.y);
+    if ((tid >> 5) == 0) tmem_dealloc(g.tmem, tcols);
+}
+
 
 // ------------------------------------------------------------------------------------------
 // V -> A1 -> MXINT8 along TOKENS (32-token windows per column) -> bf16 MMA-ready V^T operand.
@@ -741,7 +794,7 @@ struct VPrepParams {
     unsigned char* v_op;
 };
 
-__global__ void __launch_bounds__(K2T)
+static __global__ void __launch_bounds__(K2T)
 k_prep_v(const VPrepParams p) {
     const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
     const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
@@ -819,7 +872,7 @@ __device__ __forceinline__ uint4 dequant8_bf16(uint32_t lo, uint32_t hi, float w
 // Compact codes/exps -> MMA-ready operands (public mxp_sparse_attention entry, which receives
 // codes).  which = 0: query rows (tiles of 128), 1: key rows (key blocks).  Also zero-fills padding.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_codes_to_ops(const int8_t* __restrict__ codes, const int8_t* __restrict__ exps, unsigned char* __restrict__ ops,
                int heads, int Nq, int Nk, int hd, int which) {
     const OpsLayout O = ops_layout(Nq, Nk, hd);
@@ -842,5 +895,29 @@ k_codes_to_ops(const int8_t* __restrict__ codes, const int8_t* __restrict__ exps
         *reinterpret_cast<uint4*>(ops + head * head_bytes + off) = v;
     }
 }
+
+// ---- launchers defined in mxprune_fused.cu (second translation unit of libmxprune)
+// Exact attention with the cost following top_k (mxprune_attend_sparse.cuh).  Returns 1 when the shape is outside
+// that kernel's domain (the caller then launches the dense-epilogue kernel), else 0 with the launch status in *rc_out.
+// top_k: every row of the mask holds at most top_k kept keys (masks written by the selection kernels).
+int attend_sparse_try(const AttnParams& p, int top_k, cudaStream_t st, int* rc_out);
+
+// The fused kernel (mxprune_fused.cuh): the whole path q,k,v -> out as one persistent launch.  Returns 1 when the
+// call is outside its domain (the caller then runs the three-kernel path), else 0 with the launch status in *rc_out.
+struct FusedArgs {
+    View q, k, v;
+    int B, H, Nq, Nk, hd, top_k, bf16, flush;
+    float scale;
+    float* out;
+    int64_t o_sB, o_sH, o_sN;
+    uint32_t* mask_out;              // optional: where the caller wants the row masks
+    unsigned char* slots;            // workspace for the per-group operand slots (256-byte aligned)
+    size_t slots_bytes;
+};
+struct FusedSlotLayout { size_t k, v, mask, bytes; };
+FusedSlotLayout fused_slot_layout(int Nq, int Nk, int hd);
+size_t fused_workspace_bytes(int Nq, int Nk, int hd);
+int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out);
+void fused_set_timing_buffer(unsigned long long* buf);   // debug: [2 * 160][32] u64 device buffer, or null
 
 }  // namespace mxp

@@ -1,0 +1,119 @@
+// libmxprune, second translation unit: the kernels of round 2 (cost-follows-k attention epilogue, the fused
+// predictor + attention kernel) and their launchers.  Split from mxprune.cu so that the two halves compile in parallel.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mxprune.h"
+#include "mxprune_host.cuh"
+#include "mxprune_device.cuh"
+#include "mxprune_attend.cuh"
+#include "mxprune_attend_sparse.cuh"
+#include "mxprune_fused.cuh"
+
+namespace mxp {
+
+int attend_sparse_try(const AttnParams& p, int top_k, cudaStream_t st, int* rc_out) {
+    const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
+    // domain: one key block, no additive bias, a uniform row population of at most 35 % of the keys, and the row
+    // lists + operands of two CTAs resident per SM
+    if (g_fused_path.load() == 0 || !O.single || p.key_bias || top_k < 1 || top_k * 100 > 35 * p.Nk) return 1;
+    const K2sSmem L = k2s_smem_layout(O, top_k);
+    if (L.total > SMEM_2CTA) return 1;
+    auto run = [&]() -> int {
+        MXP_ENSURE_DYN_SMEM((k_attend_sparse<true>), 160 * 1024);
+        MXP_ENSURE_DYN_SMEM((k_attend_sparse<false>), 160 * 1024);
+        const int heads = p.B * p.H;
+        int splits = (148 * 2 + heads - 1) / heads;
+        if (splits > O.q_tiles) splits = O.q_tiles;
+        if (splits < 1) splits = 1;
+        dim3 grid((unsigned)heads, (unsigned)splits);
+        // residency bounded by the 512 TMEM columns of an SM (see launch_attend_umma)
+        const int max_ctas = 512 / k2p_tmem_cols(O);
+        size_t dyn = L.total;
+        const size_t floor_bytes = SMEM_PER_SM / (size_t)(max_ctas + 1) + 1024;
+        if (dyn < floor_bytes) dyn = floor_bytes;
+        if (p.bf16) k_attend_sparse<true><<<grid, K2P_T, dyn, st>>>(p, top_k);
+        else k_attend_sparse<false><<<grid, K2P_T, dyn, st>>>(p, top_k);
+        return check_launch("k_attend_sparse");
+    };
+    *rc_out = run();
+    return 0;
+}
+
+
+// ---- the fused kernel --------------------------------------------------------------------------------
+FusedSlotLayout fused_slot_layout(int Nq, int Nk, int hd) {
+    const OpsLayout O = ops_layout(Nq, Nk, hd);
+    auto a256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    FusedSlotLayout S;
+    S.k = a256(O.q_head_bytes);
+    S.v = S.k + a256(O.k_head_bytes);
+    S.mask = S.v + a256(O.v_head_bytes);
+    S.bytes = S.mask + a256((size_t)Nq * O.nw * 4);
+    return S;
+}
+
+size_t fused_workspace_bytes(int Nq, int Nk, int hd) {
+    if (Nk > 256 || hd < 32 || (hd & 7)) return 0;
+    return (size_t)2 * 160 * fused_slot_layout(Nq, Nk, hd).bytes;       // two groups per SM, up to 160 SMs
+}
+
+static std::atomic<unsigned long long*> g_fused_timing{nullptr};
+void fused_set_timing_buffer(unsigned long long* buf) { g_fused_timing = buf; }
+
+template <int NC, int HG>
+static int launch_fused_one(const FusedParams& p, const FusedMaps& maps, int grid, cudaStream_t st) {
+    const size_t dyn = 2 * FUSED_GROUP_SMEM;
+    if (p.bf16) {
+        MXP_ENSURE_DYN_SMEM((k_fused_pruned_attention<NC, HG, true>), (int)dyn);
+        k_fused_pruned_attention<NC, HG, true><<<grid, FUSED_T, dyn, st>>>(p, maps);
+    } else {
+        MXP_ENSURE_DYN_SMEM((k_fused_pruned_attention<NC, HG, false>), (int)dyn);
+        k_fused_pruned_attention<NC, HG, false><<<grid, FUSED_T, dyn, st>>>(p, maps);
+    }
+    return check_launch("k_fused_pruned_attention");
+}
+
+int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out) {
+    // domain: the exponent-sign predictor on the tensor-core paths, one key block of 129..256 keys, a real selection
+    // (top_k < Nk), no key bias, enough heads to give every group of half the chip one
+    if (g_fused_path.load() == 0 || g_attn_path.load() != 0 || g_predict_path.load() != 0) return 1;
+    if (a.Nk > 256 || a.Nk <= 128 || a.hd < 32 || (a.hd & 7) || a.top_k >= a.Nk) return 1;
+    const int heads = a.B * a.H;
+    if (heads < 64) return 1;
+    const int nc = a.Nk <= 224 ? 7 : 8;
+    const int nb = (a.hd + 31) / 32;
+    int G = nb <= 2 ? 2 : 1;
+    if (k1c_smem_layout(a.hd, nc, 2, G).total > FUSED_GROUP_SMEM - 256) G = 1;
+    int ring = K1C_MAXR;
+    while (ring > 2 && k1c_smem_layout(a.hd, nc, ring, G).total > FUSED_GROUP_SMEM - 256) --ring;
+    const K1cSmem L1 = k1c_smem_layout(a.hd, nc, ring, G);
+    if (L1.total > FUSED_GROUP_SMEM - 256) return 1;
+    const OpsLayout O = ops_layout(a.Nq, a.Nk, a.hd);
+    const bool sparse = a.top_k * 100 <= 35 * a.Nk && k2s_smem_layout(O, a.top_k).total <= FUSED_GROUP_SMEM - 256;
+    if (!sparse && k2_smem_layout(O).total > FUSED_GROUP_SMEM - 256) return 1;
+    const FusedSlotLayout S = fused_slot_layout(a.Nq, a.Nk, a.hd);
+    int grid = sm_count();
+    if (grid > 160) grid = 160;
+    if (grid > (heads + 1) / 2) grid = (heads + 1) / 2;
+    if (!a.slots || a.slots_bytes < (size_t)2 * grid * S.bytes) return 1;
+    FusedMaps maps;
+    if (!make_view_maps(a.q, a.B, a.H, a.Nq, a.hd, &maps.q_main, &maps.q_tail)) return 1;
+    if (!make_view_maps(a.k, a.B, a.H, a.Nk, a.hd, &maps.k_main, &maps.k_tail)) return 1;
+    if (!make_view_maps(a.v, a.B, a.H, a.Nk, a.hd, &maps.v_main, &maps.v_tail)) return 1;
+    FusedParams p{};
+    p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.hd = a.hd; p.top_k = a.top_k; p.bf16 = a.bf16; p.flush = a.flush;
+    p.scale = a.scale;
+    p.out = a.out; p.o_sB = a.o_sB; p.o_sH = a.o_sH; p.o_sN = a.o_sN;
+    p.mask_out = a.mask_out;
+    p.slots = a.slots; p.slot_bytes = S.bytes; p.slot_k = S.k; p.slot_v = S.v; p.slot_mask = S.mask;
+    p.ring = ring; p.G = G; p.sparse = sparse ? 1 : 0;
+    p.timing = g_fused_timing.load();
+    if (nc == 8) *rc_out = launch_fused_one<8, 0>(p, maps, grid, st);
+    else if (a.Nk > 192 && a.Nk <= 208) *rc_out = launch_fused_one<7, 13>(p, maps, grid, st);
+    else if (a.Nk > 208) *rc_out = launch_fused_one<7, 14>(p, maps, grid, st);
+    else *rc_out = launch_fused_one<7, 0>(p, maps, grid, st);
+    return 0;
+}
+
+}  // namespace mxp

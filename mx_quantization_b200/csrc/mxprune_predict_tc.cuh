@@ -37,6 +37,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cuda_runtime.h>
+
 #include "mxprune_predict.cuh"
 
 namespace mxp {
@@ -88,6 +90,53 @@ __host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring, int
 struct K1cMaps {
     CUtensorMap q_main, q_tail, k_main, k_tail;
 };
+
+// ---- K1-TC: tensor maps over the strided (B,H,N,hd) fp32 views + launch ----------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// main map: dims {32 floats, N, hd/32, H, B}, box {32, 64, hd/32, 1, 1}, SWIZZLE_128B;
+// tail map (hd % 32 floats at column 32*(hd/32)): dims {tail, N, H, B}, box {tail, 64, 1, 1}.
+inline bool make_view_maps(const View& v, int B, int H, int N, int hd, CUtensorMap* m_main, CUtensorMap* m_tail) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const int nfull = hd >> 5, tail = hd & 31;
+    const cuuint64_t sN = (cuuint64_t)v.sN * 4, sH = (cuuint64_t)(H > 1 ? v.sH : hd) * 4,
+                     sB = (cuuint64_t)(B > 1 ? v.sB : (int64_t)N * v.sN) * 4;
+    if (!sN || !sH || !sB || (sN >> 40) || (sH >> 40) || (sB >> 40)) return false;
+    if (nfull) {
+        cuuint64_t dims[5] = {32, (cuuint64_t)N, (cuuint64_t)nfull, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[4] = {sN, 128, sH, sB};
+        cuuint32_t box[5] = {32, (cuuint32_t)K1C_ROWS, (cuuint32_t)nfull, 1, 1}, es[5] = {1, 1, 1, 1, 1};
+        if (enc(m_main, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)v.p, dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    if (tail) {
+        cuuint64_t dims[4] = {(cuuint64_t)tail, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {sN, sH, sB};
+        cuuint32_t box[4] = {(cuuint32_t)tail, (cuuint32_t)K1C_ROWS, 1, 1}, es[4] = {1, 1, 1, 1};
+        if (enc(m_tail, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(v.p + 32 * nfull), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
 
 // ---- TMA tensor loads (tile mode), completion counted on an mbarrier
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4,
@@ -260,7 +309,7 @@ __device__ __forceinline__ uint32_t keep_lowest_bits_fast(uint32_t x, int m) {
 
 // Generic path (any exponents), warp-cooperative, one row: fp32 scores, same summation order as
 // predict_row_generic in mxprune_predict.cuh.  s_ksign / s_kexp: [b][256].
-__device__ __noinline__ void predict_row_generic_tc(uint32_t* __restrict__ mask_out, int32_t* __restrict__ idx_out,
+static __device__ __noinline__ void predict_row_generic_tc(uint32_t* __restrict__ mask_out, int32_t* __restrict__ idx_out,
                                                     int Nk, int kk, int hd, int nb, int64_t row, const uint32_t* sq,
                                                     const int* ep, const uint32_t* s_ksign,
                                                     const signed char* s_kexp, const float* kbias) {

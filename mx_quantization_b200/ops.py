@@ -71,6 +71,12 @@ def set_predict_path(path: str) -> None:
     _lib.check(_lib.load().mxp_set_predict_path(codes[path]), "mxp_set_predict_path")
 
 
+def set_fused_path(on: bool) -> None:
+    """True (default): the cost-follows-k attention kernel where it applies (top_k / Nk <= 0.35, Nk <= 256);
+    False: always the dense-epilogue kernels (A/B aid; results agree)."""
+    _lib.check(_lib.load().mxp_set_fused_path(1 if on else 0), "mxp_set_fused_path")
+
+
 def last_launch_count() -> int:
     return _lib.load().mxp_last_launch_count()
 

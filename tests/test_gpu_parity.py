@@ -129,6 +129,128 @@ def test_pruned_attention_end_to_end(mxq, B, H, N, hd, kind, bfloat, flush):
     assert torch.equal(buf.permute(0, 2, 1, 3), out)
 
 
+@pytest.mark.parametrize("ratio", [0.04, 0.15, 0.34])
+@pytest.mark.parametrize("B,H,N,hd,kind,bfloat,flush", SHAPES + [(2, 12, 197, 64, "randn", 32, False),
+                                                                 (2, 4, 256, 72, "lognormal", 16, True)])
+def test_pruned_attention_cost_follows_k(mxq, B, H, N, hd, kind, bfloat, flush, ratio):
+    """Small top_k / Nk: the exact stage runs on the compacted row lists (k_attend_sparse, cost ~ k) - same masks,
+    outputs within the same budget as the dense-epilogue kernel it replaces (workloads/deit/scripts/main.py:124,147-152:
+    only the k gathered entries are ever used)."""
+    top_k = max(1, int(ratio * N))
+    q, k, v = make_qkv(B, H, N, hd, seed=11, kind=kind)
+    specs = mx_specs(bfloat, flush)
+    qv, kv, vv = fused_qkv_views(q.cuda(), k.cuda(), v.cuda())
+    ref = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, flush=flush, integer_scores=True)
+    want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], N), N)
+    outs = {}
+    try:
+        for on in (True, False):
+            mxq.set_fused_path(on)
+            out, mask = mxq.pruned_attention(qv, kv, vv, specs, top_k, return_mask=True)
+            assert torch.equal(unpack_mask(mask, N), want)
+            # (top_k < 4: p sits at / next to a power of two in most rows - one-hot rows - so the allowance is the norm)
+            assert_out_close(out.cpu(), ref, v, N, bfloat, OUT_TOL,
+                             0.02 if (kind == "randn" and bfloat == 32 and top_k >= 4) else None)
+            outs[on] = out.cpu()
+    finally:
+        mxq.set_fused_path(True)
+    # the two epilogues differ only in the order of the row sum (a few ulps of p)
+    scale = float(ref["out"].abs().max())
+    assert float((outs[True] - outs[False]).abs().max()) <= 2 * OUT_TOL * scale
+
+
+FUSED_SHAPES = [  # B, H, N, hd, top_k, kind, bfloat, flush   (B * H >= 64: the domain of the fused kernel)
+    (8, 12, 197, 64, 30, "randn", 32, False),       # C2 slice: tight 104-column split, cost-follows-k epilogue
+    (6, 12, 197, 64, 80, "lognormal", 32, False),   # dense epilogue (k / N = 0.41)
+    (4, 16, 256, 72, 154, "randn", 16, False),      # C3 slice: bfloat 16, dense epilogue
+    (4, 16, 256, 72, 77, "lognormal", 32, True),    # C4 slice: flush
+    (4, 16, 256, 72, 26, "edges", 32, True),        # C5 ratio 0.1: sparse epilogue at head_dim 72, edge rows
+    (8, 8, 160, 64, 40, "edges", 32, False),        # NC = 7 without the tight split, generic rows
+    (8, 8, 220, 64, 50, "randn", 16, False),        # 112-column split
+    (8, 9, 130, 32, 13, "randn", 32, False),        # head_dim 32
+    (33, 2, 250, 72, 60, "lognormal", 16, False),   # odd head count: the last group of the last CTA idles
+]
+
+
+@pytest.mark.parametrize("B,H,N,hd,top_k,kind,bfloat,flush", FUSED_SHAPES)
+def test_fused_kernel(mxq, B, H, N, hd, top_k, kind, bfloat, flush):
+    """The whole path as ONE persistent launch (k_fused_pruned_attention): bit-exact masks, outputs within the
+    budget, against the oracle and against the three-kernel path it replaces (workloads/deit/scripts/main.py:101-152)."""
+    q, k, v = make_qkv(B, H, N, hd, seed=21, kind=kind)
+    specs = mx_specs(bfloat, flush)
+    qv, kv, vv = fused_qkv_views(q.cuda(), k.cuda(), v.cuda())
+    ref = O.pruned_attention(q, k, v, top_k, bfloat=bfloat, flush=flush, integer_scores=True)
+    want = O.mask_words_to_dense(O.idx_to_mask_words(ref["idx"], N), N)
+    outs, launches = {}, {}
+    try:
+        for on in (True, False):
+            mxq.set_fused_path(on)
+            out, mask = mxq.pruned_attention(qv, kv, vv, specs, top_k, return_mask=True)
+            launches[on] = mxq.last_launch_count()
+            assert torch.equal(unpack_mask(mask, N), want), f"fused={on}: masks differ from the oracle"
+            assert_out_close(out.cpu(), ref, v, N, bfloat, OUT_TOL, 0.02 if (kind == "randn" and bfloat == 32) else None)
+            outs[on] = out.cpu()
+            # without a mask output (the default call): the masks stay in the kernel's workspace slots
+            out2 = mxq.pruned_attention(qv, kv, vv, specs, top_k)
+            assert torch.equal(out2.cpu(), outs[on])
+    finally:
+        mxq.set_fused_path(True)
+    assert launches[True] == 1 and launches[False] == 3, launches
+    scale = float(ref["out"].abs().max())
+    assert float((outs[True] - outs[False]).abs().max()) <= 2 * OUT_TOL * scale
+
+
+def test_fused_kernel_full_c2_properties(mxq):
+    """DeiT-base layer at its full size (B=256, H=12, N=197, hd=64, k=30): the fused launch against the three-kernel
+    path on all 3072 heads - identical masks, every row keeps exactly k keys, outputs agree."""
+    B, H, N, hd, top_k = 256, 12, 197, 64, 30
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = torch.randn(B, N, 3, H, hd, device="cuda", generator=g).permute(2, 0, 3, 1, 4)
+    specs = mx_specs()
+    res = {}
+    try:
+        for on in (True, False):
+            mxq.set_fused_path(on)
+            res[on] = mxq.pruned_attention(qkv[0], qkv[1], qkv[2], specs, top_k, return_mask=True)
+    finally:
+        mxq.set_fused_path(True)
+    torch.cuda.synchronize()
+    assert torch.equal(res[True][1], res[False][1])
+    words = res[True][1].to(torch.int64) & 0xFFFFFFFF
+    pop = sum(((words >> b) & 1) for b in range(32)).sum(-1)
+    assert bool((pop == top_k).all())
+    # the two exact stages sum the row's exponentials in different orders: a p within an ulp of a rounding tie of the
+    # P quantizer lands on the other code in a handful of the 605 184 rows (one code step of one key, see
+    # helpers.out_error_budget); everything else agrees to the tolerance
+    scale = float(res[False][0].abs().max())
+    diff = (res[True][0] - res[False][0]).abs().amax(-1)
+    assert float((diff > 2 * OUT_TOL * scale).float().mean()) < 2e-4
+    assert float(diff.max()) <= 2.0 ** -6 * float(qkv[2].abs().max()) * 1.01
+    # determinism of the persistent schedule
+    again = mxq.pruned_attention(qkv[0], qkv[1], qkv[2], specs, top_k)
+    assert torch.equal(again, res[True][0])
+
+
+def test_two_devices_one_process(mxq):
+    """the library must be callable on several devices of one process (per-device shared-memory
+    opt-in, no process-global device state)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    specs = mx_specs()
+    outs = []
+    q, k, v = make_qkv(8, 12, 197, 64, seed=5)
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        for on in (True, False):
+            mxq.set_fused_path(on)
+            out, mask = mxq.pruned_attention(q.to(dev), k.to(dev), v.to(dev), specs, 30, return_mask=True)
+            outs.append((out.cpu(), mask.cpu()))
+    mxq.set_fused_path(True)
+    for o, m in outs[2:]:
+        assert torch.equal(m, outs[0][1])
+    assert torch.equal(outs[2][0], outs[0][0]) and torch.equal(outs[4][0], outs[0][0])
+    assert torch.equal(outs[3][0], outs[1][0]) and torch.equal(outs[5][0], outs[1][0])
+
+
 @pytest.mark.parametrize("name", ["deit_small", "dit_small", "dit_bf16", "pixart_flush", "deit_edges",
                                   "deit_tiny_c1"])
 def test_against_reference_golden(mxq, name):
