@@ -294,6 +294,8 @@ int mxp_set_fused_path(int path);
  * (zeroed by the caller), or NULL to switch the accounting off; the next fused launches add, per 256-thread group,
  * the clock64() cycles its thread 0 spent in each phase (slot meanings: tools/fused_timing.py). */
 int mxp_debug_fused_timing(void* device_buffer);
+/* Debug / A-B aid: 1 (default) = the two groups of a fused CTA take turns in phase 1 (quantize + select), 0 = unsynchronised. */
+int mxp_debug_fused_pingpong(int on);
 
 /* Number of kernel launches the last successful call on this thread enqueued (bench.py's
  * gpu_launches claim is counted from this). */

@@ -22,6 +22,7 @@ _SIGNATURES = {
     "mxp_set_predict_path": (c_int, [c_int]),
     "mxp_set_fused_path": (c_int, [c_int]),
     "mxp_debug_fused_timing": (c_int, [c_void_p]),
+    "mxp_debug_fused_pingpong": (c_int, [c_int]),
     "mxp_limits": (None, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "mxp_quantize_mxint8": (c_int, _VIEW + [c_int] * 6 + [c_void_p] * 4),
     "mxp_exp_sign_approx": (c_int, _VIEW + [c_int] * 6 + [c_void_p] * 2),

@@ -789,6 +789,10 @@ int mxp_set_fused_path(int path) {
     g_fused_path = path;
     return MXP_OK;
 }
+int mxp_debug_fused_pingpong(int on) {
+    fused_set_pingpong(on != 0);
+    return MXP_OK;
+}
 int mxp_debug_fused_timing(void* device_buffer) {
     fused_set_timing_buffer((unsigned long long*)device_buffer);
     return MXP_OK;

@@ -481,12 +481,56 @@ struct GroupCtx {
             (gc).prof[i] += (unsigned long long)(now_ - (gc).t_last);       \
             (gc).t_last = now_;                                             \
         }                                                                   \
+        __syncwarp(); /* tcgen05 .sync.aligned instructions need the warp converged again */ \
     } while (0)
 #else
 #define MXP_PROF(gc, i) do { } while (0)
 #endif
 __device__ __forceinline__ void group_sync(const GroupCtx& g) {
     asm volatile("bar.sync %0, 256;" ::"r"(g.bar_id) : "memory");
+}
+
+// O tile (TMEM lanes = query rows of the tile, columns [0, hdp)) -> A1 -> global memory.  Warp w reads the TMEM lanes of
+// quarter w & 3 and the column half w >> 2; 32 x 32 blocks are transposed through the warp's private 4 KiB of shared
+// memory (stage_base + 4096 w; conflict-free 16-byte chunks, chunk q of row l at position q ^ (l & 7)) so that 8 lanes
+// store 128 contiguous bytes of one output row: 4 full lines per store instruction instead of 32 partial ones.
+template <bool BF16>
+__device__ __forceinline__ void store_o_tile(uint32_t tmem, unsigned char* stage_base, int warp, int lane, int tile,
+                                             int Nq, int hd, int hdp, float* out_head, int64_t o_sN) {
+    const int half_cols = hdp >> 1;                                 // multiple of 8
+    const uint32_t ot = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    unsigned char* const stg = stage_base + warp * 4096;
+    const int row0 = tile * K2T + 32 * (warp & 3);
+    const int cbeg = (warp >> 2) * half_cols, cend = cbeg + half_cols;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        const int nc = min(32, cend - c0);                          // columns of this block (multiple of 8)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {                               // 8 columns at a time: few live registers
+            if (8 * h < nc) {
+                uint32_t r[8];
+                tmem_ld_32x32b_x8(ot + c0 + 8 * h, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    uint4 v = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+                    if (BF16) { v.x = bf16_half_away(v.x); v.y = bf16_half_away(v.y); v.z = bf16_half_away(v.z); v.w = bf16_half_away(v.w); }
+                    *reinterpret_cast<uint4*>(stg + lane * 128 + (((2 * h + q) ^ (lane & 7)) << 4)) = v;
+                }
+            }
+        }
+        __syncwarp();
+        const int ch = lane & 7;
+        const int col = c0 + 4 * ch;
+        if (4 * ch < nc && col < hd) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rl = (lane >> 3) + 4 * it;
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((ch ^ (rl & 7)) << 4));
+                if (row0 + rl < Nq) *reinterpret_cast<uint4*>(out_head + (int64_t)(row0 + rl) * o_sN + col) = v;
+            }
+        }
+        __syncwarp();
+    }
 }
 
 // One head (query tiles tile_begin, tile_begin + tile_step, ...) through the dense-epilogue exact attention.
@@ -724,33 +768,8 @@ __device__ __forceinline__ void attend_pair_head(GroupCtx& gc, const OpsLayout& 
         ph_o ^= 1u;
         tcgen05_fence_after_sync();
 
-        // ---- O -> A1 -> global: warp w reads TMEM lanes of quarter w & 3, column half w >> 2
-        {
-            const int io = tile * K2T + 32 * (warp & 3) + lane;
-            const bool vo = io < Nq;
-            float* orow = out_head + (int64_t)(vo ? io : 0) * o_sN;
-            const int half_cols = hdp >> 1;                         // multiple of 8
-            const uint32_t ot = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-            for (int c0 = (warp >> 2) * half_cols; c0 < ((warp >> 2) + 1) * half_cols; c0 += 8) {
-                uint32_t r[8];
-                tmem_ld_32x32b_x8(ot + c0, r);
-                tmem_ld_wait();
-                if (vo) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        if (c0 + q * 4 < hd) {
-                            float4 o = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
-                                                   __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
-                            if (bf16) {
-                                o.x = bf16_half_away(o.x); o.y = bf16_half_away(o.y);
-                                o.z = bf16_half_away(o.z); o.w = bf16_half_away(o.w);
-                            }
-                            *reinterpret_cast<float4*>(orow + c0 + q * 4) = o;
-                        }
-                    }
-                }
-            }
-        }
+        // ---- O -> A1 -> global (coalesced through the P region, which the finished MMAs no longer read)
+        store_o_tile<BF16>(tmem, sP, warp, lane, tile, Nq, hd, hdp, out_head, o_sN);
         fence_proxy_async_smem();               // P writes (generic proxy) before the next TMA into the region
         tcgen05_fence_before_sync();
         group_sync(gc);                          // every lane has read O before TMEM / sP are reused
@@ -918,6 +937,7 @@ struct FusedSlotLayout { size_t k, v, mask, bytes; };
 FusedSlotLayout fused_slot_layout(int Nq, int Nk, int hd);
 size_t fused_workspace_bytes(int Nq, int Nk, int hd);
 int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out);
+void fused_set_pingpong(int on);
 void fused_set_timing_buffer(unsigned long long* buf);   // debug: [2 * 160][32] u64 device buffer, or null
 
 }  // namespace mxp

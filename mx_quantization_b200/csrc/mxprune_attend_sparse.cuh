@@ -317,33 +317,8 @@ __device__ __forceinline__ void attend_sparse_head(GroupCtx& g, const OpsLayout&
         tcgen05_fence_after_sync();
         MXP_PROF(g, 18);
 
-        // ---- O -> A1 -> global: warp w reads TMEM lanes of quarter w & 3, column half w >> 2
-        {
-            const int io = tile * K2T + 32 * (warp & 3) + lane;
-            const bool vo = io < Nq;
-            float* orow = out_head + (int64_t)(vo ? io : 0) * o_sN;
-            const int half_cols = hdp >> 1;                         // multiple of 8
-            const uint32_t ot = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-            for (int c0 = (warp >> 2) * half_cols; c0 < ((warp >> 2) + 1) * half_cols; c0 += 8) {
-                uint32_t r[8];
-                tmem_ld_32x32b_x8(ot + c0, r);
-                tmem_ld_wait();
-                if (vo) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        if (c0 + q * 4 < hd) {
-                            float4 o = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
-                                                   __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
-                            if (bf16) {
-                                o.x = bf16_half_away(o.x); o.y = bf16_half_away(o.y);
-                                o.z = bf16_half_away(o.z); o.w = bf16_half_away(o.w);
-                            }
-                            *reinterpret_cast<float4*>(orow + c0 + q * 4) = o;
-                        }
-                    }
-                }
-            }
-        }
+        // ---- O -> A1 -> global (coalesced through the P region, which the finished MMAs no longer read)
+        store_o_tile<BF16>(tmem, sP, warp, lane, tile, Nq, hd, hdp, out_head, o_sN);
         MXP_PROF(g, 19);
         fence_proxy_async_smem();               // list / P writes (generic proxy) before the next tile's TMA overwrites them
         tcgen05_fence_before_sync();

@@ -59,6 +59,8 @@ size_t fused_workspace_bytes(int Nq, int Nk, int hd) {
 }
 
 static std::atomic<unsigned long long*> g_fused_timing{nullptr};
+static std::atomic<int> g_fused_pingpong{1};
+void fused_set_pingpong(int on) { g_fused_pingpong = on; }
 void fused_set_timing_buffer(unsigned long long* buf) { g_fused_timing = buf; }
 
 template <int NC, int HG>
@@ -109,6 +111,7 @@ int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out) {
     p.slots = a.slots; p.slot_bytes = S.bytes; p.slot_k = S.k; p.slot_v = S.v; p.slot_mask = S.mask;
     p.ring = ring; p.G = G; p.sparse = sparse ? 1 : 0;
     p.timing = g_fused_timing.load();
+    p.pingpong = g_fused_pingpong.load();
     if (nc == 8) *rc_out = launch_fused_one<8, 0>(p, maps, grid, st);
     else if (a.Nk > 192 && a.Nk <= 208) *rc_out = launch_fused_one<7, 13>(p, maps, grid, st);
     else if (a.Nk > 208) *rc_out = launch_fused_one<7, 14>(p, maps, grid, st);

@@ -38,6 +38,7 @@ struct FusedParams {
     size_t slot_bytes, slot_k, slot_v, slot_mask;    // byte offsets of the k / v operands and the mask inside a slot
     int ring, G;                 // TMA ring of phase 1
     int sparse;                  // phase 2: 1 = cost-follows-k epilogue, 0 = dense epilogue
+    int pingpong;                // 1: at most one group of a CTA inside phase 1 at a time (drives the groups into anti-phase)
     unsigned long long* timing;  // debug: [2 * gridDim][32] per-phase cycle sums of each group's thread 0 (null = off)
 };
 
@@ -372,6 +373,7 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
             const __half2 t2 = u32_as_h2(T * 0x00010001u);
             const bool store = valid && fast;
             uint32_t* mrow32 = mask_head + (size_t)(valid ? i : 0) * NW;
+            uint32_t lw[NLW];                                       // tight split: this lane's words, lane-local bit order
 #pragma unroll
             for (int w = 0; w < NLW; ++w) {
                 uint32_t gt = 0u, eq = 0u;                          // lane-local bit i <-> key column my_cols_beg + 32 w + i
@@ -404,13 +406,22 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
                 if (HG == 0) {
                     const int gw = part * NCH + w;
                     if (store && gw < NW) mrow32[gw] = word;
-                } else if (store) {
-                    unsigned char* mrow = reinterpret_cast<unsigned char*>(mrow32);
+                } else {
+                    lw[w] = word;
+                }
+            }
+            if constexpr (HG != 0) {                                // aligned word stores (see k_predict_topk_tc)
+                const uint32_t other0 = __shfl_xor_sync(FULL, lw[0], 16);
+                if (store) {
+                    if (part == 0) {
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (4 * w + b < HG) mrow[part * HG + 4 * w + b] = (unsigned char)(word >> (8 * b));
-                    if (part == 1 && w == NLW - 1)
-                        for (int b = 2 * HG; b < 4 * NW; ++b) mrow[b] = 0;
+                        for (int w = 0; w < NPAIR; ++w) mrow32[w] = lw[w];
+                        mrow32[NPAIR] = lw[NPAIR] | (other0 << REM);
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < NPAIR; ++w)
+                            if (NPAIR + 1 + w < NW) mrow32[NPAIR + 1 + w] = __funnelshift_l(lw[w], lw[w + 1], REM);
+                    }
                 }
             }
         }
@@ -437,26 +448,53 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
     st.ph_mma = ph_mma;
 }
 
+// The two phases of a head.  (Inlined: as separate functions the call ABI's callee-saved registers cost 0.5 - 1.2 KB
+// of spills per thread; inlined the kernel stays at the 128-register cap with a handful of spilled loop invariants.
+// Keep an eye on `-Xptxas -v`: spills next to in-flight tcgen05.ld results are not something to live with.)
+template <int NC, int HG>
+__device__ __forceinline__ void fused_phase1(GroupCtx& gc, K1State& st, uint64_t* bars, const FusedParams& p, const FusedMaps& maps,
+                                          int head, unsigned char* slot, uint32_t* mask_head) {
+    const K1cSmem L1 = k1c_smem_layout(p.hd, NC, p.ring, p.G);
+    const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
+    predict_topk_head<NC, HG>(gc, st, &bars[0], &bars[K1C_MAXR], p, maps, L1, O, head, slot, slot + p.slot_k, slot + p.slot_v,
+                              mask_head);
+}
+template <bool BF16>
+__device__ __forceinline__ void fused_phase2(GroupCtx& gc, const FusedParams& p, int head, const unsigned char* slot,
+                                          const uint32_t* mask_head) {
+    const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
+    const int bb = head / p.H, hh = head - bb * p.H;
+    float* out_head = p.out + bb * p.o_sB + hh * p.o_sH;
+    if (p.sparse) {
+        const K2sSmem L2 = k2s_smem_layout(O, p.top_k);
+        attend_sparse_head<BF16>(gc, O, L2, p.Nq, p.Nk, p.hd, p.scale, p.flush != 0, slot, slot + p.slot_k, slot + p.slot_v,
+                                 mask_head, out_head, p.o_sN, 0, 1);
+    } else {
+        attend_pair_head<BF16, false>(gc, O, p.Nq, p.Nk, p.hd, p.scale, p.flush != 0, slot, slot + p.slot_k, slot + p.slot_v,
+                                      mask_head, out_head, p.o_sN, nullptr, nullptr, 0, 1);
+    }
+}
+
 // NC, HG: key-column geometry of phase 1 (see k_predict_topk_tc); BF16: A1 rounding on (bfloat 16)
 template <int NC, int HG, bool BF16>
 __global__ void __launch_bounds__(FUSED_T, 1)
-k_fused_pruned_attention(const FusedParams p, const __grid_constant__ FusedMaps maps) {
+k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_constant__ FusedMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem_fused[];
     __shared__ uint64_t s_bars[2][K1C_MAXR + 4];                    // per group: ring, mma, ld, s, o
     __shared__ uint32_t s_tmem[2];
+    __shared__ int s_lock;                                          // phase-1 token of the CTA's two groups
     const int grp = threadIdx.x >> 8;
     const int tid = threadIdx.x & 255;
     uint64_t* bars = s_bars[grp];
-    const K1cSmem L1 = k1c_smem_layout(p.hd, NC, p.ring, p.G);
-    const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
-    const K2sSmem L2 = k2s_smem_layout(O, p.top_k);
     const int heads = p.B * p.H;
-    const int NW = O.nw;
+    const int NW = (p.Nk + 31) >> 5;
+    const bool has_tail = (p.hd & 31) != 0;
 
+    if (threadIdx.x == 0) s_lock = 0;
     if (tid == 0) {
         for (int r = 0; r < K1C_MAXR + 4; ++r) mbar_init(&bars[r], 1);
         prefetch_tmap(&maps.k_main); prefetch_tmap(&maps.q_main); prefetch_tmap(&maps.v_main);
-        if (L1.tail) { prefetch_tmap(&maps.k_tail); prefetch_tmap(&maps.q_tail); prefetch_tmap(&maps.v_tail); }
+        if (has_tail) { prefetch_tmap(&maps.k_tail); prefetch_tmap(&maps.q_tail); prefetch_tmap(&maps.v_tail); }
     }
     if ((threadIdx.x >> 5) == 0) tmem_alloc(&s_tmem[0], 512u);        // the SM's whole tensor memory: 256 columns per group
     tcgen05_fence_before_sync();
@@ -474,15 +512,17 @@ k_fused_pruned_attention(const FusedParams p, const __grid_constant__ FusedMaps 
     K1State st{0, 0u, 0u};
     const int gslot = 2 * (int)blockIdx.x + grp;
     unsigned char* const slot = p.slots + (size_t)gslot * p.slot_bytes;
-    unsigned char* const q_op = slot;
-    unsigned char* const k_op = slot + p.slot_k;
-    unsigned char* const v_op = slot + p.slot_v;
 
     for (int head = gslot; head < heads; head += 2 * (int)gridDim.x) {
-        const int bb = head / p.H, hh = head - bb * p.H;
         uint32_t* mask_head = p.mask_out ? p.mask_out + (size_t)head * p.Nq * NW
                                          : reinterpret_cast<uint32_t*>(slot + p.slot_mask);
-        predict_topk_head<NC, HG>(gc, st, &bars[0], &bars[K1C_MAXR], p, maps, L1, O, head, q_op, k_op, v_op, mask_head);
+        if (p.pingpong) {                                           // take the phase-1 token
+            if (tid == 0) {
+                while (atomicCAS(&s_lock, 0, 1) != 0) __nanosleep(64);
+            }
+            group_sync(gc);
+        }
+        fused_phase1<NC, HG>(gc, st, bars, p, maps, head, slot, mask_head);
         // phase 1 -> phase 2: the slot's operands (generic-proxy global stores) are read back by TMA bulk copies
         // (async proxy), the masks by ordinary loads of other threads of the group; phase 2 also re-purposes the
         // shared memory that phase 1 wrote with generic stores as TMA destinations
@@ -491,14 +531,9 @@ k_fused_pruned_attention(const FusedParams p, const __grid_constant__ FusedMaps 
         tcgen05_fence_before_sync();
         group_sync(gc);
         tcgen05_fence_after_sync();
+        if (p.pingpong && tid == 0) atomicExch(&s_lock, 0);         // every thread of the group has left phase 1
         MXP_PROF(gc, 21);
-        float* out_head = p.out + bb * p.o_sB + hh * p.o_sH;
-        if (p.sparse)
-            attend_sparse_head<BF16>(gc, O, L2, p.Nq, p.Nk, p.hd, p.scale, p.flush != 0, q_op, k_op, v_op, mask_head, out_head,
-                                     p.o_sN, 0, 1);
-        else
-            attend_pair_head<BF16, false>(gc, O, p.Nq, p.Nk, p.hd, p.scale, p.flush != 0, q_op, k_op, v_op, mask_head,
-                                          out_head, p.o_sN, nullptr, nullptr, 0, 1);
+        fused_phase2<BF16>(gc, p, head, slot, mask_head);
         // phase 2 ends with fence.proxy.async + group barrier: its shared memory and TMEM may be reused, and its TMA
         // reads of the slot have completed (every copy was waited for), so the next head may overwrite the slot
     }

@@ -802,6 +802,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
             int pos = part == 0 ? 0 : ngt0 + min(rem_all, ties0);   // kept keys below this thread's columns
             const __half2 t2 = u32_as_h2(T * 0x00010001u);
             const bool store = valid && fast;
+            uint32_t lw[NLW];                                       // tight split: this lane's words, lane-local bit order
 #pragma unroll
             for (int w = 0; w < NLW; ++w) {
                 uint32_t gt = 0u, eq = 0u;                          // lane-local bit i <-> key column my_cols_beg + 32 w + i
@@ -835,15 +836,8 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                 if (HG == 0) {
                     const int gw = part * NCH + w;
                     if (store && gw < NW) p.mask[row * NW + gw] = word;
-                } else if (store) {
-                    // 8 HG is a byte boundary of the row's bitmask: this lane owns bytes [part HG, part HG + HG);
-                    // the upper lane also clears what is left of the row's last words
-                    unsigned char* mrow = reinterpret_cast<unsigned char*>(p.mask + row * NW);
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (4 * w + b < HG) mrow[part * HG + 4 * w + b] = (unsigned char)(word >> (8 * b));
-                    if (part == 1 && w == NLW - 1)
-                        for (int b = 2 * HG; b < 4 * NW; ++b) mrow[b] = 0;
+                } else {
+                    lw[w] = word;
                 }
                 if (store && p.idx) {
                     uint32_t w2 = word;
@@ -851,6 +845,24 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
                         const int bpos = __ffs(w2) - 1;
                         w2 &= w2 - 1u;
                         p.idx[row * kk + pos++] = my_cols_beg + 32 * w + bpos;
+                    }
+                }
+            }
+            if constexpr (HG != 0) {
+                // tight split: the upper lane's bits start REM bits into global word NPAIR.  The lower lane stores
+                // words 0 .. NPAIR (the shared word completed with the partner's first bits), the upper lane the
+                // funnel-shifted rest - aligned 32-bit stores, 16 consecutive rows per instruction
+                const uint32_t other0 = __shfl_xor_sync(FULL, lw[0], 16);
+                if (store) {
+                    uint32_t* mrow = p.mask + row * NW;
+                    if (part == 0) {
+#pragma unroll
+                        for (int w = 0; w < NPAIR; ++w) mrow[w] = lw[w];
+                        mrow[NPAIR] = lw[NPAIR] | (other0 << REM);
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < NPAIR; ++w)
+                            if (NPAIR + 1 + w < NW) mrow[NPAIR + 1 + w] = __funnelshift_l(lw[w], lw[w + 1], REM);
                     }
                 }
             }
