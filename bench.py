@@ -11,8 +11,15 @@ L2, so no L2 flush is needed between iterations).  Prints ONE JSON line (rank 0)
 
 Default workload = BASELINE.json configs[1]: DeiT-base attention, batch 256 x 197 tokens,
 12 heads, head_dim 64, all 12 layers, k = 30 (workloads/deit/scripts/run_deit.sh:51).
-Multi-GPU: batch x heads shards across ranks with no data-path collective (weak scaling: every
-rank runs the full per-GPU workload); NCCL is used for the barrier and the max-over-ranks time.
+Multi-GPU (one process per GPU, torchrun): independent (batch, head) units, no data-path collective.
+  --scaling weak (default)  every rank runs its own full batch (seed per rank); value = all ranks' heads / max time
+  --scaling strong          ONE global batch (same seed everywhere) cut into contiguous batch slices
+                            (mx_quantization_b200.sharding); after the timed region the ranks all_gather per-entry
+                            digests of masks and outputs and rank 0 compares them with its own single-GPU run of
+                            the whole batch ("verification" in the JSON line)
+NCCL is used for the barrier, the max-over-ranks time and that verification gather only.
+roofline: the dominant kernel of the default call (the fused launch where it applies: algorithmic bytes 16 N hd
+per head) + full_path_frac of the whole step + the per-kernel view of the three-kernel path.
 """
 import argparse
 import json
@@ -138,10 +145,16 @@ def cpu_port_heads_per_s(w, budget_s=12.0, threads=None):
     return B * w["H"] / med, threads, f"B={B} slice of one layer ({B * w['H']} heads), median of {len(times)} reps"
 
 
-def config_dict(name, w, gpus):
+def config_dict(name, w, gpus, scaling="weak"):
+    if scaling == "strong":
+        par = (f"one global batch of {w['B']} split into contiguous batch slices over {gpus} GPU(s) "
+               "(mx_quantization_b200.sharding.take_shard), no data-path collective; digests all_gathered for verification")
+    else:
+        par = (f"{gpus} GPU(s), each running its own full batch of {w['B']} (weak scaling: independent (batch, head) "
+               "units, no data-path collective)")
     return {"workload": name, "batch": w["B"], "heads": w["H"], "tokens": w["N"], "head_dim": w["hd"],
             "top_k": w["top_k"], "layers": w["layers"], "mx_specs": f"int8/block32/bfloat{w['bfloat']}"
-            + ("/flush" if w["flush"] else ""), "parallelism": f"batch x heads sharded over {gpus} GPU(s), no collective",
+            + ("/flush" if w["flush"] else ""), "parallelism": par,
             "l2": "inputs (one q/k/v set per layer) exceed L2; no flush needed"}
 
 
@@ -181,6 +194,53 @@ def run_reference(args, name, w):
     }))
 
 
+def make_layers(torch, w, dev, seed, batch_slice=None):
+    """One fused qkv buffer per layer; q/k/v are the permuted views the attention modules produce
+    (workloads/deit/scripts/main.py:87-88).  batch_slice = (lo, hi): keep only that slice of the (seeded) global batch."""
+    B, H, N, hd, L = w["B"], w["H"], w["N"], w["hd"], w["layers"]
+    g = torch.Generator(device=dev).manual_seed(seed)
+    layers = []
+    for _ in range(L):
+        buf = torch.randn(B, N, 3, H, hd, device=dev, generator=g)
+        if batch_slice is not None:
+            buf = buf[batch_slice[0]:batch_slice[1]].clone()
+        qkv = buf.permute(2, 0, 3, 1, 4)
+        layers.append((qkv[0], qkv[1], qkv[2]))
+    return layers
+
+
+def time_steps(torch, step, steps, barrier):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1) / steps
+
+
+def kernel_breakdown(torch, mxq, layers, specs, top_k, out_view, reps):
+    """Per-kernel CUDA-event times of one call (mxp_pruned_attention_profile), averaged over layers x reps.
+    Default policy first (one fused launch where it applies), then the three-kernel path for the per-stage view."""
+    res = {}
+    for label, mode in (("default", 1), ("three_kernels", 0)):
+        acc, n = [0.0, 0.0, 0.0], 0
+        mxq.set_fused_path(mode)
+        try:
+            for it in range(1 + reps):                          # first pass untimed
+                for (q, k, v) in layers:
+                    ms3 = []
+                    mxq.pruned_attention(q, k, v, specs, top_k, out=out_view, _kernel_ms=ms3)
+                    if it:
+                        acc = [a + m for a, m in zip(acc, ms3)]
+                        n += 1
+            res[label] = ([a / n for a in acc], mxq.last_launch_count())
+        finally:
+            mxq.set_fused_path(1)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,8 +248,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="deit_base_c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank runs the full batch; strong: one global batch partitioned over the ranks, verified")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the device-timed lines of the other workload shapes")
     args = ap.parse_args()
     name, w = args.workload, WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -199,6 +262,7 @@ def main():
     import torch
     import torch.distributed as dist
     import mx_quantization_b200 as mxq
+    from mx_quantization_b200 import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
@@ -211,57 +275,41 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     specs = mx_specs(w["bfloat"], w["flush"])
     B, H, N, hd, L, top_k = w["B"], w["H"], w["N"], w["hd"], w["layers"], w["top_k"]
-    heads_per_step = B * H * L                      # per GPU (weak scaling)
-
-    # synthetic activations: one fused qkv buffer per layer, q/k/v are the permuted views the
-    # attention modules produce (workloads/deit/scripts/main.py:87-88)
-    g = torch.Generator(device=dev).manual_seed(1000 * rank)
-    layers = []
-    for _ in range(L):
-        buf = torch.randn(B, N, 3, H, hd, device=dev, generator=g)
-        qkv = buf.permute(2, 0, 3, 1, 4)
-        layers.append((qkv[0], qkv[1], qkv[2]))
-    out = torch.empty(B, N, H, hd, device=dev)      # (B,N,H,hd): the module's transpose(1,2) is free
-    out_view = out.permute(0, 2, 1, 3)
-
-    def step():
-        for (q, k, v) in layers:
-            mxq.pruned_attention(q, k, v, specs, top_k, out=out_view)
+    strong = args.scaling == "strong"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- inputs.  weak: every rank its own full batch (seed per rank).  strong: ONE global batch (same seed on every
+    # rank), each rank keeps its contiguous batch slice (sharding.shard_batch_heads / take_shard)
+    if strong:
+        kind, lo, hi = sharding.shard_batch_heads(B, H, world, rank)
+        if kind != "batch":
+            raise SystemExit("bench.py --scaling strong: batch < ranks is not a bench configuration")
+        layers = make_layers(torch, w, dev, 1234, (lo, hi))
+        Bl = hi - lo
+    else:
+        layers = make_layers(torch, w, dev, 1000 * rank)
+        Bl = B
+    heads_per_step_total = (B if strong else world * B) * H * L
+    out = torch.empty(Bl, N, H, hd, device=dev)     # (B,N,H,hd): the module's transpose(1,2) is free
+    out_view = out.permute(0, 2, 1, 3)
+
+    def step():
+        for (q, k, v) in layers:
+            mxq.pruned_attention(q, k, v, specs, top_k, out=out_view)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    W = max(args.warmup, 3)
+    for _ in range(W):
         step()
     launches_per_call = mxq.last_launch_count()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    # ---- per-kernel timing for the roofline: CUDA events around each kernel of the same call,
-    # recorded inside the library on the launching stream (mxp_pruned_attention_profile)
-    kt = {"predict_topk": 0.0, "prep_v": 0.0, "exact_attention": 0.0}
-    reps = 0
-    for it in range(1 + max(1, min(args.steps, 3))):        # first pass untimed
-        for (q, k, v) in layers:
-            ms3 = []
-            mxq.pruned_attention(q, k, v, specs, top_k, out=out_view, _kernel_ms=ms3)
-            if it == 0:
-                continue
-            kt["predict_topk"] += ms3[0]
-            kt["prep_v"] += ms3[1]
-            kt["exact_attention"] += ms3[2]
-            reps += 1
+    ms_per_step = time_steps(torch, step, args.steps, barrier)
+    kb = kernel_breakdown(torch, mxq, layers, specs, top_k, out_view, max(1, min(args.steps, 3))) if rank == 0 or world > 1 else None
     if rank == 0:
         # the timed region (a few tens of ms) can be shorter than one nvidia-smi period: keep the SAME
         # step loop running, untimed, until a few samples have been taken under that load
@@ -274,23 +322,50 @@ def main():
         clocks["note"] = ("sampled from warm-up to the end of an untimed continuation of the same step loop "
                           "(nvidia-smi period 50 ms; the timed region alone can be shorter than one period)")
     if world > 1:
-        t = torch.tensor([ms], device=dev)
+        t = torch.tensor([ms_per_step], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = world * heads_per_step / (ms_per_step * 1e-3)
+        ms_per_step = float(t.item())
+    value = heads_per_step_total / (ms_per_step * 1e-3)
+
+    # ---- strong scaling: cross-rank verification, outside every timed region.  Each rank digests the masks and the
+    # outputs of its slice of layer 0; the digests are all_gathered (NCCL over NVLink) and rank 0 compares them with
+    # its own single-GPU run of the WHOLE global batch
+    verification = None
+    if strong:
+        q, k, v = layers[0]
+        o_s, m_s = mxq.pruned_attention(q, k, v, specs, top_k, return_mask=True)
+        dig = torch.stack([m_s.to(torch.int64).reshape(Bl, -1).sum(1).double(),
+                           o_s.double().reshape(Bl, -1).sum(1), o_s.double().abs().reshape(Bl, -1).sum(1)], 1)
+        parts = sharding.gather_for_verification(dig, world)
+        if rank == 0:
+            full = make_layers(torch, dict(w, layers=1), dev, 1234)[0]
+            o_f, m_f = mxq.pruned_attention(full[0], full[1], full[2], specs, top_k, return_mask=True)
+            ref = torch.stack([m_f.to(torch.int64).reshape(B, -1).sum(1).double(),
+                               o_f.double().reshape(B, -1).sum(1), o_f.double().abs().reshape(B, -1).sum(1)], 1)
+            got = torch.cat(parts, 0)
+            verification = {"what": "per-batch-entry digests (mask word sums, output sums) of layer 0: all_gather of the "
+                                    f"{world} shards vs rank 0's single-GPU run of the whole batch",
+                            "batch_entries": int(got.shape[0]), "masks_equal": bool(torch.equal(got[:, 0], ref[:, 0])),
+                            "outputs_equal": bool(torch.equal(got[:, 1:], ref[:, 1:]))}
+            del full, o_f, m_f
+        del o_s, m_s
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing
     e2e = None
     if not args.no_e2e:
-        e2e_layers = min(L, 4)                      # bounded pinned footprint; per-layer cost is uniform
-        host_in = [torch.empty(B, N, 3, H, hd).pin_memory() for _ in range(e2e_layers)]
+        e2e_layers = L
+        try:
+            host_in = [torch.empty(Bl, N, 3, H, hd).pin_memory() for _ in range(e2e_layers)]
+            host_out = [torch.empty(Bl, N, H, hd).pin_memory() for _ in range(e2e_layers)]
+        except RuntimeError:                        # pinned-memory limit of the box: fall back to a third of the layers
+            e2e_layers = max(1, L // 3)
+            host_in = [torch.empty(Bl, N, 3, H, hd).pin_memory() for _ in range(e2e_layers)]
+            host_out = [torch.empty(Bl, N, H, hd).pin_memory() for _ in range(e2e_layers)]
         for hbuf in host_in:
             hbuf.normal_()
-        host_out = [torch.empty(B, N, H, hd).pin_memory() for _ in range(e2e_layers)]
         NBUF = 3                                    # device staging buffers: keeps the H2D engine busy back to back
-        dev_in = [torch.empty(B, N, 3, H, hd, device=dev) for _ in range(NBUF)]
-        dev_out = [torch.empty(B, N, H, hd, device=dev) for _ in range(NBUF)]
+        dev_in = [torch.empty(Bl, N, 3, H, hd, device=dev) for _ in range(NBUF)]
+        dev_out = [torch.empty(Bl, N, H, hd, device=dev) for _ in range(NBUF)]
         s_in, s_out, s_cmp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
         ev_in = [torch.cuda.Event() for _ in range(NBUF)]
         ev_cmp = [torch.cuda.Event() for _ in range(NBUF)]
@@ -317,56 +392,95 @@ def main():
             s_cmp.wait_stream(s_out)
 
         e2e_step()
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        n_e2e = max(1, min(args.steps, 3))
-        t0.record()
-        for _ in range(n_e2e):
-            e2e_step()
-        t1.record()
-        barrier()
-        ems = t0.elapsed_time(t1) / n_e2e
+        ems = time_steps(torch, e2e_step, max(1, min(args.steps, 3)), barrier)
         if world > 1:
             t = torch.tensor([ems], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         scale_l = L / e2e_layers                    # bytes/heads reported for the full L-layer step
-        e2e = {"value": world * B * H * e2e_layers / (ems * 1e-3), "unit": "heads/s",
-               "h2d_bytes_per_step": int(host_in[0].numel() * 4 * e2e_layers * scale_l),
-               "d2h_bytes_per_step": int(host_out[0].numel() * 4 * e2e_layers * scale_l),
-               "ms_per_step": ems * scale_l,
-               "note": f"timed on {e2e_layers} of {L} layers per step (uniform per-layer cost; pinned host "
-                       "buffers, H2D/compute/D2H triple-buffered on 3 streams), scaled to the full step"}
+        h2d, d2h = host_in[0].numel() * 4 * e2e_layers, host_out[0].numel() * 4 * e2e_layers
+        e2e = {"value": (B if strong else world * B) * H * e2e_layers / (ems * 1e-3), "unit": "heads/s",
+               "h2d_bytes_per_step": int(h2d * scale_l), "d2h_bytes_per_step": int(d2h * scale_l),
+               "ms_per_step": ems * scale_l, "h2d_gbs_per_rank": h2d / (ems * 1e-3) / 1e9,
+               "note": f"timed on {e2e_layers} of {L} layers per step, every layer from its own pinned host buffer "
+                       "(H2D / compute / D2H triple-buffered on 3 streams); bytes are per rank"}
+        del host_in, host_out, dev_in, dev_out
+
+    # ---- the other workload shapes, device-timed only (their own lines: --workload NAME)
+    others = None
+    if rank == 0 and world == 1 and not args.no_others and name == "deit_base_c2":
+        others = {}
+        del layers
+        torch.cuda.empty_cache()
+        for oname in ("dit_xl2_c3", "pixart_c4"):
+            ow = WORKLOADS[oname]
+            ol = make_layers(torch, ow, dev, 7)
+            oo = torch.empty(ow["B"], ow["N"], ow["H"], ow["hd"], device=dev).permute(0, 2, 1, 3)
+            osp = mx_specs(ow["bfloat"], ow["flush"])
+
+            def ostep():
+                for (q, k, v) in ol:
+                    mxq.pruned_attention(q, k, v, osp, ow["top_k"], out=oo)
+
+            for _ in range(3):
+                ostep()
+            oms = time_steps(torch, ostep, 3, barrier)
+            oh = ow["B"] * ow["H"] * ow["layers"]
+            ob = bytes_per_head(ow["N"], ow["hd"])
+            peak, _ = hbm_peak()
+            others[oname] = {"value": oh / (oms * 1e-3), "unit": "heads/s", "ms_per_step": oms,
+                             "full_path_gbs": ob["full"] * oh / (oms * 1e-3) / 1e9,
+                             "full_path_frac": ob["full"] * oh / (oms * 1e-3) / 1e9 / peak,
+                             "config": {k: ow[k] for k in ("B", "H", "N", "hd", "top_k", "layers", "bfloat", "flush")}}
+            del ol, oo
+            torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = hbm_peak()
         bph = bytes_per_head(N, hd)
+        heads_call = Bl * H                                     # heads one launch processes on this rank
+        (dms, dlaunch), (tms, tlaunch) = kb["default"], kb["three_kernels"]
+        full_gbs = bph["full"] * (heads_per_step_total / world) / (ms_per_step * 1e-3) / 1e9     # per GPU
         kernels = {}
-        for kname, tot in kt.items():
-            avg_ms = tot / reps
-            if avg_ms <= 0:
-                continue
-            ach = bph[kname] * B * H / (avg_ms * 1e-3) / 1e9
-            kernels[kname] = {"avg_ms": avg_ms, "achieved_gbs": ach, "frac": ach / peak,
-                              "bytes_per_launch": bph[kname] * B * H}
-        dom = max(kernels, key=lambda n: kernels[n]["avg_ms"])
-        traffic = None
+        for kname, avg_ms in zip(("predict_topk", "prep_v", "exact_attention"), tms):
+            ach = bph[kname] * heads_call / (avg_ms * 1e-3) / 1e9
+            kernels[kname] = {"avg_ms": avg_ms, "achieved_gbs": ach, "frac": ach / peak, "bytes_per_launch": bph[kname] * heads_call}
+        fused = dlaunch == 1
+        tj = {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(name, {}).get(dom)
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                    "kernels": kernels,
-                    "full_path_gbs": bph["full"] * heads_per_step / (ms_per_step * 1e-3) / 1e9}
+            tj = json.load(open(tpath)).get(name, {})
+        if fused:
+            # the dominant (only) kernel of the default path: k_fused_pruned_attention, q,k,v -> out in one launch;
+            # algorithmic bytes = SURVEY 8(d)'s full-path figure 16 N hd per head
+            ach = bph["full"] * heads_call / (dms[0] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "k_fused_pruned_attention", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": tj.get("fused"), "bytes_per_launch": bph["full"] * heads_call,
+                        "avg_ms": dms[0]}
+        else:
+            # three launches per call: SURVEY 8(d)'s metric kernel is the fused predictor + top-k (8 N hd + 4 N ceil(N/32))
+            roofline = {"bound": "hbm", "kernel": "predict_topk", "achieved": kernels["predict_topk"]["achieved_gbs"],
+                        "peak": peak, "unit": "GB/s", "frac": kernels["predict_topk"]["frac"], "traffic": tj.get("predict_topk"),
+                        "bytes_per_launch": kernels["predict_topk"]["bytes_per_launch"], "avg_ms": tms[0]}
+        roofline.update({"peak_source": peak_src, "full_path_gbs": full_gbs, "full_path_frac": full_gbs / peak,
+                         "three_kernel_path": {"note": "the same call with mxp_set_fused_path(0): per-kernel CUDA-event times "
+                                                       "against each kernel's bytes (predict_topk: SURVEY 8(d)'s 8 N hd + 4 N ceil(N/32); "
+                                                       "prep_v / exact_attention: the bytes those kernels move, operands included)",
+                                               "kernels": kernels, "ms_per_layer": sum(tms)},
+                         "launches_per_call": dlaunch})
         line = {
             "metric": "pruned-attention heads/s", "value": value, "unit": "heads/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
-            "data": "synthetic", "config": config_dict(name, w, world),
-            "tokens_per_s": world * B * N * L / (ms_per_step * 1e-3),
+            "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int8",
+            "data": "synthetic", "config": config_dict(name, w, world, args.scaling),
+            "tokens_per_s": value / H * N,
             "roofline": roofline, "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches_per_call * L * args.steps,
         }
+        if verification is not None:
+            line["verification"] = verification
+        if others:
+            line["other_workloads"] = others
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_port_heads_per_s(w)
             line["cpu_baseline"] = {"value": v, "unit": "heads/s", "cores": cores, "kind": "port", "sample": sample}

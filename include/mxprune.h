@@ -281,11 +281,15 @@ int mxp_set_attention_path(int path);
 int mxp_set_predict_path(int path);
 
 /*
- * The round-2 kernels behind mxp_pruned_attention (same results as the three-kernel path they replace):
- *   1 (default)  exact attention whose cost follows top_k when top_k / Nk <= 0.35 (Nk <= 256, no key bias):
- *                only the k gathered entries of a row are scaled, exponentiated and quantized, as in
- *                workloads/deit/scripts/main.py:124,147-152; other shapes use the dense-epilogue kernel
- *   0            always the dense-epilogue kernels (A/B aid)
+ * The round-2 kernels behind mxp_pruned_attention (same results as the three-kernel path they replace;
+ * workloads/deit/scripts/main.py:101-152 as one launch):
+ *   1 (default)  k_fused_pruned_attention - quantizer, predictor, top-k, V preparation and exact attention in ONE
+ *                persistent launch - when top_k / Nk <= 0.35 (129 <= Nk <= 256, >= 64 heads, no key bias), where the
+ *                exact stage runs on the k gathered entries only (main.py:124,147-152) and the launch is measured
+ *                faster than the three kernels; the cost-follows-k attention kernel alone for smaller problems;
+ *                everything else on the three-kernel path
+ *   2            the fused launch wherever the shape is in its domain, dense epilogue included (tests, A/B)
+ *   0            always the three-kernel path with the dense-epilogue attention kernels (A/B aid)
  * Process-wide; returns MXP_E_BADARG for any other value.
  */
 int mxp_set_fused_path(int path);

@@ -785,7 +785,8 @@ int mxp_set_predict_path(int path) {
     return MXP_OK;
 }
 int mxp_set_fused_path(int path) {
-    if (path != 0 && path != 1) return fail(MXP_E_BADARG, "fused path %d: 1 = fused / cost-follows-k kernels where they apply, 0 = off", path);
+    if (path < 0 || path > 2)
+        return fail(MXP_E_BADARG, "fused path %d: 0 = off, 1 = where measured faster (default), 2 = wherever in domain", path);
     g_fused_path = path;
     return MXP_OK;
 }

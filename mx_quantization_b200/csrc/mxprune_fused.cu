@@ -93,6 +93,10 @@ int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out) {
     if (L1.total > FUSED_GROUP_SMEM - 256) return 1;
     const OpsLayout O = ops_layout(a.Nq, a.Nk, a.hd);
     const bool sparse = a.top_k * 100 <= 35 * a.Nk && k2s_smem_layout(O, a.top_k).total <= FUSED_GROUP_SMEM - 256;
+    // measured on B200 (tools/ab_fused.py): with the cost-follows-k epilogue the fused launch beats the three kernels
+    // (DeiT-base layer 0.504 vs 0.521 ms); with the dense epilogue it does not (DiT-XL/2 1.01 vs 0.95 ms) - both phases
+    // are then issue-bound and gain nothing from sharing an SM.  Path 2 forces it (tests, A/B).
+    if (!sparse && g_fused_path.load() != 2) return 1;
     if (!sparse && k2_smem_layout(O).total > FUSED_GROUP_SMEM - 256) return 1;
     const FusedSlotLayout S = fused_slot_layout(a.Nq, a.Nk, a.hd);
     int grid = sm_count();
@@ -111,7 +115,7 @@ int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out) {
     p.slots = a.slots; p.slot_bytes = S.bytes; p.slot_k = S.k; p.slot_v = S.v; p.slot_mask = S.mask;
     p.ring = ring; p.G = G; p.sparse = sparse ? 1 : 0;
     p.timing = g_fused_timing.load();
-    p.pingpong = g_fused_pingpong.load();
+    p.pingpong = (g_fused_pingpong.load() && sparse) ? 1 : 0;   // the phase-1 token pays when phase 2 is the latency-bound one
     if (nc == 8) *rc_out = launch_fused_one<8, 0>(p, maps, grid, st);
     else if (a.Nk > 192 && a.Nk <= 208) *rc_out = launch_fused_one<7, 13>(p, maps, grid, st);
     else if (a.Nk > 208) *rc_out = launch_fused_one<7, 14>(p, maps, grid, st);

@@ -348,21 +348,10 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
         MXP_PROF(gc, 7);
 
         // ---- select: T = top_k-th largest key; the row's two lanes add their counts
-        int wbits = 32 - __clz(moff + 1);
-        wbits = __reduce_max_sync(FULL, wbits);
-        uint32_t Tv = 0u;
-        int nge_m = min(my_cols_end, max(Nk, my_cols_beg)) - my_cols_beg;
-        int nge_o = Nk - nge_m;
-        int ngt_m = 0, ngt_o = 0;
-#pragma unroll 1
-        for (int bit = wbits - 1; bit >= 0; --bit) {
-            const uint32_t cand = (Tv | (1u << bit)) + K1_KEY_BIAS;
-            const int mine = count_ge_regs<NWORDS>(kw, cand) - (key0 >= cand ? my_pad : 0);
-            const int theirs = __shfl_xor_sync(FULL, mine, 16);
-            if (mine + theirs >= kk) { Tv |= 1u << bit; nge_m = mine; nge_o = theirs; }
-            else { ngt_m = mine; ngt_o = theirs; }
-        }
-        const uint32_t T = Tv + K1_KEY_BIAS;
+        int nge_m, nge_o, ngt_m, ngt_o;
+        const int nvalid_m = min(my_cols_end, max(Nk, my_cols_beg)) - my_cols_beg;
+        const uint32_t T = select_kth_key<NWORDS, (HG == 0 && (NC & 1))>(kw, key0, my_pad, kk, nvalid_m, Nk - nvalid_m,
+                                                                       nge_m, nge_o, ngt_m, ngt_o);
         MXP_PROF(gc, 8);
 
         // ---- emit the row bitmask (ties: ascending key index; the lower lane owns the lower columns)

@@ -153,6 +153,9 @@ __device__ __forceinline__ void prefetch_row_l2(const float* row, int hd) {
 constexpr uint32_t K1_KEY_BIAS = 0x0400u;        // first normal fp16 bit pattern
 constexpr int K1_MAX_M = 0x7BFF - 0x0400 - 2;    // largest |S| bound that keeps biased keys finite fp16
 
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 x) {
+    return *reinterpret_cast<const uint32_t*>(&x);
+}
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t x) {
     return *reinterpret_cast<const __half2*>(&x);
 }

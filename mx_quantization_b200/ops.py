@@ -71,10 +71,11 @@ def set_predict_path(path: str) -> None:
     _lib.check(_lib.load().mxp_set_predict_path(codes[path]), "mxp_set_predict_path")
 
 
-def set_fused_path(on: bool) -> None:
-    """True (default): the cost-follows-k attention kernel where it applies (top_k / Nk <= 0.35, Nk <= 256);
-    False: always the dense-epilogue kernels (A/B aid; results agree)."""
-    _lib.check(_lib.load().mxp_set_fused_path(1 if on else 0), "mxp_set_fused_path")
+def set_fused_path(mode) -> None:
+    """True / 1 (default): the fused one-launch kernel and the cost-follows-k attention kernel where they are measured
+    faster (top_k / Nk <= 0.35, Nk <= 256); 2: the fused launch wherever the shape is in its domain; False / 0: always the
+    three-kernel path with the dense-epilogue kernels.  Results agree (A/B aid)."""
+    _lib.check(_lib.load().mxp_set_fused_path(int(mode)), "mxp_set_fused_path")
 
 
 def last_launch_count() -> int:

@@ -184,7 +184,7 @@ def test_fused_kernel(mxq, B, H, N, hd, top_k, kind, bfloat, flush):
     outs, launches = {}, {}
     try:
         for on in (True, False):
-            mxq.set_fused_path(on)
+            mxq.set_fused_path(2 if on else 0)          # 2: also where the default policy prefers the three kernels
             out, mask = mxq.pruned_attention(qv, kv, vv, specs, top_k, return_mask=True)
             launches[on] = mxq.last_launch_count()
             assert torch.equal(unpack_mask(mask, N), want), f"fused={on}: masks differ from the oracle"

@@ -13,7 +13,7 @@ import json, glob
 for f in sorted(glob.glob("gpurun_out/bench_${TAG}_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
-        ks = d.get("roofline", {}).get("kernels", {})
+        ks = d.get("roofline", {}).get("three_kernel_path", {}).get("kernels", {})
         print(f.split("/")[-1], d.get("impl", "ours"), int(d["value"]), d["unit"], "ms/step", round(d["ms_per_step"], 3),
               "e2e", d.get("e2e") and int(d["e2e"]["value"]), "cpu", d.get("cpu_baseline") and round(d["cpu_baseline"]["value"], 1),
               {k: (round(v["avg_ms"], 3), round(v["frac"], 3)) for k, v in ks.items()}, d.get("clocks"))
