@@ -82,6 +82,55 @@ k_quantize(View x, int rows_per_bh, int H, int64_t total_rows, int hd, int bf16,
 }
 
 // ------------------------------------------------------------------------------------
+// K0b: the stand-alone quantizer proper (codes / exps / sign words): ONE THREAD PER MX BLOCK with the F2I-free block
+// arithmetic of the fused kernels (quantize_block_thread, mxprune_predict_tc.cuh).  Consecutive threads take
+// consecutive blocks of a row, so a warp reads 4 KB of contiguous fp32 with eight independent 128-bit loads per
+// thread and writes 1 KB of contiguous codes.  Replaces the reference's quantize_mx_innermost / _by_tile CUDA
+// kernels (microxscaling/mx/cpp/mx.cuh:57-158) on this path: tools/bench_quant.py times them side by side.
+// ------------------------------------------------------------------------------------
+template <bool SIGNS>
+__global__ void __launch_bounds__(256)
+k_quantize_blocks(View x, int rows_per_bh, int H, int64_t total_rows, int hd, int nb, int bf16, int flush,
+                  int8_t* __restrict__ codes, int8_t* __restrict__ exps, uint32_t* __restrict__ signs) {
+    const int64_t total = total_rows * nb;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / nb;
+        const int b = (int)(t - row * nb);
+        const int64_t bh = row / rows_per_bh;
+        const int n = (int)(row - bh * rows_per_bh);
+        const float* src = x.p + (bh / H) * x.sB + (bh % H) * x.sH + (int64_t)n * x.sN + 32 * b;
+        const int nd = min(32, hd - 32 * b);
+        uint32_t xv[32];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (4 * s < nd) v = __ldg(reinterpret_cast<const uint4*>(src) + s);
+            xv[4 * s] = v.x; xv[4 * s + 1] = v.y; xv[4 * s + 2] = v.z; xv[4 * s + 3] = v.w;
+        }
+        BlockQ r;
+        quantize_block_thread<true, false>(xv, nd, bf16 != 0, flush != 0, r);
+        exps[row * nb + b] = (int8_t)r.e;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(codes + row * hd + 32 * b);
+        if ((hd & 15) == 0) {
+            reinterpret_cast<uint4*>(dst)[0] = make_uint4(r.cw[0], r.cw[1], r.cw[2], r.cw[3]);
+            reinterpret_cast<uint4*>(dst)[1] = make_uint4(r.cw[4], r.cw[5], r.cw[6], r.cw[7]);
+        } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+                if (4 * v < nd) dst[v] = r.cw[v];
+        }
+        if (SIGNS) {
+            // sign word in natural element order: bit d = (code d < 0); four code bytes -> four bits per multiply
+            uint32_t sw = 0u;
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+                sw |= (((((r.cw[v] >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * v);
+            signs[row * nb + b] = sw;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Predictor parameters
 // ------------------------------------------------------------------------------------
 // Quantize the Nk key rows of one head into shared memory: sign words + 2^e weights.
@@ -818,11 +867,19 @@ static int quantize_common(const float* x, int64_t sB, int64_t sH, int64_t sN, i
     if (blocks > 148 * 16) blocks = 148 * 16;
     View v{x, sB, sH, sN};
     cudaStream_t st = (cudaStream_t)stream;
-    if (approx)
+    if (approx) {
         k_quantize<true><<<(unsigned)blocks, THREADS, 0, st>>>(v, N, H, rows, hd, bfloat_bits == 16, flush != 0, nullptr, nullptr, nullptr, approx);
+        return check_launch("k_quantize");
+    }
+    const int nb = (hd + 31) / 32;
+    int64_t qblocks = (rows * nb + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    if (qblocks > cap) qblocks = cap;
+    if (signs)
+        k_quantize_blocks<true><<<(unsigned)qblocks, 256, 0, st>>>(v, N, H, rows, hd, nb, bfloat_bits == 16, flush != 0, codes, exps, signs);
     else
-        k_quantize<false><<<(unsigned)blocks, THREADS, 0, st>>>(v, N, H, rows, hd, bfloat_bits == 16, flush != 0, codes, exps, signs, nullptr);
-    return check_launch("k_quantize");
+        k_quantize_blocks<false><<<(unsigned)qblocks, 256, 0, st>>>(v, N, H, rows, hd, nb, bfloat_bits == 16, flush != 0, codes, exps, signs);
+    return check_launch("k_quantize_blocks");
 }
 
 int mxp_quantize_mxint8(const float* x, int64_t sB, int64_t sH, int64_t sN, int B, int H, int N,

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .specs import resolve_specs
+from .specs import resolve_linear_specs, resolve_specs
 
 
 class PrunedAttentionCore(nn.Module):
@@ -140,23 +140,23 @@ class QuantizedMlp(nn.Module):
 
 def apply_quantization_to_deit(model, config, mx_quant=True, top_k=True, k=20, approx_flag=True, pred_mode="ex_pred",
                                anal=False, file_name_dict=None, exclude_blocks=(), exclude_block_type="ex_pred",
-                               orthogonal_matrix=None):
+                               orthogonal_matrix=None, dense_blocks=(11,)):
     """Swap the attention / MLP modules of a timm-style DeiT (``model.blocks[i].attn`` / ``.mlp``) for the shims, with
-    the reference's block policy (workloads/deit/scripts/main.py:231-318): the last block (index 11 in the
-    reference; here ``len(model.blocks) - 1``) runs dense MXINT8 attention (top_k=False), blocks in
+    the reference's block policy (workloads/deit/scripts/main.py:231-318): the blocks in ``dense_blocks`` - index 11, as
+    the reference hard-codes it (:266,:281,:296) - run dense MXINT8 attention (top_k=False), blocks in
     ``exclude_blocks`` use ``exclude_block_type`` as their pred_mode, every other listed block uses ``pred_mode``."""
     block_indices = config.get('blocks', [])
     components = config.get('components', ['attn', 'ffn'])
     mx_specs = config.get('mx_specs')
     if mx_specs is None:
         raise ValueError("config['mx_specs'] is required (the reference's default dict lacks keys this path validates)")
-    last = len(model.blocks) - 1
+    dense_blocks = set(dense_blocks)
     for idx in block_indices:
         if idx >= len(model.blocks):
             continue
         block = model.blocks[idx]
         if 'attn' in components:
-            dense, excluded = idx == last, idx in exclude_blocks
+            dense, excluded = idx in dense_blocks, idx in exclude_blocks
             block.attn = QuantizedAttention(
                 orig_attn=block.attn, mx_quant=mx_quant, mx_specs=mx_specs, top_k=top_k and not dense, k=k,
                 approx_flag=approx_flag, pred_mode=exclude_block_type if (dense or excluded) else pred_mode,
@@ -275,13 +275,23 @@ class MxLinear(nn.Linear):
 
     def __init__(self, in_features, out_features, bias=True, mx_specs=None, name=None):
         super().__init__(in_features, out_features, bias)
-        resolve_specs(mx_specs)
+        resolve_linear_specs(mx_specs)          # also w_elem_format / round_weight / round (mx/linear.py:36-75)
         self.mx_specs = mx_specs
         self.name = name
         self._w_op = None
         self._w_key = None
+        # a loaded checkpoint writes the weight through .data (no version bump): drop the cached operand
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.invalidate())
+
+    def invalidate(self):
+        """Drop the cached MX-quantized weight operand (call after writing the weight through ``.data``)."""
+        self._w_op = None
+        self._w_key = None
 
     def forward(self, inputs):
+        if torch.is_grad_enabled() and (self.weight.requires_grad or inputs.requires_grad):
+            raise RuntimeError("MxLinear is the inference forward of mx.Linear (the reference's backward is out of scope): "
+                               "call it under torch.no_grad() / inference_mode, or freeze the parameters")
         key = (self.weight.data_ptr(), self.weight._version, str(self.weight.device))
         if self._w_op is None or self._w_key != key:
             self._w_op = ops.mx_linear_prepare_weight(self.weight.detach(), self.mx_specs)

@@ -9,7 +9,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from .specs import resolve_specs
+from .specs import resolve_linear_specs, resolve_specs
 
 
 def _stream() -> c_void_p:
@@ -273,17 +273,25 @@ def sparse_attention(q_codes, q_exps, k_codes, k_exps, v: torch.Tensor, mask: to
     lib = _lib.load()
     v = _view4(v, "v")
     B, H, Nk, hd = v.shape
+    if q_codes.dim() != 4:
+        raise ValueError(f"q_codes: expected a 4-D (B,H,Nq,head_dim) tensor, got shape {tuple(q_codes.shape)}")
     Nq = q_codes.shape[2]
+    nb, nw = (hd + 31) // 32, (Nk + 31) // 32
     dev = _same_device(v, q_codes, q_exps, k_codes, k_exps, mask)
-    for name, t, dt in (("q_codes", q_codes, torch.int8), ("q_exps", q_exps, torch.int8),
-                        ("k_codes", k_codes, torch.int8), ("k_exps", k_exps, torch.int8),
-                        ("mask", mask, torch.int32)):
+    for name, t, dt, shape in (("q_codes", q_codes, torch.int8, (B, H, Nq, hd)), ("q_exps", q_exps, torch.int8, (B, H, Nq, nb)),
+                               ("k_codes", k_codes, torch.int8, (B, H, Nk, hd)), ("k_exps", k_exps, torch.int8, (B, H, Nk, nb)),
+                               ("mask", mask, torch.int32, (B, H, Nq, nw))):
         if t.dtype != dt or not t.is_contiguous():
             raise ValueError(f"{name}: expected a contiguous {dt} tensor")
+        if tuple(t.shape) != shape:
+            raise ValueError(f"{name}: expected shape {shape} (from v {tuple(v.shape)}), got {tuple(t.shape)}")
     scale = float(hd) ** -0.5 if scale is None else float(scale)
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((B, H, Nq, hd), dtype=torch.float32, device=dev)
+        elif (tuple(out.shape) != (B, H, Nq, hd) or out.dtype != torch.float32 or out.stride(-1) != 1
+              or out.device != dev):
+            raise ValueError("out must be an fp32 (B,H,Nq,head_dim) view with innermost stride 1 on the inputs' device")
         ws_bytes = lib.mxp_sparse_attention_workspace_bytes(B, H, Nq, Nk, hd)
         ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
         rc = lib.mxp_sparse_attention(_ptr(q_codes), _ptr(q_exps), _ptr(k_codes), _ptr(k_exps),
@@ -366,7 +374,7 @@ def pruned_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mx_specs
 # ---- MX Linear -------------------------------------------------------------------
 def mx_linear_prepare_weight(weight: torch.Tensor, mx_specs) -> torch.Tensor:
     """MX-quantize an (out_features, in_features) fp32 weight once into the GEMM's operand order."""
-    sp = resolve_specs(mx_specs)
+    sp = resolve_linear_specs(mx_specs)
     lib = _lib.load()
     if weight.dim() != 2 or weight.dtype != torch.float32 or not weight.is_cuda:
         raise ValueError("weight must be a CUDA fp32 (out_features, in_features) tensor")
@@ -385,7 +393,7 @@ def mx_linear(x: torch.Tensor, weight, bias: Optional[torch.Tensor], mx_specs,
     """Forward of the reference's mx.Linear (microxscaling/mx/linear.py:20-103) for MXINT8:
     y = A1(A1(MXq(A1(x)) @ MXq(A1(W))^T) + A1(bias)).  ``weight`` is either the fp32 (N,K) tensor or
     the operand returned by mx_linear_prepare_weight (then pass out_features)."""
-    sp = resolve_specs(mx_specs)
+    sp = resolve_linear_specs(mx_specs)
     lib = _lib.load()
     if x.dtype != torch.float32 or not x.is_cuda:
         raise ValueError("x must be a CUDA fp32 tensor")
@@ -398,11 +406,15 @@ def mx_linear(x: torch.Tensor, weight, bias: Optional[torch.Tensor], mx_specs,
         if out_features is None:
             raise ValueError("out_features is required with a prepared weight operand")
         w_op, N = weight, int(out_features)
+        if not w_op.is_contiguous() or w_op.numel() != lib.mxp_mx_linear_weight_bytes(N, K):
+            raise ValueError(f"prepared weight operand: expected {lib.mxp_mx_linear_weight_bytes(N, K)} contiguous bytes for "
+                             f"out_features={N}, in_features={K}, got {w_op.numel()}")
     else:
         N = weight.shape[0]
         w_op = mx_linear_prepare_weight(weight, mx_specs)
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("bias must be a contiguous fp32 tensor with out_features elements")
+    _same_device(x, w_op, bias)
     with torch.cuda.device(x.device):
         out = torch.empty((M, N), dtype=torch.float32, device=x.device)
         ws_bytes = lib.mxp_mx_linear_workspace_bytes(M, N, K)

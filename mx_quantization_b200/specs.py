@@ -19,7 +19,7 @@ _DEFAULTS = {   # microxscaling/mx/specs.py:81-120
     "scale_bits": 0, "a_elem_format": None, "w_elem_format": None, "shared_exp_method": "max",
     "block_size": 0, "bfloat": 0, "fp": 0, "bfloat_subnorms": True, "round": "nearest",
     "round_output": "nearest", "round_mx_output": "nearest", "mx_flush_fp32_subnorms": False,
-    "custom_cuda": False,
+    "custom_cuda": False, "round_weight": "nearest",
 }
 
 
@@ -49,3 +49,17 @@ def resolve_specs(mx_specs) -> PathSpecs:
     # custom_cuda selected the reference's own CUDA quantizer; results are identical, so it is
     # accepted and ignored.
     return PathSpecs(16 if bfloat == 16 else 32, flush)
+
+
+def resolve_linear_specs(mx_specs) -> PathSpecs:
+    """mx.Linear additionally quantizes the WEIGHT with ``w_elem_format`` / ``round_weight`` and rounds with ``round``
+    (microxscaling/mx/linear.py:36-75): only MXINT8 weights with round-to-nearest are on the path.  ``w_elem_format=None``
+    leaves the weight unquantised in the reference and int4 / fp8 give other values - those raise here instead of
+    silently running the MXINT8 kernel."""
+    sp = resolve_specs(mx_specs)
+    get = lambda k: mx_specs[k] if k in mx_specs and mx_specs[k] is not None else _DEFAULTS[k]  # noqa: E731
+    for key, allowed in (("w_elem_format", ("int8",)), ("round_weight", ("nearest",)), ("round", ("nearest",))):
+        v = get(key)
+        if v not in allowed:
+            raise ValueError(f"mx_specs[{key!r}]={v!r} is not on the B200 MX Linear path (supported: {allowed})")
+    return sp

@@ -127,3 +127,20 @@ def assert_out_close(out, ref, v, n_keys, bfloat=32, out_tol=1e-3, max_relaxed_f
     if max_relaxed_frac is not None:     # well-conditioned inputs: almost no row may need the allowance
         assert frac_relaxed <= max_relaxed_frac, f"{frac_relaxed:.1%} of rows needed the code-step allowance"
     return float(err.max()), frac_relaxed
+
+
+def mode_window_ok(qc, qe, kc, ke, hd, mode, bits=20):
+    """Rows of the other rankings (partial_Q / partial_K / MXINT4 / two_step / true_ex / exact) whose EVERY (query, key)
+    pair keeps all its block terms inside ``bits`` bits: there the tensor core's fp32 accumulation and the reference's
+    BLAS agree in any order (footnote 1), so the selected sets are pinned.  Operand widths: an MXINT8 side
+    adds 7 bits below its block exponent, MXINT4 3, the exponent-sign / leading-one sides none; a block sum adds
+    ceil(log2(width)) + 1."""
+    import math
+    side = {"partial_Q": (7, 0), "partial_K": (0, 7), "MXINT4": (3, 3), "two_step_leading_ones": (7, 7), "true_ex": (7, 7),
+            "exact": (7, 7), "ex_pred": (0, 0)}[mode]
+    eq = O.predictor_exponents(qc, qe).to(torch.int64)
+    ek = O.predictor_exponents(kc, ke).to(torch.int64)
+    s = eq[..., :, None, :] + ek[..., None, :, :]                      # [..., Nq, Nk, nb]
+    widths = torch.tensor([math.ceil(math.log2(w)) + 1 for w in O.block_widths(hd)])
+    spread = (s + widths).amax(-1) - s.amin(-1) + side[0] + side[1]
+    return (spread <= bits).all(-1)

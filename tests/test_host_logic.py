@@ -1,0 +1,83 @@
+"""CPU tests of the host-side logic that needs no GPU: the dense arithmetic of the predictor class (fed with the
+oracle's codes in place of the CUDA quantizer's), the --anal figures, and the spec resolvers - against fixtures
+generated from the unmodified reference (tests/golden/make_golden_methods.py, make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mxint8_oracle as O
+from mx_quantization_b200 import analysis
+from mx_quantization_b200.predictor import _clz32, exponent_approximation
+from mx_quantization_b200.specs import PathSpecs, resolve_linear_specs, resolve_specs
+from tests.helpers import mx_specs
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _cpu_predictor(q, k, bfloat, flush):
+    """The class without its constructor's device plumbing: codes / exponents from the oracle quantizer."""
+    obj = object.__new__(exponent_approximation)
+    obj._sp = PathSpecs(bfloat, flush)
+    obj.mx_specs = mx_specs(bfloat, flush)
+    obj.Q, obj.K = q, k
+    qc, qe = O.quantize_mxint8(q, 32, bfloat, flush)
+    kc, ke = O.quantize_mxint8(k, 32, bfloat, flush)
+    obj._q, obj._k = (qc, qe, O.sign_words(qc)), (kc, ke, O.sign_words(kc))
+    return obj
+
+
+@pytest.mark.parametrize("name", ["predictor_methods_deit", "predictor_methods_dit_bf16", "predictor_methods_pixart"])
+def test_predictor_class_dense_math(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    B, H, N, hd, _, bfloat, flush = (int(x) for x in z["meta"])
+    q, k = torch.from_numpy(z["q"]), torch.from_numpy(z["k"])
+    obj = _cpu_predictor(q, k, bfloat, bool(flush))
+    for method in ("partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "exponent_based_sign_leading_ones"):
+        aq, ak = getattr(obj, method)()
+        assert torch.equal(aq, torch.from_numpy(z[method + ".Q"])), method
+        assert torch.equal(ak, torch.from_numpy(z[method + ".K"])), method
+    # the exponent-sign operand (the GPU method goes through mxp_exp_sign_approx; here its dense restatement)
+    (qc, qe, _), (kc, ke, _) = obj._q, obj._k
+    assert torch.equal(obj._exp_sign(qc, qe), torch.from_numpy(z["exponent_based_sign.Q"]))
+    assert torch.equal(obj._exp_sign(kc, ke), torch.from_numpy(z["exponent_based_sign.K"]))
+
+
+def test_clz32():
+    x = torch.tensor([1, 2, 3, 4, 127, 128, 255, 256, 2 ** 20 + 5, 2 ** 30], dtype=torch.int32)
+    want = torch.tensor([31, 30, 30, 29, 25, 24, 24, 23, 11, 1], dtype=torch.int32)
+    assert torch.equal(_clz32(x), want)
+
+
+def test_diff_idx_analysis_reference_value():
+    z = np.load(os.path.join(GOLDEN, "analysis_overlap.npz"))
+    got = analysis.diff_idx_analysis(torch.from_numpy(z["true_idx"]), torch.from_numpy(z["pred_idx"]))
+    assert abs(got - float(z["diff_idx_analysis"][0])) < 1e-12
+
+
+@pytest.mark.parametrize("rows", [1, 2, 5, 8, 13])
+def test_coverage_rate_any_row_count(rows):
+    g = torch.Generator().manual_seed(rows)
+    dense = torch.rand(2, 3, rows, 70, generator=g) < 0.2
+    idxs = [torch.nonzero(dense[b, h, r]).flatten() for b in range(2) for h in range(3) for r in range(rows)]
+    words = torch.zeros(2, 3, rows, 3, dtype=torch.int64)
+    for n, ids in enumerate(idxs):
+        b, h, r = n // (3 * rows), (n // rows) % 3, n % rows
+        for j in ids.tolist():
+            words[b, h, r, j >> 5] |= 1 << (j & 31)
+    mask = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    want = float((dense.any(2).sum(-1).double() / rows).mean())
+    assert abs(analysis.coverage_rate(mask) - want) < 1e-12
+
+
+def test_linear_specs_reject_other_weight_formats():
+    ok = mx_specs()
+    assert resolve_linear_specs(ok) == resolve_specs(ok)
+    for key, val in (("w_elem_format", "int4"), ("w_elem_format", None), ("w_elem_format", "fp8_e4m3"),
+                     ("round_weight", "floor"), ("round", "even")):
+        bad = dict(ok)
+        bad[key] = val
+        with pytest.raises(ValueError):
+            resolve_linear_specs(bad)
+        resolve_specs({k: v for k, v in bad.items() if k != "round"} | {"round": "nearest"}) if key == "round" else resolve_specs(bad)
