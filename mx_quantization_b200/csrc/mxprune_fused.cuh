@@ -52,7 +52,7 @@ template <int NC, int HG>
 __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uint64_t* bar_full, uint64_t* bar_mma,
                                                   const FusedParams& p, const FusedMaps& maps, const K1cSmem& L,
                                                   const OpsLayout& OL, int head, unsigned char* q_op, unsigned char* k_op,
-                                                  unsigned char* v_op, uint32_t* mask_head) {
+                                                  unsigned char* v_op, uint32_t* mask_head, int tile_begin, int tile_step) {
     unsigned char* const smem = gc.smem;
     constexpr int NMMA = 32 * NC;
     constexpr int NCH = (NC + 1) / 2;                               // key chunks per thread
@@ -90,7 +90,8 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
     const int nks = (NMMA + CR - 1) / CR;                           // every MMA row of the K operand is written
     const int nvs = (32 * NWk + CR - 1) / CR;                       // every token window of V
     const int qsteps = K1C_TILE / CR;                               // steps per query tile (2 or 1)
-    const int tiles = (Nq + K1C_TILE - 1) / K1C_TILE;
+    const int tiles_all = (Nq + K1C_TILE - 1) / K1C_TILE;
+    const int tiles = tiles_all > tile_begin ? (tiles_all - tile_begin + tile_step - 1) / tile_step : 0;   // this group's query tiles
     const int nsteps = nks + nvs + qsteps * tiles;
     const uint32_t box_main = (uint32_t)L.box_main, box_tail = (uint32_t)L.box_tail;
     const uint32_t slot_tx = (uint32_t)G * (box_main + box_tail);
@@ -104,7 +105,11 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
         int row0;
         if (c < nks) { mm = &maps.k_main; mt = &maps.k_tail; row0 = c * CR; }
         else if (c < nks + nvs) { mm = &maps.v_main; mt = &maps.v_tail; row0 = (c - nks) * CR; }
-        else { mm = &maps.q_main; mt = &maps.q_tail; row0 = (c - nks - nvs) * CR; }
+        else {
+            const int qc = c - nks - nvs, qt = qc / qsteps;
+            mm = &maps.q_main; mt = &maps.q_tail;
+            row0 = (tile_begin + qt * tile_step) * K1C_TILE + (qc - qt * qsteps) * CR;
+        }
         mbar_expect_tx(bar, slot_tx);
         for (int g = 0; g < G; ++g) {
             if (nfull) tma_load_5d(slot + g * box_main, mm, 0, row0 + g * K1C_ROWS, 0, hh, bb, bar);
@@ -130,14 +135,14 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
     const int my_pad = max(0, my_cols_end - max(Nk, my_cols_beg));
     int slot_i = st.slot_i;
     uint32_t slot_par = st.slot_par, ph_mma = st.ph_mma;
-    int tile = -1;
+    int tile = tile_begin - tile_step;
     int qstep = qsteps - 1;
 
     for (int c = 0; c < nsteps; ++c) {
         const bool is_k = c < nks;
         const bool is_v = !is_k && c < nks + nvs;
         if (!is_k && !is_v) {
-            if (++qstep == qsteps) { qstep = 0; ++tile; }
+            if (++qstep == qsteps) { qstep = 0; tile += tile_step; }
         }
         const int row0 = is_k ? c * CR : is_v ? (c - nks) * CR : tile * K1C_TILE + qstep * CR;
         const int nrows = is_k ? Nk : Nq;
@@ -442,25 +447,25 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
 // Keep an eye on `-Xptxas -v`: spills next to in-flight tcgen05.ld results are not something to live with.)
 template <int NC, int HG>
 __device__ __forceinline__ void fused_phase1(GroupCtx& gc, K1State& st, uint64_t* bars, const FusedParams& p, const FusedMaps& maps,
-                                          int head, unsigned char* slot, uint32_t* mask_head) {
+                                          int head, unsigned char* slot, uint32_t* mask_head, int tile_begin, int tile_step) {
     const K1cSmem L1 = k1c_smem_layout(p.hd, NC, p.ring, p.G);
     const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
     predict_topk_head<NC, HG>(gc, st, &bars[0], &bars[K1C_MAXR], p, maps, L1, O, head, slot, slot + p.slot_k, slot + p.slot_v,
-                              mask_head);
+                              mask_head, tile_begin, tile_step);
 }
 template <bool BF16>
 __device__ __forceinline__ void fused_phase2(GroupCtx& gc, const FusedParams& p, int head, const unsigned char* slot,
-                                          const uint32_t* mask_head) {
+                                          const uint32_t* mask_head, int tile_begin, int tile_step) {
     const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
     const int bb = head / p.H, hh = head - bb * p.H;
     float* out_head = p.out + bb * p.o_sB + hh * p.o_sH;
     if (p.sparse) {
         const K2sSmem L2 = k2s_smem_layout(O, p.top_k);
         attend_sparse_head<BF16>(gc, O, L2, p.Nq, p.Nk, p.hd, p.scale, p.flush != 0, slot, slot + p.slot_k, slot + p.slot_v,
-                                 mask_head, out_head, p.o_sN, 0, 1);
+                                 mask_head, out_head, p.o_sN, tile_begin, tile_step);
     } else {
         attend_pair_head<BF16, false>(gc, O, p.Nq, p.Nk, p.hd, p.scale, p.flush != 0, slot, slot + p.slot_k, slot + p.slot_v,
-                                      mask_head, out_head, p.o_sN, nullptr, nullptr, 0, 1);
+                                      mask_head, out_head, p.o_sN, nullptr, nullptr, tile_begin, tile_step);
     }
 }
 
@@ -502,16 +507,37 @@ k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_con
     const int gslot = 2 * (int)blockIdx.x + grp;
     unsigned char* const slot = p.slots + (size_t)gslot * p.slot_bytes;
 
-    for (int head = gslot; head < heads; head += 2 * (int)gridDim.x) {
+    // Heads are dealt round-robin to the chip's groups.  The last, partial round would leave most groups idle for a whole
+    // head time (3072 heads over 296 groups: 10 full rounds + 112 heads); when at most half of the groups have a head
+    // left and a head has two query tiles, the two groups of a CTA share one head of that round instead - each
+    // quantizes K and V for itself and takes one of the query tiles (no phase-1 token: they start together).
+    const int ngroups = 2 * (int)gridDim.x;
+    const int full = heads / ngroups, rem = heads - full * ngroups;
+    const bool tail_split = rem > 0 && 2 * rem <= ngroups && (p.Nq + K1C_TILE - 1) / K1C_TILE == 2;
+    const int nrounds = full + (rem > 0 ? 1 : 0);
+    for (int r = 0; r < nrounds; ++r) {
+        int head = r * ngroups + gslot, tile_begin = 0, tile_step = 1;
+        bool lock = p.pingpong != 0;
+        if (r == full) {
+            if (tail_split) {
+                if (gslot >= 2 * rem) break;
+                head = r * ngroups + (gslot >> 1);
+                tile_begin = gslot & 1;
+                tile_step = 2;
+                lock = false;
+            } else if (gslot >= rem) {
+                break;
+            }
+        }
         uint32_t* mask_head = p.mask_out ? p.mask_out + (size_t)head * p.Nq * NW
                                          : reinterpret_cast<uint32_t*>(slot + p.slot_mask);
-        if (p.pingpong) {                                           // take the phase-1 token
+        if (lock) {                                                 // take the phase-1 token
             if (tid == 0) {
                 while (atomicCAS(&s_lock, 0, 1) != 0) __nanosleep(64);
             }
             group_sync(gc);
         }
-        fused_phase1<NC, HG>(gc, st, bars, p, maps, head, slot, mask_head);
+        fused_phase1<NC, HG>(gc, st, bars, p, maps, head, slot, mask_head, tile_begin, tile_step);
         // phase 1 -> phase 2: the slot's operands (generic-proxy global stores) are read back by TMA bulk copies
         // (async proxy), the masks by ordinary loads of other threads of the group; phase 2 also re-purposes the
         // shared memory that phase 1 wrote with generic stores as TMA destinations
@@ -520,9 +546,9 @@ k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_con
         tcgen05_fence_before_sync();
         group_sync(gc);
         tcgen05_fence_after_sync();
-        if (p.pingpong && tid == 0) atomicExch(&s_lock, 0);         // every thread of the group has left phase 1
+        if (lock && tid == 0) atomicExch(&s_lock, 0);               // every thread of the group has left phase 1
         MXP_PROF(gc, 21);
-        fused_phase2<BF16>(gc, p, head, slot, mask_head);
+        fused_phase2<BF16>(gc, p, head, slot, mask_head, tile_begin, tile_step);
         // phase 2 ends with fence.proxy.async + group barrier: its shared memory and TMEM may be reused, and its TMA
         // reads of the slot have completed (every copy was waited for), so the next head may overwrite the slot
     }
