@@ -9,6 +9,7 @@
 #include "mxprune_attend.cuh"
 #include "mxprune_attend_sparse.cuh"
 #include "mxprune_fused.cuh"
+#include "mxprune_fused_launch.cuh"
 
 namespace mxp {
 
@@ -63,17 +64,18 @@ static std::atomic<int> g_fused_pingpong{1};
 void fused_set_pingpong(int on) { g_fused_pingpong = on; }
 void fused_set_timing_buffer(unsigned long long* buf) { g_fused_timing = buf; }
 
+// head_dim 64 (DeiT / ViT heads) has its own instantiations with the staging geometry folded at compile time; they are
+// compiled in their own translation unit (mxprune_fused64.cu)
+extern template int launch_fused_hd<8, 0, 64>(const FusedParams&, const FusedMaps&, int, cudaStream_t);
+extern template int launch_fused_hd<7, 13, 64>(const FusedParams&, const FusedMaps&, int, cudaStream_t);
+extern template int launch_fused_hd<7, 14, 64>(const FusedParams&, const FusedMaps&, int, cudaStream_t);
+extern template int launch_fused_hd<7, 0, 64>(const FusedParams&, const FusedMaps&, int, cudaStream_t);
 template <int NC, int HG>
 static int launch_fused_one(const FusedParams& p, const FusedMaps& maps, int grid, cudaStream_t st) {
-    const size_t dyn = 2 * FUSED_GROUP_SMEM;
-    if (p.bf16) {
-        MXP_ENSURE_DYN_SMEM((k_fused_pruned_attention<NC, HG, true>), (int)dyn);
-        k_fused_pruned_attention<NC, HG, true><<<grid, FUSED_T, dyn, st>>>(p, maps);
-    } else {
-        MXP_ENSURE_DYN_SMEM((k_fused_pruned_attention<NC, HG, false>), (int)dyn);
-        k_fused_pruned_attention<NC, HG, false><<<grid, FUSED_T, dyn, st>>>(p, maps);
-    }
-    return check_launch("k_fused_pruned_attention");
+#ifndef MXP_FUSED_NO_HD64
+    if (p.hd == 64 && p.sparse) return launch_fused_hd<NC, HG, 64>(p, maps, grid, st);
+#endif
+    return launch_fused_hd<NC, HG, 0>(p, maps, grid, st);
 }
 
 int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out) {
@@ -85,10 +87,7 @@ int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out) {
     if (heads < 64) return 1;
     const int nc = a.Nk <= 224 ? 7 : 8;
     const int nb = (a.hd + 31) / 32;
-    int G = nb <= 2 ? 2 : 1;
-    if (k1c_smem_layout(a.hd, nc, 2, G).total > FUSED_GROUP_SMEM - 256) G = 1;
-    int ring = K1C_MAXR;
-    while (ring > 2 && k1c_smem_layout(a.hd, nc, ring, G).total > FUSED_GROUP_SMEM - 256) --ring;
+    const int G = fused_G(a.hd, nc), ring = fused_ring(a.hd, nc);
     const K1cSmem L1 = k1c_smem_layout(a.hd, nc, ring, G);
     if (L1.total > FUSED_GROUP_SMEM - 256) return 1;
     const OpsLayout O = ops_layout(a.Nq, a.Nk, a.hd);

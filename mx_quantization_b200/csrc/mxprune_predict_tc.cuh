@@ -60,8 +60,8 @@ struct K1cSmem {
 // biased: two extra K columns carry the additive key bias through the MMA (see the kernel).
 // opw = operand width multiplier: 2 when each side carries two operand parts [A | B] per row (K1-wide's
 // two_step_leading_ones mode), chunk c of part B at chunk index (hdp >> 3) + c.
-__host__ __device__ inline K1cSmem k1c_smem_layout(int hd, int nc, int ring, int G, bool biased = false, int opw = 1) {
-    K1cSmem L;
+__host__ __device__ constexpr inline K1cSmem k1c_smem_layout(int hd, int nc, int ring, int G, bool biased = false, int opw = 1) {
+    K1cSmem L{};
     L.nfull = hd >> 5;
     L.tail = hd & 31;
     L.nb = (hd + 31) >> 5;
