@@ -597,12 +597,19 @@ inline OpsBytes ops_bytes(int B, int H, int Nq, int Nk, int hd) {
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---- K1-TC launch (tensor maps: make_view_maps, mxprune_predict_tc.cuh) ----------------------
-template <int NC, bool CODES, bool BIASED, int HG = 0>
+template <int NC, bool CODES, bool BIASED, int HG = 0, int HD = 0, int BF = -1>
 static int launch_predict_topk_tc_one(const PredParams& p, const K1cMaps& maps, const K1cSmem& L, size_t dyn,
                                       dim3 grid, cudaStream_t st) {
-    MXP_ENSURE_DYN_SMEM((k_predict_topk_tc<NC, CODES, BIASED, HG>), 227 * 1024);
-    k_predict_topk_tc<NC, CODES, BIASED, HG><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
+    MXP_ENSURE_DYN_SMEM((k_predict_topk_tc<NC, CODES, BIASED, HG, HD, BF>), 227 * 1024);
+    k_predict_topk_tc<NC, CODES, BIASED, HG, HD, BF><<<grid, K1C_T, dyn, st>>>(p, maps, L.ring, L.G);
     return check_launch("k_predict_topk_tc");
+}
+// the workload head shapes get instantiations with head_dim and the A1 switch folded at compile time
+template <int NC, int HG, int HD>
+static int launch_predict_topk_tc_hd(const PredParams& p, const K1cMaps& maps, const K1cSmem& L, size_t dyn,
+                                     dim3 grid, cudaStream_t st) {
+    return p.bf16 ? launch_predict_topk_tc_one<NC, false, false, HG, HD, 1>(p, maps, L, dyn, grid, st)
+                  : launch_predict_topk_tc_one<NC, false, false, HG, HD, 0>(p, maps, L, dyn, grid, st);
 }
 
 
@@ -614,14 +621,10 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
     if (!make_view_maps(p.k, p.B, p.H, p.Nk, p.hd, &maps.k_main, &maps.k_tail)) return 1;
     // step = 64 G rows (G = 2 when a 64-row box gives fewer than 256 block tasks); ring depth: as many
     // slots as fit with two CTAs per SM
-    const size_t per_cta2 = 232448 / 2 - 1024, per_cta1 = 232448 - 1024;
+    const size_t per_cta1 = K1C_PER_CTA1;
     const int nc = p.Nk <= 32 ? 1 : p.Nk <= 64 ? 2 : p.Nk <= 128 ? 4 : p.Nk <= 224 ? 7 : 8;
-    const int nb = (p.hd + 31) / 32;
-    int G = nb <= 2 ? 2 : 1;
     const bool biased = p.key_bias != nullptr;
-    if (k1c_smem_layout(p.hd, nc, 2, G, biased).total > per_cta2) G = 1;
-    int ring = K1C_MAXR;
-    while (ring > 2 && k1c_smem_layout(p.hd, nc, ring, G, biased).total > per_cta2) --ring;
+    const int G = k1c_G(p.hd, nc, biased), ring = k1c_ring(p.hd, nc, biased);
     K1cSmem L = k1c_smem_layout(p.hd, nc, ring, G, biased);
     if (L.total > per_cta1) return 1;
     const int heads = p.B * p.H;
@@ -647,14 +650,19 @@ static int try_predict_topk_tc(const PredParams& p, cudaStream_t st, int* rc_out
         case 4: MXP_TC(4); break;
         case 7:
             // 193 .. 224 keys: the two lanes of a row split the columns at 104 / 112 instead of 128 (no dummy chunk)
-            if (!biased && !codes && p.Nk > 192 && p.Nk <= 208)
+            if (!biased && !codes && p.Nk > 192 && p.Nk <= 208 && p.hd == 64)       // DeiT / ViT-224 heads
+                *rc_out = launch_predict_topk_tc_hd<7, 13, 64>(p, maps, L, dyn, grid, st);
+            else if (!biased && !codes && p.Nk > 192 && p.Nk <= 208)
                 *rc_out = launch_predict_topk_tc_one<7, false, false, 13>(p, maps, L, dyn, grid, st);
             else if (!biased && !codes && p.Nk > 208)
                 *rc_out = launch_predict_topk_tc_one<7, false, false, 14>(p, maps, L, dyn, grid, st);
             else
                 MXP_TC(7);
             break;
-        default: MXP_TC(8); break;
+        default:
+            if (!biased && !codes && p.hd == 72) *rc_out = launch_predict_topk_tc_hd<8, 0, 72>(p, maps, L, dyn, grid, st);   // DiT / PixArt heads
+            else MXP_TC(8);
+            break;
     }
 #undef MXP_TC
     return 0;

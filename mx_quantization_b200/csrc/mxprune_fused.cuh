@@ -65,7 +65,9 @@ struct K1State {                 // phase-1 pipeline state carried from head to 
 
 // ---- phase 1 for one head.  bar_full[ring], bar_mma: the group's mbarriers (count 1).
 // HD: head_dim as a compile-time constant (0 = run time): with it every staging / operand offset of the quantize steps folds
-template <int NC, int HG, bool BF16, int HD>
+// NN: Nq == Nk as a compile-time constant (0 = run time).  Measured with NN = 197 (DeiT): no smaller code, 116 bytes of
+// spills at the 128-register cap, 5.40 -> 5.92 ms per DeiT-base step - so only NN = 0 is instantiated.
+template <int NC, int HG, bool BF16, int HD, int NN>
 __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uint64_t* bar_full, uint64_t* bar_mma,
                                                   const FusedParams& p, const FusedMaps& maps, const K1cSmem& L,
                                                   const OpsLayout& OL, int head, unsigned char* q_op, unsigned char* k_op,
@@ -78,7 +80,7 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
     constexpr int NWORDS = HW / 2;                                  // packed key words per lane
     constexpr int NLW = (HW + 31) / 32;                             // bitmask words per lane (lane-local bit order)
     static_assert(HG == 0 || ((REM == 8 || REM == 16) && 16 * HG <= 32 * NC && NWORDS % 4 == 0), "tight split");
-    const int Nk = p.Nk, Nq = p.Nq, hd = HD ? HD : p.hd, kk = p.top_k;
+    const int Nk = NN ? NN : p.Nk, Nq = NN ? NN : p.Nq, hd = HD ? HD : p.hd, kk = p.top_k;
     const int G = L.G, ring = L.ring;
     const int nfull = L.nfull, tail = L.tail, nb = L.nb;
     const int kch = L.hdp >> 3;                                     // 16-byte chunks per predictor-operand row
@@ -463,36 +465,36 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
 // The two phases of a head.  (Inlined: as separate functions the call ABI's callee-saved registers cost 0.5 - 1.2 KB
 // of spills per thread; inlined the kernel stays at the 128-register cap with a handful of spilled loop invariants.
 // Keep an eye on `-Xptxas -v`: spills next to in-flight tcgen05.ld results are not something to live with.)
-template <int NC, int HG, bool BF16, int HD>
+template <int NC, int HG, bool BF16, int HD, int NN>
 __device__ __forceinline__ void fused_phase1(GroupCtx& gc, K1State& st, uint64_t* bars, const FusedParams& p, const FusedMaps& maps,
                                           int head, unsigned char* slot, uint32_t* mask_head, int tile_begin, int tile_step) {
     const K1cSmem L1 = HD ? k1c_smem_layout(HD, NC, fused_ring(HD, NC), fused_G(HD, NC)) : k1c_smem_layout(p.hd, NC, p.ring, p.G);
-    const OpsLayout O = ops_layout(p.Nq, p.Nk, HD ? HD : p.hd);
-    predict_topk_head<NC, HG, BF16, HD>(gc, st, &bars[0], &bars[K1C_MAXR], p, maps, L1, O, head, slot, slot + p.slot_k, slot + p.slot_v,
+    const OpsLayout O = ops_layout(NN ? NN : p.Nq, NN ? NN : p.Nk, HD ? HD : p.hd);
+    predict_topk_head<NC, HG, BF16, HD, NN>(gc, st, &bars[0], &bars[K1C_MAXR], p, maps, L1, O, head, slot, slot + p.slot_k, slot + p.slot_v,
                               mask_head, tile_begin, tile_step);
 }
 // HD != 0: head_dim at compile time; such instantiations carry the cost-follows-k epilogue only (the launcher sends
 // dense-epilogue calls to the HD = 0 kernels)
-template <bool BF16, int HD>
+template <bool BF16, int HD, int NN>
 __device__ __forceinline__ void fused_phase2(GroupCtx& gc, const FusedParams& p, int head, const unsigned char* slot,
                                           const uint32_t* mask_head, int tile_begin, int tile_step) {
-    const int hd = HD ? HD : p.hd;
-    const OpsLayout O = ops_layout(p.Nq, p.Nk, hd);
+    const int hd = HD ? HD : p.hd, Nq = NN ? NN : p.Nq, Nk = NN ? NN : p.Nk;
+    const OpsLayout O = ops_layout(Nq, Nk, hd);
     const int bb = head / p.H, hh = head - bb * p.H;
     float* out_head = p.out + bb * p.o_sB + hh * p.o_sH;
     if (HD != 0 || p.sparse) {
         const K2sSmem L2 = k2s_smem_layout(O, p.top_k);
-        attend_sparse_head<BF16>(gc, O, L2, p.Nq, p.Nk, hd, p.scale, p.flush != 0, slot, slot + p.slot_k, slot + p.slot_v,
+        attend_sparse_head<BF16>(gc, O, L2, Nq, Nk, hd, p.scale, p.flush != 0, slot, slot + p.slot_k, slot + p.slot_v,
                                  mask_head, out_head, p.o_sN, tile_begin, tile_step);
     } else {
-        attend_pair_head<BF16, false>(gc, O, p.Nq, p.Nk, hd, p.scale, p.flush != 0, slot, slot + p.slot_k, slot + p.slot_v,
+        attend_pair_head<BF16, false>(gc, O, Nq, Nk, hd, p.scale, p.flush != 0, slot, slot + p.slot_k, slot + p.slot_v,
                                       mask_head, out_head, p.o_sN, nullptr, nullptr, tile_begin, tile_step);
     }
 }
 
 // NC, HG: key-column geometry of phase 1 (see k_predict_topk_tc); BF16: A1 rounding on (bfloat 16); HD: head_dim at
-// compile time (0 = any)
-template <int NC, int HG, bool BF16, int HD>
+// compile time (0 = any); NN: Nq == Nk at compile time (0 = any)
+template <int NC, int HG, bool BF16, int HD, int NN>
 __global__ void __launch_bounds__(FUSED_T, 1)
 k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_constant__ FusedMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem_fused[];
@@ -503,7 +505,8 @@ k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_con
     const int tid = threadIdx.x & 255;
     uint64_t* bars = s_bars[grp];
     const int heads = p.B * p.H;
-    const int NW = (p.Nk + 31) >> 5;
+    const int Nq_ = NN ? NN : p.Nq, Nk_ = NN ? NN : p.Nk;
+    const int NW = (Nk_ + 31) >> 5;
     const bool has_tail = (p.hd & 31) != 0;
 
     if (threadIdx.x == 0) s_lock = 0;
@@ -535,7 +538,7 @@ k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_con
     // quantizes K and V for itself and takes one of the query tiles (no phase-1 token: they start together).
     const int ngroups = 2 * (int)gridDim.x;
     const int full = heads / ngroups, rem = heads - full * ngroups;
-    const bool tail_split = rem > 0 && 2 * rem <= ngroups && (p.Nq + K1C_TILE - 1) / K1C_TILE == 2;
+    const bool tail_split = rem > 0 && 2 * rem <= ngroups && (Nq_ + K1C_TILE - 1) / K1C_TILE == 2;
     const int nrounds = full + (rem > 0 ? 1 : 0);
     for (int r = 0; r < nrounds; ++r) {
         int head = r * ngroups + gslot, tile_begin = 0, tile_step = 1;
@@ -551,7 +554,7 @@ k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_con
                 break;
             }
         }
-        uint32_t* mask_head = p.mask_out ? p.mask_out + (size_t)head * p.Nq * NW
+        uint32_t* mask_head = p.mask_out ? p.mask_out + (size_t)head * Nq_ * NW
                                          : reinterpret_cast<uint32_t*>(slot + p.slot_mask);
         if (lock) {                                                 // take the phase-1 token
             if (tid == 0) {
@@ -559,7 +562,7 @@ k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_con
             }
             group_sync(gc);
         }
-        fused_phase1<NC, HG, BF16, HD>(gc, st, bars, p, maps, head, slot, mask_head, tile_begin, tile_step);
+        fused_phase1<NC, HG, BF16, HD, NN>(gc, st, bars, p, maps, head, slot, mask_head, tile_begin, tile_step);
         // phase 1 -> phase 2: the slot's operands (generic-proxy global stores) are read back by TMA bulk copies
         // (async proxy), the masks by ordinary loads of other threads of the group; phase 2 also re-purposes the
         // shared memory that phase 1 wrote with generic stores as TMA destinations
@@ -570,7 +573,7 @@ k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_con
         tcgen05_fence_after_sync();
         if (lock && tid == 0) atomicExch(&s_lock, 0);               // every thread of the group has left phase 1
         MXP_PROF(gc, 21);
-        fused_phase2<BF16, HD>(gc, p, head, slot, mask_head, tile_begin, tile_step);
+        fused_phase2<BF16, HD, NN>(gc, p, head, slot, mask_head, tile_begin, tile_step);
         // phase 2 ends with fence.proxy.async + group barrier: its shared memory and TMEM may be reused, and its TMA
         // reads of the slot have completed (every copy was waited for), so the next head may overwrite the slot
     }

@@ -87,6 +87,23 @@ __host__ __device__ constexpr inline K1cSmem k1c_smem_layout(int hd, int nc, int
     return L;
 }
 
+// Staging geometry of the stand-alone K1 launch as a function of (head_dim, key chunks): G = TMA boxes per ring slot
+// (2 when a 64-row box gives fewer than 256 block tasks), ring = as many slots as fit with two CTAs per SM.
+// constexpr: the launcher and the head_dim-specialised instantiations (template HD) evaluate the same rule.
+constexpr size_t K1C_PER_CTA2 = 232448 / 2 - 1024, K1C_PER_CTA1 = 232448 - 1024;
+__host__ __device__ constexpr inline int k1c_G(int hd, int nc, bool biased) {
+    const int nb = (hd + 31) / 32;
+    int G = nb <= 2 ? 2 : 1;
+    if (k1c_smem_layout(hd, nc, 2, G, biased).total > K1C_PER_CTA2) G = 1;
+    return G;
+}
+__host__ __device__ constexpr inline int k1c_ring(int hd, int nc, bool biased) {
+    const int G = k1c_G(hd, nc, biased);
+    int ring = K1C_MAXR;
+    while (ring > 2 && k1c_smem_layout(hd, nc, ring, G, biased).total > K1C_PER_CTA2) --ring;
+    return ring;
+}
+
 struct K1cMaps {
     CUtensorMap q_main, q_tail, k_main, k_tail;
 };
@@ -444,9 +461,11 @@ __device__ __forceinline__ void tmem_ld_16x32bx2_x8(uint32_t taddr, uint32_t (&r
 // columns [0, 8 HG), half 1 [8 HG, 16 HG) - so that a key count just above a multiple of 32 (DeiT's 197 -> 2 x 104)
 // does not cost a whole extra 32-key chunk of selection work per lane; the row mask is then written byte-wise
 // (8 HG is a byte boundary of the bitmask).  HG = 0: halves of NCH 32-key chunks, mask written in words.
-template <int NC, bool CODES, bool BIASED, int HG = 0>
+// HD: head_dim at compile time (0 = run time) - staging geometry and operand offsets fold; BF: A1 rounding at compile
+// time (-1 = run time, 0 = bfloat 32, 1 = bfloat 16)
+template <int NC, bool CODES, bool BIASED, int HG = 0, int HD = 0, int BF = -1>
 __global__ void __launch_bounds__(K1C_T, 2)
-k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring, const int G) {
+k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, const int ring_arg, const int G_arg) {
     extern __shared__ __align__(1024) unsigned char smem_k1c[];     // 1024-byte aligned: SWIZZLE_128B boxes
     unsigned char* const smem = smem_k1c;
     constexpr int NMMA = 32 * NC;
@@ -457,8 +476,9 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     constexpr int NLW = (HW + 31) / 32;                             // bitmask words per lane (lane-local bit order)
     static_assert(HG == 0 || (!BIASED && !CODES && (REM == 8 || REM == 16) && 16 * HG <= 32 * NC && NWORDS % 4 == 0),
                   "tight split: unbiased kernel, rest of 8 or 16 columns");
-    const int Nk = p.Nk, Nq = p.Nq, hd = p.hd, kk = p.top_k;
+    const int Nk = p.Nk, Nq = p.Nq, hd = HD ? HD : p.hd, kk = p.top_k;
     constexpr bool biased = BIASED;
+    const int ring = HD ? k1c_ring(HD, NC, BIASED) : ring_arg, G = HD ? k1c_G(HD, NC, BIASED) : G_arg;
     const K1cSmem L = k1c_smem_layout(hd, NC, ring, G, biased);
     const int nfull = L.nfull, tail = L.tail, nb = L.nb;
     const int kch = L.hdp >> 3;                                     // 16-byte chunks per predictor-operand row
@@ -486,7 +506,7 @@ k_predict_topk_tc(const PredParams p, const __grid_constant__ K1cMaps maps, cons
     const int lane_base = 32 * (warp & 3) + 16 * (warp >> 2);
     const int rr = lane_base + (lane & 15);                         // row of the tile
     const int part = lane >> 4;
-    const bool bf16 = p.bf16, flush = p.flush;
+    const bool bf16 = BF < 0 ? (p.bf16 != 0) : (BF != 0), flush = p.flush;
     const bool write_k = CODES && p.k_codes != nullptr && blockIdx.y == 0;
     const bool write_q = CODES && p.q_codes != nullptr;
     const bool write_kop = p.k_op != nullptr && blockIdx.y == 0;
