@@ -10,6 +10,7 @@
 #include "mxprune_device.cuh"
 #include "mxprune_predict.cuh"
 #include "mxprune_attend.cuh"
+#include "mxprune_attend_long.cuh"
 #include "mxprune_predict_tc.cuh"
 #include "mxprune_predict_long_tc.cuh"
 #include "mxprune_predict_wide.cuh"
@@ -531,6 +532,10 @@ inline void prof_mark(int i, cudaStream_t st) {
 int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
     const K2Smem L = k2_smem_layout(O);
+    if (!O.single) {                // Nk > 256: two lanes per row, pipelined key-block stream (mxprune_attend_long.cuh)
+        int rc = MXP_OK;
+        if (attend_long_pair_try(p, st, &rc) == 0) return rc;
+    }
     MXP_ENSURE_DYN_SMEM((k_attend_pair<true, false>), 160 * 1024);
     MXP_ENSURE_DYN_SMEM((k_attend_pair<false, false>), 160 * 1024);
     MXP_ENSURE_DYN_SMEM((k_attend_pair<true, true>), 160 * 1024);
@@ -540,6 +545,9 @@ int launch_attend_umma(const AttnParams& p, cudaStream_t st) {
     if (L.total > 160 * 1024) return fail(MXP_E_UNSUPPORTED, "attention operands need %zu bytes of shared memory", L.total);
     const int heads = p.B * p.H;
     int splits = (148 * 2 + heads - 1) / heads;
+    // key blocks streamed per query tile (Nk > 256): a CTA holds nothing across tiles, so one CTA per tile costs
+    // nothing and fills the last wave (256 heads x 2 splits = 1.73 waves of 296 CTAs -> 27.7 waves)
+    if (!O.single) splits = O.q_tiles;
     if (splits > O.q_tiles) splits = O.q_tiles;
     if (splits < 1) splits = 1;
     dim3 grid((unsigned)heads, (unsigned)splits);
