@@ -96,6 +96,10 @@ int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out) {
     // (DeiT-base layer 0.504 vs 0.521 ms); with the dense epilogue it does not (DiT-XL/2 1.01 vs 0.95 ms) - both phases
     // are then issue-bound and gain nothing from sharing an SM.  Path 2 forces it (tests, A/B).
     if (!sparse && g_fused_path.load() != 2) return 1;
+    // measured as well (tools/sweep_c5.py, tools/ab_fused.py): with 64-row steps (G = 1: three MX blocks per row, or a
+    // predictor operand that leaves no room for 128-row slots) phase 1 needs twice the steps and the fused launch loses
+    // to the three kernels (256 tokens x head_dim 72, top_k 26: 0.94 vs 0.76 ms; PixArt's 77: 1.00 vs 0.84 ms)
+    if (G != 2 && g_fused_path.load() != 2) return 1;
     if (!sparse && k2_smem_layout(O).total > FUSED_GROUP_SMEM - 256) return 1;
     const FusedSlotLayout S = fused_slot_layout(a.Nq, a.Nk, a.hd);
     int grid = sm_count();

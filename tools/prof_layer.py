@@ -1,5 +1,5 @@
 """One layer of a bench workload, a few calls - the short command ncu wraps.
-    python tools/prof_layer.py [workload] [calls]"""
+    python tools/prof_layer.py [workload] [calls] [three]      (three: the three-kernel path, mxp_set_fused_path(0))"""
 import os
 import sys
 
@@ -19,6 +19,8 @@ g = torch.Generator(device=dev).manual_seed(0)
 qkv = torch.randn(B, N, 3, H, hd, device=dev, generator=g).permute(2, 0, 3, 1, 4)
 out = torch.empty(B, N, H, hd, device=dev).permute(0, 2, 1, 3)
 specs = bench.mx_specs(w["bfloat"], w["flush"])
+if len(sys.argv) > 3 and sys.argv[3] == "three":
+    mxq.set_fused_path(False)
 for _ in range(calls):
     ms = []
     mxq.pruned_attention(qkv[0], qkv[1], qkv[2], specs, w["top_k"], out=out, _kernel_ms=ms)
