@@ -29,6 +29,32 @@ def main():
     host.fill_(1)
     gpu = torch.empty(n, dtype=torch.uint8, device=dev)
     res = {}
+    # both directions at once, in bench.py's e2e proportion (three input buffers in for one output buffer out)
+    host2 = torch.empty(n // 3, dtype=torch.uint8).pin_memory()
+    gpu2 = torch.empty(n // 3, dtype=torch.uint8, device=dev)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s_in.wait_stream(torch.cuda.current_stream())
+    s_out.wait_stream(torch.cuda.current_stream())
+    for _ in range(args.reps):
+        with torch.cuda.stream(s_in):
+            gpu.copy_(host, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            host2.copy_(gpu2, non_blocking=True)
+    torch.cuda.current_stream().wait_stream(s_in)
+    torch.cuda.current_stream().wait_stream(s_out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["both_3to1"] = {"rank_gbs": (n + n // 3) * args.reps / (ms * 1e-3) / 1e9,
+                        "aggregate_gbs": world * (n + n // 3) * args.reps / (float(t.item()) * 1e-3) / 1e9}
     for name, (dst, src) in (("h2d", (gpu, host)), ("d2h", (host, gpu))):
         dst.copy_(src, non_blocking=True)
         torch.cuda.synchronize()
@@ -65,7 +91,8 @@ def main():
         dist.all_gather_object(out, line)
         if rank == 0:
             print(json.dumps({"n_ranks": world, "h2d_aggregate_gbs": res["h2d"]["aggregate_gbs"],
-                              "d2h_aggregate_gbs": res["d2h"]["aggregate_gbs"], "ranks": out}), flush=True)
+                              "d2h_aggregate_gbs": res["d2h"]["aggregate_gbs"],
+                              "both_3to1_aggregate_gbs": res["both_3to1"]["aggregate_gbs"], "ranks": out}), flush=True)
         dist.destroy_process_group()
     else:
         print(json.dumps(line), flush=True)
