@@ -225,6 +225,7 @@ FUSED_SHAPES = [  # B, H, N, hd, top_k, kind, bfloat, flush   (B * H >= 64: the 
     (8, 8, 220, 64, 50, "randn", 16, False),        # 112-column split
     (8, 9, 130, 32, 13, "randn", 32, False),        # head_dim 32
     (33, 2, 250, 72, 60, "lognormal", 16, False),   # odd head count: the last group of the last CTA idles
+    (20, 16, 197, 64, 30, "randn", 32, False),      # 320 heads on 296 groups: the shared last round (one query tile per group)
 ]
 
 
@@ -254,6 +255,25 @@ def test_fused_kernel(mxq, B, H, N, hd, top_k, kind, bfloat, flush):
     assert launches[True] == 1 and launches[False] == 3, launches
     scale = float(ref["out"].abs().max())
     assert float((outs[True] - outs[False]).abs().max()) <= 2 * OUT_TOL * scale
+
+
+@pytest.mark.parametrize("B,H,N,hd,top_k,launches", [
+    (6, 12, 197, 64, 30, 1),       # DeiT-shaped: one fused persistent launch
+    (2, 3, 197, 64, 30, 3),        # too few heads for a persistent launch (C1)
+    (8, 16, 256, 72, 26, 3),       # head_dim 72: 64-row staging steps - the three kernels (K2 = the cost-follows-k kernel)
+    (8, 16, 256, 72, 154, 3),      # DiT's k: dense epilogue
+    (2, 4, 512, 72, 128, -6),      # streamed key blocks: operand pre-passes + selection + V prep + two-lanes-per-row attention (at most 6)
+])
+def test_default_launch_plan(mxq, B, H, N, hd, top_k, launches):
+    """The launch plan mxp_pruned_attention picks by default: results are checked elsewhere; here only that the
+    shapes of the workloads take the plan that was measured faster, and that the call stays a fixed, small number of launches."""
+    q, k, v = make_qkv(B, H, N, hd, seed=2)
+    out, mask = mxq.pruned_attention(q.cuda(), k.cuda(), v.cuda(), mx_specs(), top_k, return_mask=True)
+    n = mxq.last_launch_count()
+    assert (n == launches) if launches > 0 else (3 < n <= -launches), n
+    words = mask.to(torch.int64) & 0xFFFFFFFF
+    pop = sum(((words >> b) & 1) for b in range(32)).sum(-1)
+    assert bool((pop == top_k).all()) and bool(torch.isfinite(out).all())
 
 
 def test_fused_kernel_full_c2_properties(mxq):
