@@ -258,22 +258,30 @@ __device__ __forceinline__ void attend_sparse_head(GroupCtx& g, const OpsLayout&
                     *reinterpret_cast<uint4*>(prow + (size_t)((2 * part + j) * 4 + q) * K2T * 16) = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
             const int tbeg = gi ? n0 : 0, tend = gi ? ntot : min(n0, ntot);
-            auto emit = [&](int j, float ev) {
-                const uint2 ew = *reinterpret_cast<const uint2*>(erow + ((j & 0xe0) << 5));      // (j >> 5) * 128 * 8
-                const float s1 = __uint_as_float(ew.x);
+            // One list entry -> one bf16 element of the P operand.  The window's exponent record is a dependent shared-memory
+            // load (entry -> key index -> window -> record), so two entries are processed together with ONE branch for the
+            // rare slow exponent path (both chains in flight), and the next pair's entry is fetched before the current pair
+            // is converted.
+            auto window_rec = [&](int j) { return *reinterpret_cast<const uint2*>(erow + ((j & 0xe0) << 5)); };   // (j >> 5) * 128 * 8
+            auto p_bits = [&](float ev) {
                 uint32_t pbits = __float_as_uint(ev * inv);
                 if (bf16) pbits = bf16_half_away(pbits);
-                uint32_t val;
-                if (s1 >= 0.f) {
-                    // code = min(127, floor(p * 2^(6-e) + 0.5)) without F2I / I2F (see K1)
-                    const float v = fminf(fmaf(__uint_as_float(pbits), s1, 0.5f), 127.0f);
-                    const uint32_t cb = __float_as_uint(__fadd_rd(v, 8405760.0f)) & 0xffffu;     // bf16 pattern of 128 + code
-                    val = bf2_as_u32(__hfma2(u32_as_bf2(cb), u32_as_bf2(ew.y), u32_as_bf2(ew.y >> 16)));
-                } else {
-                    const int e = (int)s1;
-                    const float rq = __uint_as_float(pbits) * exp2i(-e) * 64.0f + 0.5f;
-                    val = __float_as_uint((float)min(__float2int_rz(rq), 127) * exp2i(e - 6)) >> 16;
-                }
+                return pbits;
+            };
+            auto fast_val = [&](uint32_t pbits, const uint2& ew) {
+                // code = min(127, floor(p * 2^(6-e) + 0.5)) without F2I / I2F (see K1)
+                const float v = fminf(fmaf(__uint_as_float(pbits), __uint_as_float(ew.x), 0.5f), 127.0f);
+                const uint32_t cb = __float_as_uint(__fadd_rd(v, 8405760.0f)) & 0xffffu;         // bf16 pattern of 128 + code
+                return bf2_as_u32(__hfma2(u32_as_bf2(cb), u32_as_bf2(ew.y), u32_as_bf2(ew.y >> 16)));
+            };
+            auto any_val = [&](uint32_t pbits, const uint2& ew) {
+                const float s1 = __uint_as_float(ew.x);
+                if (s1 >= 0.f) return fast_val(pbits, ew);
+                const int e = (int)s1;
+                const float rq = __uint_as_float(pbits) * exp2i(-e) * 64.0f + 0.5f;
+                return __float_as_uint((float)min(__float2int_rz(rq), 127) * exp2i(e - 6)) >> 16;
+            };
+            auto put = [&](int j, uint32_t val) {
                 // element (window j >> 5 & 3, key j & 31): chunk (j & 127) >> 3 of the group, 2-byte slot j & 7
                 *reinterpret_cast<unsigned short*>(prow + ((((uint32_t)j & 127u) * 0x102u) & 0x780eu)) = (unsigned short)val;
             };
@@ -282,15 +290,31 @@ __device__ __forceinline__ void attend_sparse_head(GroupCtx& g, const OpsLayout&
             const float* pl = s_list + first * K2S_LSTR + rr;
             const unsigned char* pj = s_lj + first * K2S_LSTR + rr;
             int it = 0;
+            int j0 = 0, j1 = 0;
+            float e0 = 0.f, e1 = 0.f;
+            if (nmy >= 2) { j0 = pj[0]; j1 = pj[2 * K2S_LSTR]; e0 = pl[0]; e1 = pl[2 * K2S_LSTR]; }
             for (; it + 2 <= nmy; it += 2) {
-                const int j0 = pj[0], j1 = pj[2 * K2S_LSTR];
-                const float e0 = pl[0], e1 = pl[2 * K2S_LSTR];
-                emit(j0, e0);
-                emit(j1, e1);
+                const uint2 w0 = window_rec(j0), w1 = window_rec(j1);
+                const int cj0 = j0, cj1 = j1;
+                const uint32_t pb0 = p_bits(e0), pb1 = p_bits(e1);
                 pl += 4 * K2S_LSTR;
                 pj += 4 * K2S_LSTR;
+                if (it + 4 <= nmy) { j0 = pj[0]; j1 = pj[2 * K2S_LSTR]; e0 = pl[0]; e1 = pl[2 * K2S_LSTR]; }
+                uint32_t v0, v1;
+                if (__uint_as_float(w0.x) >= 0.f && __uint_as_float(w1.x) >= 0.f) {
+                    v0 = fast_val(pb0, w0);
+                    v1 = fast_val(pb1, w1);
+                } else {
+                    v0 = any_val(pb0, w0);
+                    v1 = any_val(pb1, w1);
+                }
+                put(cj0, v0);
+                put(cj1, v1);
             }
-            if (it < nmy) emit(pj[0], pl[0]);
+            if (it < nmy) {
+                const int j = pj[0];
+                put(j, any_val(p_bits(pl[0]), window_rec(j)));
+            }
             MXP_PROF(g, 16);
             fence_proxy_async_smem();
             tcgen05_fence_before_sync();
