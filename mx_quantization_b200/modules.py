@@ -8,14 +8,14 @@ projection and their output projection:
 ``PrunedAttentionCore`` is that sequence (lines 101-152 of the DeiT file) as one call into
 libmxprune; the three shims keep the reference constructors' / ``set_config`` argument names so a
 maintainer can swap the body of ``forward`` (INTEGRATION.md shows the patch).  The qkv / output
-projections stay whatever the host model uses (``mx.Linear`` in the reference - outside the hot
-path); here they are plain ``nn.Linear`` unless the caller passes its own.
+projections are ``MxLinear`` (the reference's ``mx.Linear`` forward on the tcgen05 GEMM) when the shim is
+built with ``mx_quant=True``, else whatever the host model uses.
 
 Implemented: mx_quant && top_k && approx/ex_pred with pred_mode "ex_pred" (the pruned hot path),
-"partial_Q", "partial_K", "MXINT4", "two_step_leading_ones" or "true_ex"; mx_quant && top_k && !approx (top-k of the true scores); and
-mx_quant && !top_k (dense MXINT8 attention, what the reference runs in the last block of each
-model - same kernels with every key kept).  Every other combination (ELSA,
-mx_quant=False) raises - no silent fallback.
+"partial_Q", "partial_K", "MXINT4", "two_step_leading_ones", "true_ex" or "ELSA" (with the caller's orthogonal matrix);
+mx_quant && top_k && !approx (top-k of the true scores); and mx_quant && !top_k (dense MXINT8 attention, what the
+reference runs in the last block of each model - same kernels with every key kept).  mx_quant=False (the reference's
+unquantized torch path) raises - no silent fallback.
 """
 from typing import Optional
 
