@@ -1,5 +1,9 @@
 """Per-phase cycle accounting of the fused kernel (mxp_debug_fused_timing): where a group's thread 0 spends its time.
-    python tools/fused_timing.py [workload] [calls]"""
+    make -C mx_quantization_b200/csrc timing && MXPRUNE_LIB=.../libmxprune_timing.so timeout 120 python tools/fused_timing.py [workload] [calls]
+NOTE (round 2): the accounting build (-DMXP_FUSED_TIMING) DEADLOCKED on B200 in its last two runs (the command was killed by its
+time limit) and was not debugged; it also covers only the run-time head_dim instantiations (mxprune_fused64.cu is linked without
+the macro).  The per-phase shares under profiles/ come from tools/ncu_phases.py (ncu's per-instruction counts and stall samples)
+instead.  Run this only under `timeout`."""
 import os
 import sys
 from ctypes import c_void_p
