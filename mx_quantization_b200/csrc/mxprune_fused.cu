@@ -59,6 +59,7 @@ size_t fused_workspace_bytes(int Nq, int Nk, int hd) {
     return (size_t)2 * 160 * fused_slot_layout(Nq, Nk, hd).bytes;       // two groups per SM, up to 160 SMs
 }
 
+constexpr int FUSED_MIN_HEADS = 64;       // default policy: fewer heads take the three kernels (see fused_try)
 static std::atomic<unsigned long long*> g_fused_timing{nullptr};
 static std::atomic<int> g_fused_pingpong{1};
 void fused_set_pingpong(int on) { g_fused_pingpong = on; }
@@ -84,7 +85,11 @@ int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out) {
     if (g_fused_path.load() == 0 || g_attn_path.load() != 0 || g_predict_path.load() != 0) return 1;
     if (a.Nk > 256 || a.Nk <= 128 || a.hd < 32 || (a.hd & 7) || a.top_k >= a.Nk) return 1;
     const int heads = a.B * a.H;
-    if (heads < 64) return 1;
+    if (heads < (g_fused_path.load() == 2 ? 2 : FUSED_MIN_HEADS)) return 1;
+    // between one head per SM (both groups of a CTA share a head: 28 us per call at 96 - 144 heads against 31 - 32 us for the
+    // three kernels) and ~1.7 heads per SM every group holds a whole head for ~50 us while the three kernels spread the
+    // same heads over tiles and row splits (192 heads: 53 vs 47 us; 288 heads: 53 vs 58 us - tools/ab_small_heads.py)
+    if (g_fused_path.load() != 2 && heads > sm_count() && heads < (sm_count() * 27) / 16) return 1;
     const int nc = a.Nk <= 224 ? 7 : 8;
     const int nb = (a.hd + 31) / 32;
     const int G = fused_G(a.hd, nc), ring = fused_ring(a.hd, nc);
@@ -104,7 +109,9 @@ int fused_try(const FusedArgs& a, cudaStream_t st, int* rc_out) {
     const FusedSlotLayout S = fused_slot_layout(a.Nq, a.Nk, a.hd);
     int grid = sm_count();
     if (grid > 160) grid = 160;
-    if (grid > (heads + 1) / 2) grid = (heads + 1) / 2;
+    // up to one CTA per head: with heads <= SMs every CTA's two groups share one head (one query tile each - the kernel's
+    // shared-round rule), with up to twice that every group gets its own head on as many SMs as there are
+    if (grid > heads) grid = heads;
     if (!a.slots || a.slots_bytes < (size_t)2 * grid * S.bytes) return 1;
     FusedMaps maps;
     if (!make_view_maps(a.q, a.B, a.H, a.Nq, a.hd, &maps.q_main, &maps.q_tail)) return 1;
