@@ -29,7 +29,7 @@ timeout 120 python tools/prof_layer.py deit_base_c2 3 > gpurun_out/plain_full_$T
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_fused" -s 2 -c 1 \
     -o gpurun_out/prof_fused_$TAG python tools/prof_layer.py deit_base_c2 3 > gpurun_out/ncu_fused_$TAG.log 2>&1
 timeout 120 python tools/prof_layer.py deit_base_c2 3 three > gpurun_out/plain_three_$TAG.log 2>&1 &&
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_predict_topk_tc|k_attend_sparse|k_prep_v" -s 6 -c 3 \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_predict_topk_tc|k_attend_pair|k_prep_v" -s 3 -c 3 \
     -o gpurun_out/prof_three_$TAG python tools/prof_layer.py deit_base_c2 3 three > gpurun_out/ncu_three_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_three_$TAG.log
 timeout 500 python tools/sweep_c5.py --reps 3 --check > gpurun_out/c5_sweep_$TAG.jsonl 2> gpurun_out/c5_sweep_$TAG.err; tail -2 gpurun_out/c5_sweep_$TAG.jsonl | cut -c1-400
