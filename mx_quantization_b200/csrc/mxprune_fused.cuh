@@ -65,9 +65,9 @@ struct K1State {                 // phase-1 pipeline state carried from head to 
 
 // ---- phase 1 for one head.  bar_full[ring], bar_mma: the group's mbarriers (count 1).
 // HD: head_dim as a compile-time constant (0 = run time): with it every staging / operand offset of the quantize steps folds
-// NN: Nq == Nk as a compile-time constant (0 = run time).  Measured with NN = 197 (DeiT): no smaller code, 116 bytes of
-// spills at the 128-register cap, 5.40 -> 5.92 ms per DeiT-base step - so only NN = 0 is instantiated.
-template <int NC, int HG, bool BF16, int HD, int NN>
+// (The token count folded as well - 197 - gave no smaller code and 116 bytes of spills at the 128-register cap:
+// 5.40 -> 5.92 ms per DeiT-base step.  Not a template parameter.)
+template <int NC, int HG, bool BF16, int HD>
 __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uint64_t* bar_full, uint64_t* bar_mma,
                                                   const FusedParams& p, const FusedMaps& maps, const K1cSmem& L,
                                                   const OpsLayout& OL, int head, unsigned char* q_op, unsigned char* k_op,
@@ -80,7 +80,7 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
     constexpr int NWORDS = HW / 2;                                  // packed key words per lane
     constexpr int NLW = (HW + 31) / 32;                             // bitmask words per lane (lane-local bit order)
     static_assert(HG == 0 || ((REM == 8 || REM == 16) && 16 * HG <= 32 * NC && NWORDS % 4 == 0), "tight split");
-    const int Nk = NN ? NN : p.Nk, Nq = NN ? NN : p.Nq, hd = HD ? HD : p.hd, kk = p.top_k;
+    const int Nk = p.Nk, Nq = p.Nq, hd = HD ? HD : p.hd, kk = p.top_k;
     const int G = L.G, ring = L.ring;
     const int nfull = L.nfull, tail = L.tail, nb = L.nb;
     const int kch = L.hdp >> 3;                                     // 16-byte chunks per predictor-operand row
@@ -465,20 +465,20 @@ __device__ __forceinline__ void predict_topk_head(GroupCtx& gc, K1State& st, uin
 // The two phases of a head.  (Inlined: as separate functions the call ABI's callee-saved registers cost 0.5 - 1.2 KB
 // of spills per thread; inlined the kernel stays at the 128-register cap with a handful of spilled loop invariants.
 // Keep an eye on `-Xptxas -v`: spills next to in-flight tcgen05.ld results are not something to live with.)
-template <int NC, int HG, bool BF16, int HD, int NN>
+template <int NC, int HG, bool BF16, int HD>
 __device__ __forceinline__ void fused_phase1(GroupCtx& gc, K1State& st, uint64_t* bars, const FusedParams& p, const FusedMaps& maps,
                                           int head, unsigned char* slot, uint32_t* mask_head, int tile_begin, int tile_step) {
     const K1cSmem L1 = HD ? k1c_smem_layout(HD, NC, fused_ring(HD, NC), fused_G(HD, NC)) : k1c_smem_layout(p.hd, NC, p.ring, p.G);
-    const OpsLayout O = ops_layout(NN ? NN : p.Nq, NN ? NN : p.Nk, HD ? HD : p.hd);
-    predict_topk_head<NC, HG, BF16, HD, NN>(gc, st, &bars[0], &bars[K1C_MAXR], p, maps, L1, O, head, slot, slot + p.slot_k, slot + p.slot_v,
+    const OpsLayout O = ops_layout(p.Nq, p.Nk, HD ? HD : p.hd);
+    predict_topk_head<NC, HG, BF16, HD>(gc, st, &bars[0], &bars[K1C_MAXR], p, maps, L1, O, head, slot, slot + p.slot_k, slot + p.slot_v,
                               mask_head, tile_begin, tile_step);
 }
 // HD != 0: head_dim at compile time; such instantiations carry the cost-follows-k epilogue only (the launcher sends
 // dense-epilogue calls to the HD = 0 kernels)
-template <bool BF16, int HD, int NN>
+template <bool BF16, int HD>
 __device__ __forceinline__ void fused_phase2(GroupCtx& gc, const FusedParams& p, int head, const unsigned char* slot,
                                           const uint32_t* mask_head, int tile_begin, int tile_step) {
-    const int hd = HD ? HD : p.hd, Nq = NN ? NN : p.Nq, Nk = NN ? NN : p.Nk;
+    const int hd = HD ? HD : p.hd, Nq = p.Nq, Nk = p.Nk;
     const OpsLayout O = ops_layout(Nq, Nk, hd);
     const int bb = head / p.H, hh = head - bb * p.H;
     float* out_head = p.out + bb * p.o_sB + hh * p.o_sH;
@@ -493,8 +493,8 @@ __device__ __forceinline__ void fused_phase2(GroupCtx& gc, const FusedParams& p,
 }
 
 // NC, HG: key-column geometry of phase 1 (see k_predict_topk_tc); BF16: A1 rounding on (bfloat 16); HD: head_dim at
-// compile time (0 = any); NN: Nq == Nk at compile time (0 = any)
-template <int NC, int HG, bool BF16, int HD, int NN>
+// compile time (0 = any)
+template <int NC, int HG, bool BF16, int HD>
 __global__ void __launch_bounds__(FUSED_T, 1)
 k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_constant__ FusedMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem_fused[];
@@ -505,7 +505,7 @@ k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_con
     const int tid = threadIdx.x & 255;
     uint64_t* bars = s_bars[grp];
     const int heads = p.B * p.H;
-    const int Nq_ = NN ? NN : p.Nq, Nk_ = NN ? NN : p.Nk;
+    const int Nq_ = p.Nq, Nk_ = p.Nk;
     const int NW = (Nk_ + 31) >> 5;
     const bool has_tail = (p.hd & 31) != 0;
 
@@ -562,7 +562,7 @@ k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_con
             }
             group_sync(gc);
         }
-        fused_phase1<NC, HG, BF16, HD, NN>(gc, st, bars, p, maps, head, slot, mask_head, tile_begin, tile_step);
+        fused_phase1<NC, HG, BF16, HD>(gc, st, bars, p, maps, head, slot, mask_head, tile_begin, tile_step);
         // phase 1 -> phase 2: the slot's operands (generic-proxy global stores) are read back by TMA bulk copies
         // (async proxy), the masks by ordinary loads of other threads of the group; phase 2 also re-purposes the
         // shared memory that phase 1 wrote with generic stores as TMA destinations
@@ -573,7 +573,7 @@ k_fused_pruned_attention(const __grid_constant__ FusedParams p, const __grid_con
         tcgen05_fence_after_sync();
         if (lock && tid == 0) atomicExch(&s_lock, 0);               // every thread of the group has left phase 1
         MXP_PROF(gc, 21);
-        fused_phase2<BF16, HD, NN>(gc, p, head, slot, mask_head, tile_begin, tile_step);
+        fused_phase2<BF16, HD>(gc, p, head, slot, mask_head, tile_begin, tile_step);
         // phase 2 ends with fence.proxy.async + group barrier: its shared memory and TMEM may be reused, and its TMA
         // reads of the slot have completed (every copy was waited for), so the next head may overwrite the slot
     }
