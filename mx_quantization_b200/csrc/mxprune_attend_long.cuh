@@ -136,44 +136,36 @@ k_attend_long_pair(const AttnParams p) {
                 tma_bulk_g2s(sKb(s), k_op + (size_t)(blk + 2) * kbytes, kbytes, &bar_k[s]);
             }
             const uint32_t sb = my_tmem + (uint32_t)(s * 128);
-            // pass A (A7: bf16 rounding of the matmul output, * scale): maximum over the kept keys
-            float mb4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            // one TMEM read per window: t = bf16?(s) * scale (A7) stays in registers between the maximum over the kept keys
+            // and the exponentials; the running maximum / sum are updated window by window (online softmax)
 #pragma unroll 1
             for (int j = 0; j < 2; ++j) {
                 uint32_t r[32];
                 tmem_ld_16x32bx2_s64_x32(sb + 32 * j, r);
                 tmem_ld_wait();
                 const uint32_t mwj = j ? mw[1] : mw[0];
+                float mb4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     float sv = __uint_as_float(r[c]);
                     if (bf16) sv = bf16_half_away(sv);
                     const float tv = __fmul_rn(sv, scale);
+                    r[c] = __float_as_uint(tv);
                     mb4[c & 3] = fmaxf(mb4[c & 3], ((mwj >> c) & 1u) ? tv : -INFINITY);
                 }
-            }
-            const float mb = fmaxf(fmaxf(mb4[0], mb4[1]), fmaxf(mb4[2], mb4[3]));
-            const float m_new = fmaxf(m, mb);
-            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-            if (m != -INFINITY) l *= exp_nonpos(m - m_use);
-            // pass B: sum of exp(t - m) over the kept keys
-            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-                uint32_t r[32];
-                tmem_ld_16x32bx2_s64_x32(sb + 32 * j, r);
-                tmem_ld_wait();
-                const uint32_t mwj = j ? mw[1] : mw[0];
+                const float mb = fmaxf(fmaxf(mb4[0], mb4[1]), fmaxf(mb4[2], mb4[3]));
+                const float m_new = fmaxf(m, mb);
+                const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+                if (m != -INFINITY && m_new != m) l *= exp_nonpos(m - m_use);
+                float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    float sv = __uint_as_float(r[c]);
-                    if (bf16) sv = bf16_half_away(sv);
-                    const float ex = exp_nonpos(__fsub_rn(__fmul_rn(sv, scale), m_use));
+                    const float ex = exp_nonpos(__fsub_rn(__uint_as_float(r[c]), m_use));
                     sum4[c & 3] += ((mwj >> c) & 1u) ? ex : 0.f;
                 }
+                l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+                m = m_new;
             }
-            l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-            m = m_new;
             tcgen05_fence_before_sync();
             __syncthreads();                                        // every lane has read S(blk): its TMEM buffer is free
         }
