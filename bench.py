@@ -462,6 +462,12 @@ def main():
             roofline = {"bound": "hbm", "kernel": "predict_topk", "achieved": kernels["predict_topk"]["achieved_gbs"],
                         "peak": peak, "unit": "GB/s", "frac": kernels["predict_topk"]["frac"], "traffic": tj.get("predict_topk"),
                         "bytes_per_launch": kernels["predict_topk"]["bytes_per_launch"], "avg_ms": tms[0]}
+        # both denominators - the measured copy bandwidth (peak, above) and the north star's nominal ~8 TB/s
+        NOMINAL_GBS = 8000.0
+        for kv in kernels.values():
+            kv["frac_of_nominal_8tbs"] = kv["achieved_gbs"] / NOMINAL_GBS
+        roofline.update({"frac_of_nominal_8tbs": roofline["achieved"] / NOMINAL_GBS,
+                         "full_path_frac_of_nominal_8tbs": full_gbs / NOMINAL_GBS})
         roofline.update({"peak_source": peak_src, "full_path_gbs": full_gbs, "full_path_frac": full_gbs / peak,
                          "three_kernel_path": {"note": "the same call with mxp_set_fused_path(0): per-kernel CUDA-event times "
                                                        "against each kernel's bytes (predict_topk: SURVEY 8(d)'s 8 N hd + 4 N ceil(N/32); "

@@ -75,7 +75,11 @@ def main():
                     "kernel_ms": {"predict_topk": km[0], "prep_v": km[1], "exact_attention": km[2]},
                     "predict_topk_gbs": bph["predict_topk"] * B * H / (km[0] * 1e-3) / 1e9,
                     "predict_topk_frac_of_hbm": bph["predict_topk"] * B * H / (km[0] * 1e-3) / 1e9 / peak,
-                    "full_path_gbs": bph["full"] * B * H / (ms * 1e-3) / 1e9}
+                    "full_path_gbs": bph["full"] * B * H / (ms * 1e-3) / 1e9,
+                    # at long N the predictor is bound by its N^2 nb block scorings, not by bytes - report that
+                    # fraction too: (block scorings / s) against the 16 POPC lanes/clk/SM x SMs x clock the survey assumes
+                    "predict_block_scorings_per_s": float(N) * N * ((hd + 31) // 32) * B * H / (km[0] * 1e-3),
+                    "predict_frac_of_popc_issue_peak": float(N) * N * ((hd + 31) // 32) * B * H / (km[0] * 1e-3) / (16 * 148 * 1.965e9)}
             if args.check and rank == 0:
                 from oracle import mxint8_oracle as O
                 print("check: gpu slice", file=sys.stderr, flush=True)
