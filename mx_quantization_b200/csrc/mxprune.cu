@@ -766,7 +766,7 @@ static int try_predict_topk_long_tc(const PredParams& p, cudaStream_t st, int* r
     if (W.total == 0 || !p.long_ws || p.long_ws_bytes < W.total || ((uintptr_t)p.long_ws & 255)) return 1;
     const OpsLayout O = ops_layout(p.Nq, p.Nk, p.hd);
     const KLSmem L = kl_smem_layout(O);
-    if (L.total > 232448 / 2 - 1024) return 1;
+    if (L.total > 227 * 1024) return 1;
     unsigned char* w = (unsigned char*)p.long_ws;
     const int heads = p.B * p.H, nb = (p.hd + 31) / 32;
     uint32_t* head_meta = (uint32_t*)(w + W.head_meta);
@@ -806,14 +806,14 @@ static int try_predict_topk_long_tc(const PredParams& p, cudaStream_t st, int* r
         sp.q_pp = w + W.q_pp; sp.k_pp = w + W.k_pp; sp.q_ep = (const int8_t*)(w + W.q_ep);
         sp.head_meta = head_meta; sp.flags = flags; sp.mask = p.mask; sp.idx = p.idx;
         sp.H = p.H; sp.Nq = p.Nq; sp.Nk = p.Nk; sp.hd = p.hd; sp.top_k = p.top_k;
-        // a tile is ~Nk/256 times the work of a short-kernel tile: spread tiles over enough CTAs for
-        // >= 8 waves of the 296 resident CTAs (a CTA's fixed cost is small next to one tile)
-        int splits = (148 * 2 * 8 + heads - 1) / heads;
-        if (splits > O.q_tiles) splits = O.q_tiles;
+        sp.adaptive = g_fused_path.load() != 0;                     // mxp_set_fused_path(0): radix levels only (A/B)
+        // one CTA (a pair of query tiles) per SM - its shared memory and 512 TMEM columns fill it; a pair is
+        // ~Nk/128 times the work of a short-kernel tile: spread the pairs over enough CTAs for >= 8 waves
+        const int n_pairs = (O.q_tiles + 1) / 2;
+        int splits = (148 * 8 + heads - 1) / heads;
+        if (splits > n_pairs) splits = n_pairs;
         if (splits < 1) splits = 1;
-        size_t dyn = L.total;
-        const size_t floor_bytes = (size_t)232448 / 3 + 1024;       // two CTAs per SM: 2 x 256 TMEM columns
-        if (dyn < floor_bytes) dyn = floor_bytes;
+        const size_t dyn = L.total;
         k_select_long_tc<<<dim3((unsigned)heads, (unsigned)splits), KL_T, dyn, st>>>(sp);
         if ((*rc_out = check_launch("k_select_long_tc"))) return 0;
     }

@@ -22,9 +22,11 @@
 
 namespace mxp {
 
-constexpr int KL_T = 256;             // threads per CTA: two lanes per query row
+constexpr int KL_T = 512;             // threads per CTA: a pair of query tiles, two lanes per query row
 constexpr int KL_TILE = 128;          // query rows per tile
-constexpr int KL_BINS = 64;
+constexpr int KL_BINS = 64;           // bins of a radix level
+constexpr int KL_FBINS = 128;         // bins of the fine window (adaptive front end)
+constexpr int KL_MAX_RANGE = 1400;    // widest sample key range the fine window takes on
 
 // ------------------------------------------------------------------------------------------
 // k_quantize_ops: fp32 (B,H,N,hd) view -> MMA-ready bf16 operands in HBM, one thread per MX block.
@@ -110,22 +112,37 @@ struct LongSelParams {
     uint32_t* mask;
     int32_t* idx;
     int H, Nq, Nk, hd, top_k;
+    int adaptive;                   // 1: sampled fine window in front of the radix levels (see below)
 };
 
 struct KLSmem {
     size_t off_k, off_hist, off_misc, total;
+    int bins;
 };
 __host__ __device__ inline KLSmem kl_smem_layout(const OpsLayout& O) {
     KLSmem L;
-    size_t o = O.q_tile_bytes;
+    size_t o = 2 * O.q_tile_bytes;
     L.off_k = o;    o += 2 * O.k_blk_bytes;
-    L.off_hist = o; o += (size_t)KL_BINS * KL_T * 2;
+    // the fine window wants 128 counters per lane; head dims whose operand tiles leave no room keep 64
+    L.bins = (o + (size_t)KL_FBINS * KL_T * 2 + 128 <= (size_t)227 * 1024) ? KL_FBINS : KL_BINS;
+    L.off_hist = o; o += (size_t)L.bins * KL_T * 2;
     L.off_misc = o; o += 128;
     L.total = o;
     return L;
 }
 
-__global__ void __launch_bounds__(KL_T, 2)
+// One CTA = one PAIR of 128-row query tiles of one head (16 warps: warps 0-7 the even tile, 8-15 the odd
+// one; 512 TMEM columns = two score buffers per tile) sharing every K block it streams.
+//
+// Adaptive front end (p.adaptive): a radix level resolves 6 bits of a key whose STATIC width is 11-13
+// bits, while a row's keys really spread over a few hundred values around a threshold that a sample
+// predicts well.  So: (1) score the first 256 keys once (both TMEM buffers), take their min / max and a
+// 128-bin histogram, and read off the sample's top_k/Nk quantile c; (2) ONE pass over all keys with
+// 126 exact bins for the keys c-63 .. c+62 and two clamp bins; if the k-th largest key falls into an
+// exact bin the row has its threshold and tie count, and the emit pass follows: two passes instead of
+// three or four.  A row whose sample spreads too far for the window, or whose threshold lands in a clamp
+// bin, sends its tile pair through the radix levels - same result, the old cost.
+__global__ void __launch_bounds__(KL_T, 1)
 k_select_long_tc(const LongSelParams p) {
     extern __shared__ __align__(1024) unsigned char smem_kl[];
     unsigned char* const smem = smem_kl;
@@ -141,29 +158,33 @@ k_select_long_tc(const LongSelParams p) {
     uint64_t* bar_q = bar_k + 4;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_k + 5);
     int* s_nlev = reinterpret_cast<int*>(s_tmem + 1);
+    int* s_gen = s_nlev + 1;                            // 1: this tile pair takes the radix levels
 
     const int head = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int lane_base = 32 * (warp & 3) + 16 * (warp >> 2);
+    const int half = warp >> 3, w8 = warp & 7;          // which tile of the pair; warp within the tile
+    const int lane_base = 32 * (w8 & 3) + 16 * (w8 >> 2);
     const int rr = lane_base + (lane & 15);             // row of the tile
     const int part = lane >> 4;                         // keys [64 part, 64 part + 64) of every block
     const unsigned char* q_pp = p.q_pp + (size_t)head * O.q_head_bytes;
     const unsigned char* k_pp = p.k_pp + (size_t)head * O.k_head_bytes;
     const int q_rows_pad = O.q_tiles * KL_TILE;
+    const int n_pairs = (O.q_tiles + 1) >> 1;
 
     if (tid == 0) {
         mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1);
         mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1);
         mbar_init(bar_q, 1);
     }
-    if (warp == 0) tmem_alloc(s_tmem, 256u);
+    if (warp == 0) tmem_alloc(s_tmem, 512u);
     tcgen05_fence_before_sync();
     __syncthreads();
     tcgen05_fence_after_sync();
     const uint32_t tmem = *s_tmem;
     const uint32_t my_lane = (uint32_t)lane_base << 16;
+    const uint32_t my_col = (uint32_t)(half * 256);     // this tile's two 128-column score buffers
     const uint32_t idesc = umma_idesc_bf16_f32(128, 128);
-    uint32_t ph_k[2] = {0u, 0u}, ph_m[2] = {0u, 0u}, ph_q = 0u;
+    uint32_t ph_k = 0u, ph_m = 0u, ph_q = 0u;           // bit s = phase of barrier s (registers, not a local array)
 
     int kmin[4], spread[4];
     bool wide = false;
@@ -185,19 +206,36 @@ k_select_long_tc(const LongSelParams p) {
     unsigned short* my_hist = s_hist + hslot;           // bin b at my_hist[b * KL_T]
     const unsigned short* their_hist = s_hist + ((warp >> 1) * 64 + 2 * (lane ^ 16) + (warp & 1));
 
-    for (int tile = blockIdx.y; tile < O.q_tiles; tile += gridDim.y) {
+    for (int pt = blockIdx.y; pt < n_pairs; pt += gridDim.y) {
+        const int nh = 2 * pt + 1 < O.q_tiles ? 2 : 1;  // tiles of this pair
+        const int tile = 2 * pt + half;
         const int i = tile * KL_TILE + rr;
-        const bool valid = i < Nq;
+        const bool valid = half < nh && i < Nq;
         const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
         if (tid == 0) {
             *s_nlev = 0;
-            mbar_expect_tx(bar_q, (uint32_t)O.q_tile_bytes);
-            tma_bulk_g2s(sQ, q_pp + (size_t)tile * O.q_tile_bytes, (uint32_t)O.q_tile_bytes, bar_q);
+            *s_gen = (p.adaptive && L.bins == KL_FBINS) ? 0 : 1;
+            mbar_expect_tx(bar_q, (uint32_t)(nh * O.q_tile_bytes));
+            tma_bulk_g2s(sQ, q_pp + (size_t)(2 * pt) * O.q_tile_bytes, (uint32_t)(nh * O.q_tile_bytes), bar_q);
         }
+        // K block in sK[s] x the pair's query tiles -> score buffer s of each tile (thread 0 only)
+        auto issue_mma = [&](int s) {
+            tcgen05_fence_after_sync();
+            const unsigned char* kb = sK + (size_t)s * O.k_blk_bytes;
+            for (int h = 0; h < nh; ++h) {
+                const unsigned char* qt = sQ + (size_t)h * O.q_tile_bytes;
+                for (int ks = 0; ks < (O.hdp >> 4); ++ks) {
+                    const uint64_t da = umma_smem_desc(smem_u32(qt + (size_t)(2 * ks) * KL_TILE * 16), KL_TILE * 16, 128);
+                    const uint64_t db = umma_smem_desc(smem_u32(kb + (size_t)(2 * ks) * 128 * 16), 128 * 16, 128);
+                    umma_bf16_ss(tmem + (uint32_t)(h * 256 + s * 128), da, db, idesc, ks > 0);
+                }
+            }
+            umma_commit(&bar_mma[s]);
+        };
         // ---- integer-key parameters of this thread's row (same window rules as the short kernels)
         int epq[4];
         {
-            const int8_t* e4 = p.q_ep + ((size_t)head * q_rows_pad + i) * 4;
+            const int8_t* e4 = p.q_ep + ((size_t)head * q_rows_pad + (half < nh ? i : 0)) * 4;
 #pragma unroll
             for (int b = 0; b < 4; ++b) epq[b] = b < nb ? (int)e4[b] : 0;
         }
@@ -221,7 +259,6 @@ k_select_long_tc(const LongSelParams p) {
         if (!fast) M = 0;
         const int moff = ((int)M + 1) & ~1;
         const float scl = fast ? exp2i(-g - 1) : 0.f;
-        // keys carry the fp16 bias of the short kernel (two keys per word compare with one HSET2)
         // histogram passes rank on the plain key u = S/2 + moff/2 + 1 (fewest digits); the emit pass adds
         // the fp16 bias of the short kernel so that two keys per word compare with one HSET2
         const uint32_t key0 = (uint32_t)((moff >> 1) + 1);          // key of a score of exactly 0
@@ -239,16 +276,96 @@ k_select_long_tc(const LongSelParams p) {
         mbar_wait(bar_q, ph_q);
         ph_q ^= 1u;
 
+        // ---- adaptive front end, step 1: the sample (key blocks 0 and 1, scored once into both buffers)
+        // worth it when sample (~5 block steps) + fine + emit beat the nlev + 1 passes of the radix select
+        bool adapt = nlev > 0 && *s_gen == 0 && 5 + 2 * nblk < (nlev + 1) * nblk;
+        int lo_key = 0;                                             // fine bin e <-> key lo_key + e
+        if (adapt) {
+            if (tid == 0) {
+                for (int b = 0; b < 2; ++b) {
+                    mbar_expect_tx(&bar_k[b], (uint32_t)O.k_blk_bytes);
+                    tma_bulk_g2s(sK + (size_t)b * O.k_blk_bytes, k_pp + (size_t)b * O.k_blk_bytes, (uint32_t)O.k_blk_bytes, &bar_k[b]);
+                }
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_wait(&bar_k[b], (ph_k >> b) & 1u);
+                ph_k ^= 1u << b;
+                if (tid == 0) issue_mma(b);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_wait(&bar_mma[b], (ph_m >> b) & 1u);
+                ph_m ^= 1u << b;
+            }
+            tcgen05_fence_after_sync();
+            const bool any_fast = __any_sync(FULL, fast);
+            const uint32_t tbase = tmem + my_lane + my_col;
+            float fmn = 3.0e38f, fmx = 0.f;
+            if (any_fast) {
+#pragma unroll 1
+                for (int q4 = 0; q4 < 4; ++q4) {                    // buffer q4 >> 1, this lane's columns 32 (q4 & 1) + c
+                    uint32_t r[32];
+                    tmem_ld_16x32bx2_s64_x32(tbase + (q4 >> 1) * 128 + (q4 & 1) * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float f = fmaf(__uint_as_float(r[c]), scl, cadd);
+                        fmn = fminf(fmn, f);
+                        fmx = fmaxf(fmx, f);
+                    }
+                }
+            }
+            fmn = fminf(fmn, __shfl_xor_sync(FULL, fmn, 16));
+            fmx = fmaxf(fmx, __shfl_xor_sync(FULL, fmx, 16));
+            const int umin = (int)(__float_as_uint(fmn) & 0xffffu), umax = (int)(__float_as_uint(fmx) & 0xffffu);
+            const int range = fast ? umax - umin : 0;
+            const int csh = 32 - __clz(range >> 7);                 // (range >> csh) < 128
+            for (int b = 0; b < KL_FBINS; ++b) my_hist[b * KL_T] = 0;
+            if (any_fast) {
+#pragma unroll 1
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint32_t r[32];
+                    tmem_ld_16x32bx2_s64_x32(tbase + (q4 >> 1) * 128 + (q4 & 1) * 32, r);
+                    tmem_ld_wait();
+                    if (fast) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int u = (int)(__float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0xffffu);
+                            my_hist[((u - umin) >> csh) * KL_T] += 1;
+                        }
+                    }
+                }
+            }
+            __syncwarp();                                           // the partner lane's column is complete
+            if (fast) {
+                const int ks = max(1, (kk * 256 + (Nk >> 1)) / Nk); // the sample's share of top_k
+                int cum = 0, bin = KL_FBINS - 1;
+                for (; bin > 0; --bin) {
+                    const int h = (int)my_hist[bin * KL_T] + (int)their_hist[bin * KL_T];
+                    if (cum + h >= ks) break;
+                    cum += h;
+                }
+                lo_key = umin + (bin << csh) + ((1 << csh) >> 1) - KL_FBINS / 2;
+                if (range > KL_MAX_RANGE) atomicOr(s_gen, 1);       // too wide for the window: radix levels
+            }
+            tcgen05_fence_before_sync();
+            __syncthreads();                                        // score buffers free again; *s_gen final
+            adapt = *s_gen == 0;
+        }
+        const int lo_bits = 0x4B000000 + lo_key;                    // bits of 2^23 + lo_key
+
         uint32_t prefix = 0u;
         int krem = kk;
-        // passes 0..nlev-1: histogram levels; pass nlev: emit (skipped when no row of the tile is fast)
+        // pass -1: the fine window (adaptive only); passes 0..nlev-1: radix levels; pass nlev: emit
+        // (no pass at all when no row of the pair is fast)
         const int npass = nlev > 0 ? nlev + 1 : 0;
-        for (int pass = 0; pass < npass; ++pass) {
+        for (int pass = adapt ? -1 : 0; pass < npass; ++pass) {
+            const bool fine = pass < 0;
             const bool emit = pass == nlev;
             const int lo = 6 * (my_lev - 1 - pass);                 // < 0: this row already has its full key
-            const bool counting = !emit && fast && lo >= 0;
+            const bool counting = fine ? fast : (!emit && fast && lo >= 0);
             if (!emit) {
-                for (int b = 0; b < KL_BINS; ++b) my_hist[b * KL_T] = 0;
+                const int nbins = fine ? KL_FBINS : KL_BINS;
+                for (int b = 0; b < nbins; ++b) my_hist[b * KL_T] = 0;
             }
             int rem = krem, pos = 0;                                // emit state (identical in both lanes)
             const uint32_t T = prefix + K1_KEY_BIAS;                // emit compares biased keys
@@ -262,30 +379,21 @@ k_select_long_tc(const LongSelParams p) {
             for (int it = 0; it <= nblk; ++it) {
                 if (it < nblk) {
                     const int s = it & 1;
-                    mbar_wait(&bar_k[s], ph_k[s]);
-                    ph_k[s] ^= 1u;
-                    if (tid == 0) {
-                        tcgen05_fence_after_sync();
-                        const unsigned char* kb = sK + (size_t)s * O.k_blk_bytes;
-                        for (int ks = 0; ks < (O.hdp >> 4); ++ks) {
-                            const uint64_t da = umma_smem_desc(smem_u32(sQ + (size_t)(2 * ks) * KL_TILE * 16), KL_TILE * 16, 128);
-                            const uint64_t db = umma_smem_desc(smem_u32(kb + (size_t)(2 * ks) * 128 * 16), 128 * 16, 128);
-                            umma_bf16_ss(tmem + (uint32_t)(s * 128), da, db, idesc, ks > 0);
-                        }
-                        umma_commit(&bar_mma[s]);
-                    }
+                    mbar_wait(&bar_k[s], (ph_k >> s) & 1u);
+                    ph_k ^= 1u << s;
+                    if (tid == 0) issue_mma(s);
                 }
                 if (it > 0) {
                     const int j = it - 1, s = j & 1;
-                    mbar_wait(&bar_mma[s], ph_m[s]);
-                    ph_m[s] ^= 1u;
+                    mbar_wait(&bar_mma[s], (ph_m >> s) & 1u);
+                    ph_m ^= 1u << s;
                     tcgen05_fence_after_sync();
                     if (tid == 0 && j + 2 < nblk) {                 // MMA j has finished reading sK[s]
                         mbar_expect_tx(&bar_k[s], (uint32_t)O.k_blk_bytes);
                         tma_bulk_g2s(sK + (size_t)s * O.k_blk_bytes, k_pp + (size_t)(j + 2) * O.k_blk_bytes,
                                      (uint32_t)O.k_blk_bytes, &bar_k[s]);
                     }
-                    const uint32_t tbase = tmem + my_lane + (uint32_t)(s * 128);
+                    const uint32_t tbase = tmem + my_lane + my_col + (uint32_t)(s * 128);
                     if (!emit) {
                         if (__any_sync(FULL, counting)) {
 #pragma unroll 1
@@ -294,7 +402,13 @@ k_select_long_tc(const LongSelParams p) {
                                 tmem_ld_16x32bx2_s64_x32(tbase + q2 * 32, r);
                                 tmem_ld_wait();
                                 if (counting) {
-                                    if (pass == 0) {                // no prefix yet: every key counts
+                                    if (fine) {                     // clamp(key - lo_key, 0, 127): one VIADDMNMX
+#pragma unroll
+                                        for (int c = 0; c < 32; ++c) {
+                                            const int ub = __float_as_int(fmaf(__uint_as_float(r[c]), scl, cadd));
+                                            my_hist[__viaddmin_s32_relu(ub, -lo_bits, KL_FBINS - 1) * KL_T] += 1;
+                                        }
+                                    } else if (pass == 0) {         // no prefix yet: every key counts
 #pragma unroll
                                         for (int c = 0; c < 32; ++c) {
                                             const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd));
@@ -374,7 +488,27 @@ k_select_long_tc(const LongSelParams p) {
                 tcgen05_fence_before_sync();
                 __syncthreads();                                    // TMEM buffer of block j is free again
             }
-            if (!emit) {
+            if (fine) {
+                // the zero rows of Kp all scored key0: discount them (each lane its own columns)
+                if (counting && my_npad > 0)
+                    my_hist[__viaddmin_s32_relu((int)key0, -lo_key, KL_FBINS - 1) * KL_T] -= (unsigned short)my_npad;
+                __syncwarp();                                       // the partner lane's column is complete
+                int cum = 0, bin = KL_FBINS - 1;
+                if (counting) {
+                    for (; bin > 0; --bin) {
+                        const int h = (int)my_hist[bin * KL_T] + (int)their_hist[bin * KL_T];
+                        if (cum + h >= kk) break;
+                        cum += h;
+                    }
+                    if (bin == 0 || bin == KL_FBINS - 1) atomicOr(s_gen, 1);    // threshold in a clamp bin
+                }
+                __syncthreads();                                    // (also: both lanes have scanned)
+                if (*s_gen == 0) {                                  // every row of the pair has its threshold
+                    prefix = (uint32_t)(lo_key + bin);
+                    krem = kk - cum;
+                    pass = nlev - 1;                                // next: emit
+                }
+            } else if (!emit) {
                 // the zero rows of Kp all scored key0: discount them (each lane its own columns)
                 if (counting && my_npad > 0 && (key0 >> (lo + 6)) == prefix)
                     my_hist[((key0 >> lo) & 63u) * KL_T] -= (unsigned short)my_npad;
@@ -395,7 +529,7 @@ k_select_long_tc(const LongSelParams p) {
     }
     tcgen05_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256u);
+    if (warp == 0) tmem_dealloc(tmem, 512u);
 }
 
 }  // namespace mxp
