@@ -27,6 +27,9 @@ constexpr int KL_TILE = 128;          // query rows per tile
 constexpr int KL_BINS = 64;           // bins of a radix level
 constexpr int KL_FBINS = 128;         // bins of the fine window (adaptive front end)
 constexpr int KL_MAX_RANGE = 1400;    // widest sample key range the fine window takes on
+constexpr int KL_WIDE_M = 1 << 21;    // largest |S| bound (in key units) of a row this kernel ranks: every partial sum of the
+                                      // score is an integer below 2^22 - exact in fp32 in any order, and the products span
+                                      // <= 16 bits, inside the tensor core's measured exact window (profiles/r01_umma_exactness)
 
 // ------------------------------------------------------------------------------------------
 // k_quantize_ops: fp32 (B,H,N,hd) view -> MMA-ready bf16 operands in HBM, one thread per MX block.
@@ -131,6 +134,30 @@ __host__ __device__ inline KLSmem kl_smem_layout(const OpsLayout& O) {
     return L;
 }
 
+// gt / eq bit masks of one 32-key window against the row's threshold: keys (c, c + 16) packed per register and compared as
+// fp16 bit patterns (one HSET2 per two keys).  Narrow rows (|S| bound <= K1_MAX_M): the key itself, biased into the
+// normal fp16 range.  WIDE: the key re-centred on the threshold and clamped, max(min(u - T + 0x4000, 0x7BFF), 0) - one
+// VIADDMNMX more per key; the clamp only moves keys that are far from T, so the classification is exact for any width.
+template <bool WIDE>
+__device__ __forceinline__ void kl_compare_window(const uint32_t (&r)[32], float scl, float cadd, int aw, __half2 t2,
+                                                  uint32_t& gt_out, uint32_t& eq_out) {
+    uint32_t gt = 0u, eq = 0u;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        uint32_t fl = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd));
+        uint32_t fh = __float_as_uint(fmaf(__uint_as_float(r[c + 16]), scl, cadd));
+        if (WIDE) {
+            fl = (uint32_t)__viaddmin_s32_relu((int)fl, aw, 0x7BFF);
+            fh = (uint32_t)__viaddmin_s32_relu((int)fh, aw, 0x7BFF);
+        }
+        const __half2 kv = u32_as_h2(__byte_perm(fl, fh, 0x5410));
+        gt |= __hgt2_mask(kv, t2) & (0x00010001u << c);
+        eq |= __heq2_mask(kv, t2) & (0x00010001u << c);
+    }
+    gt_out = gt;
+    eq_out = eq;
+}
+
 // One CTA = one PAIR of 128-row query tiles of one head (16 warps: warps 0-7 the even tile, 8-15 the odd
 // one; 512 TMEM columns = two score buffers per tile) sharing every K block it streams.
 //
@@ -159,6 +186,7 @@ k_select_long_tc(const LongSelParams p) {
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_k + 5);
     int* s_nlev = reinterpret_cast<int*>(s_tmem + 1);
     int* s_gen = s_nlev + 1;                            // 1: this tile pair takes the radix levels
+    int* s_wide = s_nlev + 2;                           // 1: some row of the pair has keys wider than 15 bits
 
     const int head = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -214,6 +242,7 @@ k_select_long_tc(const LongSelParams p) {
         const int64_t row = (int64_t)head * Nq + (valid ? i : 0);
         if (tid == 0) {
             *s_nlev = 0;
+            *s_wide = 0;
             *s_gen = (p.adaptive && L.bins == KL_FBINS) ? 0 : 1;
             mbar_expect_tx(bar_q, (uint32_t)(nh * O.q_tile_bytes));
             tma_bulk_g2s(sQ, q_pp + (size_t)(2 * pt) * O.q_tile_bytes, (uint32_t)(nh * O.q_tile_bytes), bar_q);
@@ -254,7 +283,8 @@ k_select_long_tc(const LongSelParams p) {
                 M += (long long)nbw << (sh + min(spread[b], K1_MAX_SPREAD));
             }
         }
-        if (M > K1_MAX_M) fast = false;
+        if (M > KL_WIDE_M) fast = false;
+        const bool narrow = M <= K1_MAX_M;                          // keys fit the 15-bit fp16 patterns of the short kernels
         if (valid && part == 0) p.flags[row] = fast ? 0 : 1;
         if (!fast) M = 0;
         const int moff = ((int)M + 1) & ~1;
@@ -269,10 +299,15 @@ k_select_long_tc(const LongSelParams p) {
         __syncthreads();                                            // *s_nlev = 0 visible
         {
             const int wl = __reduce_max_sync(FULL, fast ? my_lev : 0);
-            if (lane == 0) atomicMax(s_nlev, wl);
+            const bool ww = __any_sync(FULL, fast && !narrow);
+            if (lane == 0) {
+                atomicMax(s_nlev, wl);
+                if (ww) atomicOr(s_wide, 1);
+            }
         }
         __syncthreads();
         const int nlev = *s_nlev;
+        const bool wide_pair = *s_wide != 0;
         mbar_wait(bar_q, ph_q);
         ph_q ^= 1u;
 
@@ -316,7 +351,7 @@ k_select_long_tc(const LongSelParams p) {
             }
             fmn = fminf(fmn, __shfl_xor_sync(FULL, fmn, 16));
             fmx = fmaxf(fmx, __shfl_xor_sync(FULL, fmx, 16));
-            const int umin = (int)(__float_as_uint(fmn) & 0xffffu), umax = (int)(__float_as_uint(fmx) & 0xffffu);
+            const int umin = (int)(__float_as_uint(fmn) & 0x7fffffu), umax = (int)(__float_as_uint(fmx) & 0x7fffffu);
             const int range = fast ? umax - umin : 0;
             const int csh = 32 - __clz(range >> 7);                 // (range >> csh) < 128
             for (int b = 0; b < KL_FBINS; ++b) my_hist[b * KL_T] = 0;
@@ -329,7 +364,7 @@ k_select_long_tc(const LongSelParams p) {
                     if (fast) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
-                            const int u = (int)(__float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0xffffu);
+                            const int u = (int)(__float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0x7fffffu);
                             my_hist[((u - umin) >> csh) * KL_T] += 1;
                         }
                     }
@@ -368,7 +403,9 @@ k_select_long_tc(const LongSelParams p) {
                 for (int b = 0; b < nbins; ++b) my_hist[b * KL_T] = 0;
             }
             int rem = krem, pos = 0;                                // emit state (identical in both lanes)
-            const uint32_t T = prefix + K1_KEY_BIAS;                // emit compares biased keys
+            // emit compares fp16 patterns: the biased key against T + bias, or (wide pair) the key re-centred on T against 0x4000
+            const uint32_t T = wide_pair ? 0x4000u : prefix + K1_KEY_BIAS;
+            const int aw = 0x4000 - (0x4B000000 + (int)prefix);
             if (tid == 0) {
                 const int pre = min(2, nblk);
                 for (int b = 0; b < pre; ++b) {
@@ -417,7 +454,7 @@ k_select_long_tc(const LongSelParams p) {
                                     } else {
 #pragma unroll
                                         for (int c = 0; c < 32; ++c) {
-                                            const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0xffffu;
+                                            const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0x7fffffu;
                                             if ((u >> (lo + 6)) == prefix) my_hist[((u >> lo) & 63u) * KL_T] += 1;
                                         }
                                     }
@@ -435,15 +472,9 @@ k_select_long_tc(const LongSelParams p) {
                             uint32_t r[32];
                             tmem_ld_16x32bx2_s64_x32(tbase + q2 * 32, r);
                             tmem_ld_wait();
-                            uint32_t gt = 0u, eq = 0u;
-#pragma unroll
-                            for (int c = 0; c < 16; ++c) {
-                                const uint32_t fl = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd_e));
-                                const uint32_t fh = __float_as_uint(fmaf(__uint_as_float(r[c + 16]), scl, cadd_e));
-                                const __half2 kv = u32_as_h2(__byte_perm(fl, fh, 0x5410));
-                                gt |= __hgt2_mask(kv, t2) & (0x00010001u << c);
-                                eq |= __heq2_mask(kv, t2) & (0x00010001u << c);
-                            }
+                            uint32_t gt, eq;
+                            if (wide_pair) kl_compare_window<true>(r, scl, cadd, aw, t2, gt, eq);
+                            else kl_compare_window<false>(r, scl, cadd_e, 0, t2, gt, eq);
                             const int nv = Nk - (j * 128 + 64 * part + 32 * q2);
                             const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : (1u << nv) - 1u);
                             gtw[q2] = gt & vm;

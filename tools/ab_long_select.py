@@ -67,6 +67,11 @@ def main():
                     mxq.set_fused_path(1)
                     got = mxq.predict_topk(q, k, specs, top_k, return_idx=True)
                     ok = torch.equal(want["mask"], got["mask"]) and torch.equal(want["idx"], got["idx"])
+                    if r == 0.25:                       # and both against the CUDA-core integer kernel (no tensor core, no 15-bit window)
+                        mxq.set_predict_path("cuda_core")
+                        core = mxq.predict_topk(q, k, specs, top_k, return_idx=True)
+                        mxq.set_predict_path("tcgen05")
+                        ok = ok and torch.equal(core["mask"], got["mask"]) and torch.equal(core["idx"], got["idx"])
                     bad += 0 if ok else 1
                     if not ok:
                         rows = (want["mask"] != got["mask"]).any(-1).sum().item()
