@@ -187,6 +187,7 @@ k_select_long_tc(const LongSelParams p) {
     int* s_nlev = reinterpret_cast<int*>(s_tmem + 1);
     int* s_gen = s_nlev + 1;                            // 1: this tile pair takes the radix levels
     int* s_wide = s_nlev + 2;                           // 1: some row of the pair has keys wider than 15 bits
+    int* s_l2 = s_nlev + 3;                             // 1: some row's fine bins hold more than one key value
 
     const int head = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -243,6 +244,7 @@ k_select_long_tc(const LongSelParams p) {
         if (tid == 0) {
             *s_nlev = 0;
             *s_wide = 0;
+            *s_l2 = 0;
             *s_gen = (p.adaptive && L.bins == KL_FBINS) ? 0 : 1;
             mbar_expect_tx(bar_q, (uint32_t)(nh * O.q_tile_bytes));
             tma_bulk_g2s(sQ, q_pp + (size_t)(2 * pt) * O.q_tile_bytes, (uint32_t)(nh * O.q_tile_bytes), bar_q);
@@ -314,7 +316,7 @@ k_select_long_tc(const LongSelParams p) {
         // ---- adaptive front end, step 1: the sample (key blocks 0 and 1, scored once into both buffers)
         // worth it when sample (~5 block steps) + fine + emit beat the nlev + 1 passes of the radix select
         bool adapt = nlev > 0 && *s_gen == 0 && 5 + 2 * nblk < (nlev + 1) * nblk;
-        int lo_key = 0;                                             // fine bin e <-> key lo_key + e
+        int lo_key = 0, fs = 0;                                     // fine bin e <-> keys [lo_key + (e << fs), + 2^fs)
         if (adapt) {
             if (tid == 0) {
                 for (int b = 0; b < 2; ++b) {
@@ -379,25 +381,37 @@ k_select_long_tc(const LongSelParams p) {
                     if (cum + h >= ks) break;
                     cum += h;
                 }
-                lo_key = umin + (bin << csh) + ((1 << csh) >> 1) - KL_FBINS / 2;
-                if (range > KL_MAX_RANGE) atomicOr(s_gen, 1);       // too wide for the window: radix levels
+                // bins of one key value while the sample spreads over <= KL_MAX_RANGE values; beyond that bins of 2^fs
+                // values (window >= 0.18 of the sample range) and one more level for the digit inside the bin
+                if (range > KL_MAX_RANGE) fs = 32 - __clz(range / (KL_MAX_RANGE / 2));
+                const int c_est = umin + (bin << csh) + ((1 << csh) >> 1);
+                lo_key = ((c_est >> fs) - KL_FBINS / 2) << fs;
+                if (fs > 6) atomicOr(s_gen, 1);                     // too wide even so: radix levels
+                else if (fs > 0) atomicOr(s_l2, 1);
             }
             tcgen05_fence_before_sync();
             __syncthreads();                                        // score buffers free again; *s_gen final
             adapt = *s_gen == 0;
         }
-        const int lo_bits = 0x4B000000 + lo_key;                    // bits of 2^23 + lo_key
+        const bool pair_l2 = adapt && *s_l2 != 0;
+        const int lo_sh = (0x4B000000 + lo_key) >> fs;              // (bits of 2^23 + lo_key) >> fs; lo_key is a multiple of 2^fs
 
         uint32_t prefix = 0u;
         int krem = kk;
-        // pass -1: the fine window (adaptive only); passes 0..nlev-1: radix levels; pass nlev: emit
-        // (no pass at all when no row of the pair is fast)
-        const int npass = nlev > 0 ? nlev + 1 : 0;
-        for (int pass = adapt ? -1 : 0; pass < npass; ++pass) {
-            const bool fine = pass < 0;
-            const bool emit = pass == nlev;
-            const int lo = 6 * (my_lev - 1 - pass);                 // < 0: this row already has its full key
+        // pass sequence of the pair (uniform): [fine window -> (one level for the digit inside a bin)] or
+        // [nlev radix levels], then emit; no pass at all when no row of the pair is fast.  A level counts digit
+        // (u >> lo_cur) & (2^dbits - 1) among the keys whose higher bits equal prefix (per-thread lo_cur / dbits).
+        enum { P_FINE, P_LEVEL, P_EMIT, P_DONE };
+        int kind = nlev == 0 ? P_DONE : (adapt ? P_FINE : P_LEVEL);
+        int levels_left = nlev;
+        bool first_level = true;                                    // first radix level: no prefix yet, every key counts
+        int lo_cur = 6 * (my_lev - 1), dbits = 6;
+        while (kind != P_DONE) {
+            const bool fine = kind == P_FINE;
+            const bool emit = kind == P_EMIT;
+            const int lo = lo_cur;                                  // < 0: this row already has its full key
             const bool counting = fine ? fast : (!emit && fast && lo >= 0);
+            const uint32_t dmask = (1u << dbits) - 1u;
             if (!emit) {
                 const int nbins = fine ? KL_FBINS : KL_BINS;
                 for (int b = 0; b < nbins; ++b) my_hist[b * KL_T] = 0;
@@ -439,13 +453,19 @@ k_select_long_tc(const LongSelParams p) {
                                 tmem_ld_16x32bx2_s64_x32(tbase + q2 * 32, r);
                                 tmem_ld_wait();
                                 if (counting) {
-                                    if (fine) {                     // clamp(key - lo_key, 0, 127): one VIADDMNMX
+                                    if (fine && !pair_l2) {         // clamp(key - lo_key, 0, 127): one VIADDMNMX
 #pragma unroll
                                         for (int c = 0; c < 32; ++c) {
                                             const int ub = __float_as_int(fmaf(__uint_as_float(r[c]), scl, cadd));
-                                            my_hist[__viaddmin_s32_relu(ub, -lo_bits, KL_FBINS - 1) * KL_T] += 1;
+                                            my_hist[__viaddmin_s32_relu(ub, -lo_sh, KL_FBINS - 1) * KL_T] += 1;
                                         }
-                                    } else if (pass == 0) {         // no prefix yet: every key counts
+                                    } else if (fine) {              // bins of 2^fs keys (per row)
+#pragma unroll
+                                        for (int c = 0; c < 32; ++c) {
+                                            const int ub = __float_as_int(fmaf(__uint_as_float(r[c]), scl, cadd));
+                                            my_hist[__viaddmin_s32_relu(ub >> fs, -lo_sh, KL_FBINS - 1) * KL_T] += 1;
+                                        }
+                                    } else if (first_level) {       // no prefix yet: every key counts
 #pragma unroll
                                         for (int c = 0; c < 32; ++c) {
                                             const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd));
@@ -455,7 +475,7 @@ k_select_long_tc(const LongSelParams p) {
 #pragma unroll
                                         for (int c = 0; c < 32; ++c) {
                                             const uint32_t u = __float_as_uint(fmaf(__uint_as_float(r[c]), scl, cadd)) & 0x7fffffu;
-                                            if ((u >> (lo + 6)) == prefix) my_hist[((u >> lo) & 63u) * KL_T] += 1;
+                                            if ((u >> (lo + dbits)) == prefix) my_hist[((u >> lo) & dmask) * KL_T] += 1;
                                         }
                                     }
                                 }
@@ -522,7 +542,7 @@ k_select_long_tc(const LongSelParams p) {
             if (fine) {
                 // the zero rows of Kp all scored key0: discount them (each lane its own columns)
                 if (counting && my_npad > 0)
-                    my_hist[__viaddmin_s32_relu((int)key0, -lo_key, KL_FBINS - 1) * KL_T] -= (unsigned short)my_npad;
+                    my_hist[__viaddmin_s32_relu((0x4B000000 + (int)key0) >> fs, -lo_sh, KL_FBINS - 1) * KL_T] -= (unsigned short)my_npad;
                 __syncwarp();                                       // the partner lane's column is complete
                 int cum = 0, bin = KL_FBINS - 1;
                 if (counting) {
@@ -534,27 +554,38 @@ k_select_long_tc(const LongSelParams p) {
                     if (bin == 0 || bin == KL_FBINS - 1) atomicOr(s_gen, 1);    // threshold in a clamp bin
                 }
                 __syncthreads();                                    // (also: both lanes have scanned)
-                if (*s_gen == 0) {                                  // every row of the pair has its threshold
-                    prefix = (uint32_t)(lo_key + bin);
+                if (*s_gen == 0) {                                  // every row of the pair has its threshold bin
+                    prefix = (uint32_t)((lo_key >> fs) + bin);      // = key >> fs
                     krem = kk - cum;
-                    pass = nlev - 1;                                // next: emit
+                    first_level = false;
+                    lo_cur = fs > 0 ? 0 : -1;                       // rows with wider bins: one level for the low fs bits
+                    dbits = fs;
+                    levels_left = 1;
+                    kind = pair_l2 ? P_LEVEL : P_EMIT;
+                } else {
+                    kind = P_LEVEL;                                 // the radix levels, from the top
                 }
             } else if (!emit) {
                 // the zero rows of Kp all scored key0: discount them (each lane its own columns)
-                if (counting && my_npad > 0 && (key0 >> (lo + 6)) == prefix)
-                    my_hist[((key0 >> lo) & 63u) * KL_T] -= (unsigned short)my_npad;
+                if (counting && my_npad > 0 && (key0 >> (lo + dbits)) == prefix)
+                    my_hist[((key0 >> lo) & dmask) * KL_T] -= (unsigned short)my_npad;
                 __syncwarp();                                       // the partner lane's column is complete
                 if (counting) {
-                    int cum = 0, bin = KL_BINS - 1;
+                    int cum = 0, bin = (int)dmask;
                     for (; bin > 0; --bin) {
                         const int h = (int)my_hist[bin * KL_T] + (int)their_hist[bin * KL_T];
                         if (cum + h >= krem) break;
                         cum += h;
                     }
                     krem -= cum;
-                    prefix = (prefix << 6) | (uint32_t)bin;
+                    prefix = (prefix << dbits) | (uint32_t)bin;
                 }
                 __syncwarp();                                       // both lanes have scanned before the next zeroing
+                first_level = false;
+                lo_cur -= 6;
+                if (--levels_left == 0) kind = P_EMIT;
+            } else {
+                kind = P_DONE;
             }
         }
     }
