@@ -146,22 +146,27 @@ k_attend_long_pair(const AttnParams p) {
                 const uint32_t mwj = j ? mw[1] : mw[0];
                 float mb4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
+                for (int c = 0; c < 32; ++c) {                      // dropped keys become -inf: no part in the maximum, exp = 0
                     float sv = __uint_as_float(r[c]);
                     if (bf16) sv = bf16_half_away(sv);
-                    const float tv = __fmul_rn(sv, scale);
+                    const float tv = ((mwj >> c) & 1u) ? __fmul_rn(sv, scale) : -INFINITY;
                     r[c] = __float_as_uint(tv);
-                    mb4[c & 3] = fmaxf(mb4[c & 3], ((mwj >> c) & 1u) ? tv : -INFINITY);
+                    mb4[c & 3] = fmaxf(mb4[c & 3], tv);
                 }
                 const float mb = fmaxf(fmaxf(mb4[0], mb4[1]), fmaxf(mb4[2], mb4[3]));
                 const float m_new = fmaxf(m, mb);
                 const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
                 if (m != -INFINITY && m_new != m) l *= exp_nonpos(m - m_use);
+                // this pass only needs the row SUM: 2^((t - m) log2 e) straight from MUFU.EX2 (<= 2 ulp per term, the
+                // argument error grows with |t - m|, i.e. only where the term no longer matters) - the sum keeps the
+                // relative accuracy of the exact-argument form used for P in pass 2, at a third of the instructions
                 float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    const float ex = exp_nonpos(__fsub_rn(__uint_as_float(r[c]), m_use));
-                    sum4[c & 3] += ((mwj >> c) & 1u) ? ex : 0.f;
+                    const float d2 = __fmul_rn(__fsub_rn(__uint_as_float(r[c]), m_use), 1.4426950408889634f);
+                    float ex;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(d2));
+                    sum4[c & 3] += ex;
                 }
                 l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
                 m = m_new;
