@@ -453,17 +453,27 @@ k_select_long_tc(const LongSelParams p) {
                                 tmem_ld_16x32bx2_s64_x32(tbase + q2 * 32, r);
                                 tmem_ld_wait();
                                 if (counting) {
-                                    if (fine && !pair_l2) {         // clamp(key - lo_key, 0, 127): one VIADDMNMX
+                                    // fine window: bin = clamp((key - lo_key) >> fs, 0, 127), one VIADDMNMX.  The counter
+                                    // updates go in PAIRS - both loads issued before either store, the second store adding
+                                    // 2 when the bins coincide - so that two shared-memory round trips overlap (the loop is
+                                    // bound by that latency, not by issue slots)
+                                    if (fine && !pair_l2) {
 #pragma unroll
-                                        for (int c = 0; c < 32; ++c) {
-                                            const int ub = __float_as_int(fmaf(__uint_as_float(r[c]), scl, cadd));
-                                            my_hist[__viaddmin_s32_relu(ub, -lo_sh, KL_FBINS - 1) * KL_T] += 1;
+                                        for (int c = 0; c < 32; c += 2) {
+                                            const int e0 = __viaddmin_s32_relu(__float_as_int(fmaf(__uint_as_float(r[c]), scl, cadd)), -lo_sh, KL_FBINS - 1);
+                                            const int e1 = __viaddmin_s32_relu(__float_as_int(fmaf(__uint_as_float(r[c + 1]), scl, cadd)), -lo_sh, KL_FBINS - 1);
+                                            const unsigned short v0 = my_hist[e0 * KL_T], v1 = my_hist[e1 * KL_T];
+                                            my_hist[e0 * KL_T] = (unsigned short)(v0 + 1);
+                                            my_hist[e1 * KL_T] = (unsigned short)(v1 + (e0 == e1 ? 2 : 1));
                                         }
                                     } else if (fine) {              // bins of 2^fs keys (per row)
 #pragma unroll
-                                        for (int c = 0; c < 32; ++c) {
-                                            const int ub = __float_as_int(fmaf(__uint_as_float(r[c]), scl, cadd));
-                                            my_hist[__viaddmin_s32_relu(ub >> fs, -lo_sh, KL_FBINS - 1) * KL_T] += 1;
+                                        for (int c = 0; c < 32; c += 2) {
+                                            const int e0 = __viaddmin_s32_relu(__float_as_int(fmaf(__uint_as_float(r[c]), scl, cadd)) >> fs, -lo_sh, KL_FBINS - 1);
+                                            const int e1 = __viaddmin_s32_relu(__float_as_int(fmaf(__uint_as_float(r[c + 1]), scl, cadd)) >> fs, -lo_sh, KL_FBINS - 1);
+                                            const unsigned short v0 = my_hist[e0 * KL_T], v1 = my_hist[e1 * KL_T];
+                                            my_hist[e0 * KL_T] = (unsigned short)(v0 + 1);
+                                            my_hist[e1 * KL_T] = (unsigned short)(v1 + (e0 == e1 ? 2 : 1));
                                         }
                                     } else if (first_level) {       // no prefix yet: every key counts
 #pragma unroll
