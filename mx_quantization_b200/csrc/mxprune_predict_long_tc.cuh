@@ -313,23 +313,25 @@ k_select_long_tc(const LongSelParams p) {
         mbar_wait(bar_q, ph_q);
         ph_q ^= 1u;
 
-        // ---- adaptive front end, step 1: the sample (key blocks 0 and 1, scored once into both buffers)
-        // worth it when sample (~5 block steps) + fine + emit beat the nlev + 1 passes of the radix select
-        bool adapt = nlev > 0 && *s_gen == 0 && 5 + 2 * nblk < (nlev + 1) * nblk;
+        // ---- adaptive front end, step 1: the sample (key blocks 0 and 1 - block 0 alone for short rows - scored once
+        // into the score buffers); worth it when sample (~2.5 block steps per sampled block) + fine + emit beat the
+        // nlev + 1 passes of the radix select
+        const int nsamp = nblk >= 8 ? 2 : 1;
+        bool adapt = nlev > 0 && *s_gen == 0 && 5 * nsamp + 4 * nblk < 2 * (nlev + 1) * nblk;
         int lo_key = 0, fs = 0;                                     // fine bin e <-> keys [lo_key + (e << fs), + 2^fs)
         if (adapt) {
             if (tid == 0) {
-                for (int b = 0; b < 2; ++b) {
+                for (int b = 0; b < nsamp; ++b) {
                     mbar_expect_tx(&bar_k[b], (uint32_t)O.k_blk_bytes);
                     tma_bulk_g2s(sK + (size_t)b * O.k_blk_bytes, k_pp + (size_t)b * O.k_blk_bytes, (uint32_t)O.k_blk_bytes, &bar_k[b]);
                 }
             }
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < nsamp; ++b) {
                 mbar_wait(&bar_k[b], (ph_k >> b) & 1u);
                 ph_k ^= 1u << b;
                 if (tid == 0) issue_mma(b);
             }
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < nsamp; ++b) {
                 mbar_wait(&bar_mma[b], (ph_m >> b) & 1u);
                 ph_m ^= 1u << b;
             }
@@ -339,7 +341,7 @@ k_select_long_tc(const LongSelParams p) {
             float fmn = 3.0e38f, fmx = 0.f;
             if (any_fast) {
 #pragma unroll 1
-                for (int q4 = 0; q4 < 4; ++q4) {                    // buffer q4 >> 1, this lane's columns 32 (q4 & 1) + c
+                for (int q4 = 0; q4 < 2 * nsamp; ++q4) {                    // buffer q4 >> 1, this lane's columns 32 (q4 & 1) + c
                     uint32_t r[32];
                     tmem_ld_16x32bx2_s64_x32(tbase + (q4 >> 1) * 128 + (q4 & 1) * 32, r);
                     tmem_ld_wait();
@@ -359,7 +361,7 @@ k_select_long_tc(const LongSelParams p) {
             for (int b = 0; b < KL_FBINS; ++b) my_hist[b * KL_T] = 0;
             if (any_fast) {
 #pragma unroll 1
-                for (int q4 = 0; q4 < 4; ++q4) {
+                for (int q4 = 0; q4 < 2 * nsamp; ++q4) {
                     uint32_t r[32];
                     tmem_ld_16x32bx2_s64_x32(tbase + (q4 >> 1) * 128 + (q4 & 1) * 32, r);
                     tmem_ld_wait();
@@ -374,7 +376,7 @@ k_select_long_tc(const LongSelParams p) {
             }
             __syncwarp();                                           // the partner lane's column is complete
             if (fast) {
-                const int ks = max(1, (kk * 256 + (Nk >> 1)) / Nk); // the sample's share of top_k
+                const int ks = max(1, (kk * 128 * nsamp + (Nk >> 1)) / Nk);    // the sample's share of top_k
                 int cum = 0, bin = KL_FBINS - 1;
                 for (; bin > 0; --bin) {
                     const int h = (int)my_hist[bin * KL_T] + (int)their_hist[bin * KL_T];
