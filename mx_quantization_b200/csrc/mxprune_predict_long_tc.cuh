@@ -316,7 +316,7 @@ k_select_long_tc(const LongSelParams p) {
         // ---- adaptive front end, step 1: the sample (key blocks 0 and 1 - block 0 alone for short rows - scored once
         // into the score buffers); worth it when sample (~2.5 block steps per sampled block) + fine + emit beat the
         // nlev + 1 passes of the radix select
-        const int nsamp = nblk >= 8 ? 2 : 1;
+        const int nsamp = nblk >= 16 ? 2 : 1;                      // measured: N = 1024 better with one block, 2048 with two
         bool adapt = nlev > 0 && *s_gen == 0 && 5 * nsamp + 4 * nblk < 2 * (nlev + 1) * nblk;
         int lo_key = 0, fs = 0;                                     // fine bin e <-> keys [lo_key + (e << fs), + 2^fs)
         if (adapt) {
