@@ -814,7 +814,8 @@ static int try_predict_topk_long_tc(const PredParams& p, cudaStream_t st, int* r
         if (splits > n_pairs) splits = n_pairs;
         if (splits < 1) splits = 1;
         const size_t dyn = L.total;
-        k_select_long_tc<<<dim3((unsigned)heads, (unsigned)splits), KL_T, dyn, st>>>(sp);
+        sp.splits = splits;
+        k_select_long_tc<<<dim3((unsigned)((size_t)heads * splits)), KL_T, dyn, st>>>(sp);
         if ((*rc_out = check_launch("k_select_long_tc"))) return 0;
     }
     // rows outside the integer-key window: the CUDA-core kernel, restricted to the flagged rows

@@ -52,7 +52,10 @@ k_attend_long_pair(const AttnParams p) {
     auto sVb = [&](int b) { return smem + L.off_v0 + (size_t)b * (L.off_v1 - L.off_v0); };
     unsigned char* const sP = smem + L.off_p;
     unsigned char* const sQ = smem + L.off_q;
-    const int head = blockIdx.x, bb = head / p.H, hh = head % p.H;
+    // linear grid, query tile fastest: the CTAs resident at one time belong to a handful of heads, whose K / V operands
+    // (streamed twice / once per tile) then come from L2 - head-fastest order had every head's operands in flight at once
+    // (ncu at N = 4096: 16 GB of DRAM reads for 0.7 GB of operands)
+    const int head = blockIdx.x / O.q_tiles, bb = head / p.H, hh = head % p.H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int lane_base = 32 * (warp & 3) + 16 * (warp >> 2);
     const int rr = lane_base + (lane & 15);                         // row of the tile
@@ -92,7 +95,7 @@ k_attend_long_pair(const AttnParams p) {
         umma_commit(bar);
     };
 
-    for (int tile = blockIdx.y; tile < O.q_tiles; tile += gridDim.y) {
+    for (int tile = blockIdx.x % O.q_tiles; tile < O.q_tiles; tile += O.q_tiles) {      // one tile per CTA
         const int i = tile * K2T + rr;
         const bool valid = i < Nq;
         const uint32_t* mrow = p.mask + ((size_t)head * Nq + (valid ? i : 0)) * NW;

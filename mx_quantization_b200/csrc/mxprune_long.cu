@@ -22,7 +22,7 @@ int attend_long_pair_try(const AttnParams& p, cudaStream_t st, int* rc_out) {
         MXP_ENSURE_DYN_SMEM((k_attend_long_pair<false>), (int)(SMEM_PER_SM - 2048));
         // one CTA per query tile (a CTA holds nothing across tiles); 256 TMEM columns per CTA: at most two CTAs per SM,
         // which the dynamic shared-memory request enforces (see launch_attend_umma)
-        dim3 grid((unsigned)(p.B * p.H), (unsigned)O.q_tiles);
+        dim3 grid((unsigned)((size_t)p.B * p.H * O.q_tiles));
         size_t dyn = L.total;
         const size_t floor_bytes = SMEM_PER_SM / 3 + 1024;
         if (dyn < floor_bytes) dyn = floor_bytes;

@@ -116,6 +116,7 @@ struct LongSelParams {
     int32_t* idx;
     int H, Nq, Nk, hd, top_k;
     int adaptive;                   // 1: sampled fine window in front of the radix levels (see below)
+    int splits;                     // CTAs per head (linear grid, a head's CTAs adjacent: its Kp operand stays in L2)
 };
 
 struct KLSmem {
@@ -189,7 +190,7 @@ k_select_long_tc(const LongSelParams p) {
     int* s_wide = s_nlev + 2;                           // 1: some row of the pair has keys wider than 15 bits
     int* s_l2 = s_nlev + 3;                             // 1: some row's fine bins hold more than one key value
 
-    const int head = blockIdx.x;
+    const int head = blockIdx.x / p.splits;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = warp >> 3, w8 = warp & 7;          // which tile of the pair; warp within the tile
     const int lane_base = 32 * (w8 & 3) + 16 * (w8 >> 2);
@@ -235,7 +236,7 @@ k_select_long_tc(const LongSelParams p) {
     unsigned short* my_hist = s_hist + hslot;           // bin b at my_hist[b * KL_T]
     const unsigned short* their_hist = s_hist + ((warp >> 1) * 64 + 2 * (lane ^ 16) + (warp & 1));
 
-    for (int pt = blockIdx.y; pt < n_pairs; pt += gridDim.y) {
+    for (int pt = blockIdx.x % p.splits; pt < n_pairs; pt += p.splits) {
         const int nh = 2 * pt + 1 < O.q_tiles ? 2 : 1;  // tiles of this pair
         const int tile = 2 * pt + half;
         const int i = tile * KL_TILE + rr;
