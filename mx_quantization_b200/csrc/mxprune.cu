@@ -813,6 +813,9 @@ static int try_predict_topk_long_tc(const PredParams& p, cudaStream_t st, int* r
         int splits = (148 * 8 + heads - 1) / heads;
         if (splits > n_pairs) splits = n_pairs;
         if (splits < 1) splits = 1;
+        // equal shares where the pair count allows: the next divisor of n_pairs (N = 4096: 16 pairs over 8 CTAs, not 4 + 3 + 3 + 3 + 3)
+        for (int d = splits; d <= n_pairs && d <= 2 * splits; ++d)
+            if (n_pairs % d == 0) { splits = d; break; }
         const size_t dyn = L.total;
         sp.splits = splits;
         k_select_long_tc<<<dim3((unsigned)((size_t)heads * splits)), KL_T, dyn, st>>>(sp);
