@@ -31,6 +31,9 @@ def make_qkv(B, H, N, hd, seed=0, kind="randn", Nk=None):
         q = q * torch.exp(1.5 * torch.randn(B, H, N, 1, generator=g))
         k = k * torch.exp(1.5 * torch.randn(B, H, Nk, 1, generator=g))
         v = v * torch.exp(0.5 * torch.randn(B, H, Nk, 1, generator=g))
+    if kind == "lognormal05":           # moderate per-token scale spread: key windows of 16-21 bits at long N
+        q = q * torch.exp(0.5 * torch.randn(B, H, N, 1, generator=g))
+        k = k * torch.exp(0.5 * torch.randn(B, H, Nk, 1, generator=g))
     if kind == "edges":
         q[0, 0, 3 % N] = 0.0
         k[0, 0, 5 % Nk] = 0.0

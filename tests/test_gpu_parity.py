@@ -452,6 +452,8 @@ def test_exact_attention_long_sequences(mxq, B, H, N, hd, bfloat):
     (1, 3, 333, 64, "randn", 16, 0.2),
     (1, 1, 4096, 72, "randn", 32, 0.1),            # C5's largest point (BASELINE.json configs[4]), both ends of the ratio range
     (1, 1, 4096, 72, "randn", 32, 0.5),
+    (1, 2, 1536, 72, "lognormal05", 32, 0.25),     # keys wider than 15 bits stay on the tensor-core selection; bins of 2^fs keys
+    (1, 1, 2304, 64, "lognormal05", 16, 0.1),
 ])
 @pytest.mark.parametrize("pred_path", ["tcgen05", "cuda_core"])
 def test_long_sequence_end_to_end(mxq, B, H, N, hd, kind, bfloat, kfrac, pred_path):
@@ -466,6 +468,54 @@ def test_long_sequence_end_to_end(mxq, B, H, N, hd, kind, bfloat, kfrac, pred_pa
         _long_e2e(mxq, q, k, v, specs, top_k, N, bfloat)
     finally:
         mxq.set_predict_path("tcgen05")
+
+
+def _long_inputs(kind, H, N, hd, seed):
+    g = torch.Generator().manual_seed(seed)
+    q, k = torch.randn(1, H, N, hd, generator=g), torch.randn(1, H, N, hd, generator=g)
+    if kind.startswith("lognormal"):
+        s = float(kind[len("lognormal"):])
+        q = q * torch.exp(s * torch.randn(1, H, N, 1, generator=g))
+        k = k * torch.exp(s * torch.randn(1, H, N, 1, generator=g))
+    elif kind == "ties":                # few distinct key rows: long runs of equal scores
+        k = k[:, :, :7].repeat(1, 1, (N + 6) // 7, 1)[:, :, :N].contiguous()
+    elif kind == "constant":            # every key row the same: all scores of a row tie
+        k = k[:, :, :1].expand(1, H, N, hd).contiguous()
+    elif kind == "zeros":               # zero keys in the second half, zero query rows here and there
+        k[:, :, N // 2:] = 0.0
+        q[:, :, ::17] = 0.0
+    elif kind == "skewed":              # the sampled first keys misrepresent the rest of the row
+        k[:, :, :256] *= 0.05
+        k[:, :, 256:] += 0.5
+    elif kind == "outliers":            # a few huge keys widen the static key window
+        k[:, :, 5::511] *= 40.0
+        q[:, :, 3::97, :32] *= 0.01
+    return q, k
+
+
+@pytest.mark.parametrize("kind", ["randn", "lognormal0.25", "lognormal0.5", "lognormal1.5", "ties", "constant", "zeros",
+                                  "skewed", "outliers"])
+@pytest.mark.parametrize("N,hd,kfrac", [(640, 72, 0.25), (1100, 64, 0.1), (2048, 72, 0.5)])
+def test_long_selection_paths_agree(mxq, kind, N, hd, kfrac):
+    """The long-sequence selection (k_select_long_tc) resolves a row's threshold three ways - sampled fine window (bins of one
+    or of 2^fs key values), the radix levels alone (fused path 0), and, outside the tensor-core window, the CUDA-core integer
+    kernel: masks AND index lists must be identical, whatever the input does to the sample (funcs: main.py:118-123 top-k of
+    the predicted scores; the canonical tie rule of SURVEY 8a)."""
+    q, k = _long_inputs(kind, 2, N, hd, seed=N + hd)
+    specs = mx_specs(32, False)
+    top_k = max(1, int(kfrac * N))
+    res = {}
+    try:
+        for name, fused, pred in (("fine", 1, "tcgen05"), ("radix", 0, "tcgen05"), ("core", 1, "cuda_core")):
+            mxq.set_fused_path(fused)
+            mxq.set_predict_path(pred)
+            res[name] = mxq.predict_topk(q.cuda(), k.cuda(), specs, top_k, return_idx=True)
+    finally:
+        mxq.set_fused_path(True)
+        mxq.set_predict_path("tcgen05")
+    for name in ("radix", "core"):
+        assert torch.equal(res["fine"]["mask"], res[name]["mask"]), f"fine window vs {name}: masks differ"
+        assert torch.equal(res["fine"]["idx"], res[name]["idx"]), f"fine window vs {name}: index lists differ"
 
 
 def _long_e2e(mxq, q, k, v, specs, top_k, N, bfloat):
