@@ -160,16 +160,12 @@ k_attend_long_pair(const AttnParams p) {
                 const float m_new = fmaxf(m, mb);
                 const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
                 if (m != -INFINITY && m_new != m) l *= exp_nonpos(m - m_use);
-                // this pass only needs the row SUM: 2^((t - m) log2 e) straight from MUFU.EX2 (<= 2 ulp per term, the
-                // argument error grows with |t - m|, i.e. only where the term no longer matters) - the sum keeps the
-                // relative accuracy of the exact-argument form used for P in pass 2, at a third of the instructions
+                // 2^((t - m) log2 e) straight from MUFU.EX2 (exp_fast_nonpos: <= 2 ulp per term, the argument error
+                // grows with |t - m|, i.e. only where the term no longer matters), a third of exp_nonpos's instructions
                 float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    const float d2 = __fmul_rn(__fsub_rn(__uint_as_float(r[c]), m_use), 1.4426950408889634f);
-                    float ex;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(d2));
-                    sum4[c & 3] += ex;
+                    sum4[c & 3] += exp_fast_nonpos(__fsub_rn(__uint_as_float(r[c]), m_use));
                 }
                 l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
                 m = m_new;
@@ -234,7 +230,7 @@ k_attend_long_pair(const AttnParams p) {
                 for (int c = 0; c < 32; ++c) {
                     float sv = __uint_as_float(r[c]);
                     if (bf16) sv = bf16_half_away(sv);
-                    const float ex = exp_nonpos(__fsub_rn(__fmul_rn(sv, scale), m_fin));
+                    const float ex = exp_fast_nonpos(__fsub_rn(__fmul_rn(sv, scale), m_fin));      // as in pass 1: sum(p) stays 1
                     const float ev = ((mwj >> c) & 1u) ? ex : 0.f;
                     uint32_t pb = __float_as_uint(ev * inv);
                     if (bf16) pb = bf16_half_away(pb);

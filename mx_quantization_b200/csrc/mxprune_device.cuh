@@ -143,6 +143,16 @@ __device__ __forceinline__ float exp_nonpos(float x) {
     return __uint_as_float(__float_as_uint(r) + (__float_as_uint(t) << 23));
 }
 
+// exp(x), x <= 0, for the streamed long-sequence kernel: MUFU.EX2 on fl(x * log2 e).  Relative error <= 2 ulp (MUFU) +
+// 0.9e-7 |x| (the rounded product; -inf and anything below -87.3 give +0).  The second term only grows where exp(x) no longer
+// matters: a key 10 below the row maximum carries 4.5e-5 of its weight and 9e-7 of relative error, and can change an MXINT8
+// code of P only in a 32-key window whose every key is that small (one step there is < 1e-6 of the row's largest p).
+__device__ __forceinline__ float exp_fast_nonpos(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(x, 1.4426950408889634f)));
+    return r;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
