@@ -4,7 +4,7 @@
 TAG=${1:-r02d}
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.txt 2>&1; tail -2 gpurun_out/pytest_gpu_$TAG.txt
-timeout 500 python tools/sweep_c5.py --reps 5 --check > gpurun_out/c5_sweep_$TAG.jsonl 2> gpurun_out/c5_sweep_$TAG.err
+timeout 500 python tools/sweep_c5.py --reps 3 --check > gpurun_out/c5_sweep_$TAG.jsonl 2> gpurun_out/c5_sweep_$TAG.err
 python - <<PY
 import json
 for l in open("gpurun_out/c5_sweep_$TAG.jsonl"):
