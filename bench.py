@@ -40,6 +40,10 @@ WORKLOADS = {
     "pixart_c4": dict(B=256, H=16, N=256, hd=72, top_k=77, layers=28, bfloat=32, flush=True),
     "deit_tiny_c1": dict(B=8, H=3, N=197, hd=64, top_k=80, layers=1, bfloat=32, flush=False),
 }
+# device-timed only, as an `other_workloads` entry of the default line (the long-sequence kernels; tools/sweep_c5.py has the sweep)
+LONG_WORKLOADS = {
+    "dit_long_c5": dict(B=16, H=16, N=4096, hd=72, top_k=1024, layers=1, bfloat=32, flush=False),   # BASELINE.json configs[4], N = 4096
+}
 CPU_SAMPLE_B = 8          # cpu_baseline / reference arm: a B=8 slice of one layer
 
 
@@ -412,8 +416,8 @@ def main():
         others = {}
         del layers
         torch.cuda.empty_cache()
-        for oname in ("dit_xl2_c3", "pixart_c4"):
-            ow = WORKLOADS[oname]
+        for oname in ("dit_xl2_c3", "pixart_c4", "dit_long_c5"):
+            ow = WORKLOADS.get(oname) or LONG_WORKLOADS[oname]
             ol = make_layers(torch, ow, dev, 7)
             oo = torch.empty(ow["B"], ow["N"], ow["H"], ow["hd"], device=dev).permute(0, 2, 1, 3)
             osp = mx_specs(ow["bfloat"], ow["flush"])
