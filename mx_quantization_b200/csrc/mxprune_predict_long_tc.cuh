@@ -1,22 +1,21 @@
 // K1-long-TC: the fused quantizer + exponent-sign predictor + exact top-k for Nk > 256 (the
 // long-sequence sweep, config C5) with the scores on the tensor cores.
 //
-// A row's keys no longer fit in registers or shared memory, so the selection is a most-significant-
-// digit radix select that RE-SCORES the row in every pass - which is what the tensor core makes
-// cheap: a pass streams the head's predictor operand Kp (bf16 +-2^e, MMA-ready, written once per
-// head by k_quantize_ops) through shared memory in blocks of 128 keys, one tcgen05.mma per block
-// into one of two TMEM buffers, and the threads read their scores back with tcgen05.ld.16x32bx2:
-// a warp owns 16 query rows, lanes l and l + 16 share row l and take keys [0,64) / [64,128) of the block.
-//   pass 0..L-1  per-thread histogram (64 bins x 6 bits per level, [bin][thread] in shared memory:
-//                conflict-free, no atomics) of the current digit among keys whose higher digits
-//                equal the prefix found so far; the two lanes of a row add their columns when they
-//                scan from the top bin for the digit of the k-th key
-//   last pass    emit: keys > T kept, keys == T kept in ascending index until top_k
-// Keys are the exact 15-bit integers of the short kernels (score * 2^(-g-1) + offset, read from the
-// low mantissa bits of one FFMA).  Rows outside that window are flagged and left to the CUDA-core
-// kernel (k_predict_topk_long, row-filtered), which handles any exponents.
-// Pipeline per pass: TMA bulk copy of block j+2 and the MMA of block j+1 run while the threads
-// histogram block j.
+// A row's keys no longer fit in registers or shared memory, so the selection RE-SCORES the row in every pass - which is
+// what the tensor core makes cheap: a pass streams the head's predictor operand Kp (bf16 +-2^e, MMA-ready, written once per
+// head by k_quantize_ops) through shared memory in blocks of 128 keys, one tcgen05.mma per block and query tile into one of
+// two TMEM buffers, and the threads read their scores back with tcgen05.ld.16x32bx2: a warp owns 16 query rows, lanes l and
+// l + 16 share row l and take keys [0,64) / [64,128) of the block.  Per-lane u16 histograms in shared memory ([bin][thread]:
+// conflict-free, no atomics); the two lanes of a row add their columns when they scan from the top bin.
+//   fine window   (default) a sample of the row predicts its threshold; ONE pass with 126 exact bins around the prediction
+//                 (bins of 2^fs keys + one level for the digit inside the bin when the sample spreads wide) - see
+//                 k_select_long_tc
+//   radix levels  64 bins x 6 bits per level over the key's static width, most significant digit first: the fallback when
+//                 the threshold misses the window, and the whole selection under mxp_set_fused_path(0)
+//   emit          keys > T kept, keys == T kept in ascending index until top_k
+// Keys are exact integers (score * 2^(-g-1) + offset, read from the low mantissa bits of one FFMA) of up to 22 bits; rows
+// beyond that window are flagged and left to the CUDA-core kernel (k_predict_topk_long, row-filtered), which handles any
+// exponents.  Pipeline per pass: TMA bulk copy of block j+2 and the MMA of block j+1 run while the threads count block j.
 #pragma once
 #include "mxprune_predict_tc.cuh"
 
@@ -162,14 +161,14 @@ __device__ __forceinline__ void kl_compare_window(const uint32_t (&r)[32], float
 // One CTA = one PAIR of 128-row query tiles of one head (16 warps: warps 0-7 the even tile, 8-15 the odd
 // one; 512 TMEM columns = two score buffers per tile) sharing every K block it streams.
 //
-// Adaptive front end (p.adaptive): a radix level resolves 6 bits of a key whose STATIC width is 11-13
-// bits, while a row's keys really spread over a few hundred values around a threshold that a sample
-// predicts well.  So: (1) score the first 256 keys once (both TMEM buffers), take their min / max and a
-// 128-bin histogram, and read off the sample's top_k/Nk quantile c; (2) ONE pass over all keys with
-// 126 exact bins for the keys c-63 .. c+62 and two clamp bins; if the k-th largest key falls into an
-// exact bin the row has its threshold and tie count, and the emit pass follows: two passes instead of
-// three or four.  A row whose sample spreads too far for the window, or whose threshold lands in a clamp
-// bin, sends its tile pair through the radix levels - same result, the old cost.
+// Adaptive front end (p.adaptive): a radix level resolves 6 bits of a key whose STATIC width is 11-13 bits (up to 22), while a
+// row's keys really spread over a few hundred values around a threshold that a sample predicts well.  So: (1) score the first
+// 256 keys once (128 below 2048 keys) into the TMEM buffers, take their min / max and a 128-bin histogram, and read off the
+// sample's top_k/Nk quantile c; (2) ONE pass over all keys with 126 exact bins for the keys c-63 .. c+62 and two clamp bins;
+// if the k-th largest key falls into an exact bin the row has its threshold and tie count, and the emit pass follows: two
+// passes instead of three or four.  A row whose sample spreads over more than KL_MAX_RANGE values takes bins of 2^fs keys
+// (fs <= 6) and ONE radix level for the fs bits inside the bin (three passes for its pair).  A row whose threshold lands in a
+// clamp bin, or whose sample is wider still, sends its tile pair through the radix levels - same result, the old cost.
 __global__ void __launch_bounds__(KL_T, 1)
 k_select_long_tc(const LongSelParams p) {
     extern __shared__ __align__(1024) unsigned char smem_kl[];
