@@ -81,3 +81,20 @@ def test_linear_specs_reject_other_weight_formats():
         with pytest.raises(ValueError):
             resolve_linear_specs(bad)
         resolve_specs({k: v for k, v in bad.items() if k != "round"} | {"round": "nearest"}) if key == "round" else resolve_specs(bad)
+
+
+def test_exp_fast_argument_error_bound():
+    """csrc/mxprune_device.cuh::exp_fast_nonpos evaluates 2^(fl(x * fl(log2 e))) for x <= 0 in the long-sequence attention kernel.
+    The part of its error that is NOT MUFU.EX2's own (<= 2 ulp) comes from rounding the constant and the product to fp32; this
+    checks the bound the header states - relative error <= 0.9e-7 |x| (+ one half ulp for tiny |x|) - in float64 arithmetic, and
+    that the weight exp(x) of a key shrinks faster than that error grows (the bound's justification)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    x = -np.concatenate([rng.uniform(0, 1, 20000), rng.uniform(1, 20, 20000), rng.uniform(20, 87, 20000)]).astype(np.float32)
+    l2e = np.float32(1.4426950408889634)
+    arg = (x * l2e).astype(np.float32)                          # __fmul_rn
+    approx = np.exp2(arg.astype(np.float64))                    # an exact 2^y on the rounded argument
+    exact = np.exp(x.astype(np.float64))
+    rel = np.abs(approx / exact - 1.0)
+    assert np.all(rel <= 0.9e-7 * np.abs(x.astype(np.float64)) + 6e-8), float(rel.max())
+    assert np.all(rel * exact <= 4e-8)                          # absolute effect on a weight in (0, 1]: never above ~1/3 ulp of 1
