@@ -98,3 +98,90 @@ def test_exp_fast_argument_error_bound():
     rel = np.abs(approx / exact - 1.0)
     assert np.all(rel <= 0.9e-7 * np.abs(x.astype(np.float64)) + 6e-8), float(rel.max())
     assert np.all(rel * exact <= 4e-8)                          # absolute effect on a weight in (0, 1]: never above ~1/3 ulp of 1
+
+
+def _select_model(u, kk, nsamp_keys=256, fbins=128, max_range=1400):
+    """Host model of k_select_long_tc's control flow for ONE row of integer keys u (csrc/mxprune_predict_long_tc.cuh): returns
+    (threshold T, ties wanted at T, passes over the keys).  Sample -> fine window with clamp bins (bins of 2^fs keys + one
+    level for the digit inside the bin) -> radix levels when the threshold lands in a clamp bin."""
+    import numpy as np
+    n = len(u)
+    s = u[:nsamp_keys]
+    umin, umax = int(s.min()), int(s.max())
+    rng = umax - umin
+    csh = int(rng >> 7).bit_length()
+    hist = np.bincount((s - umin) >> csh, minlength=fbins)
+    ks = max(1, (kk * len(s) + n // 2) // n)
+    cum, b = 0, fbins - 1
+    while b > 0 and cum + hist[b] < ks:
+        cum += hist[b]
+        b -= 1
+    fs = 0 if rng <= max_range else int(rng // (max_range // 2)).bit_length()
+    passes = 0
+    if fs <= 6:
+        c_est = umin + (b << csh) + ((1 << csh) >> 1)
+        lo = ((c_est >> fs) - fbins // 2) << fs
+        e = np.clip((u >> fs) - (lo >> fs), 0, fbins - 1)
+        h = np.bincount(e, minlength=fbins)
+        passes += 1
+        cum, b = 0, fbins - 1
+        while b > 0 and cum + h[b] < kk:
+            cum += h[b]
+            b -= 1
+        if 0 < b < fbins - 1:
+            prefix, krem = (lo >> fs) + b, kk - cum
+            if fs:                                              # the digit inside the bin: one level of 2^fs bins
+                d = u[(u >> fs) == prefix] & ((1 << fs) - 1)
+                h2 = np.bincount(d, minlength=1 << fs)
+                passes += 1
+                cum, b2 = 0, (1 << fs) - 1
+                while b2 > 0 and cum + h2[b2] < krem:
+                    cum += h2[b2]
+                    b2 -= 1
+                prefix, krem = (prefix << fs) | b2, krem - cum
+            return prefix, krem, passes + 1
+    # radix levels, 6 bits each, most significant digit first
+    width = max(1, int(u.max()).bit_length())
+    lev = (width + 5) // 6
+    prefix, krem = 0, kk
+    for lv in range(lev):
+        lo = 6 * (lev - 1 - lv)
+        d = (u[(u >> (lo + 6)) == prefix] >> lo) & 63
+        h = np.bincount(d, minlength=64)
+        passes += 1
+        cum, b = 0, 63
+        while b > 0 and cum + h[b] < krem:
+            cum += h[b]
+            b -= 1
+        prefix, krem = (prefix << 6) | b, krem - cum
+    return prefix, krem, passes + 1
+
+
+def test_long_selection_model_is_exact_on_every_path():
+    """Whatever the sample predicts, the row ends with the canonical threshold (the top_k-th largest key) and the number of
+    ties still wanted at it - the emit pass then keeps keys > T and the first `ties` keys == T in ascending index (SURVEY 8a:
+    the canonical tie rule).  Covers: narrow rows (two passes), wide rows (bins of 2^fs keys, three passes), a sample that
+    misleads (radix levels), constant rows, heavy ties."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    seen = set()
+    for trial in range(300):
+        n = int(rng.choice([512, 1024, 4096]))
+        kind = trial % 6
+        sigma = [12, 60, 400, 3000, 60, 60][kind]
+        u = np.rint(rng.normal(0, sigma, n)).astype(np.int64)
+        if kind == 4:
+            u[:256] = np.rint(rng.normal(-8 * sigma, 3, 256))      # the sample sits far below the row
+        if kind == 5:
+            u = (u // 40) * 40                                      # long tie runs
+        if trial % 50 == 49:
+            u[:] = 7                                                # every key equal
+        u = u - u.min() + 1
+        kk = max(1, int(n * float(rng.choice([0.1, 0.25, 0.5]))))
+        T, ties, passes = _select_model(u, kk, nsamp_keys=256 if n >= 2048 else 128)
+        srt = np.sort(u)[::-1]
+        want_T = int(srt[kk - 1])
+        assert T == want_T, (trial, kind, n, kk)
+        assert ties == kk - int((u > want_T).sum()) and 1 <= ties <= int((u == want_T).sum())
+        seen.add(passes)
+    assert {2, 3} <= seen and max(seen) >= 4                        # every path was exercised
